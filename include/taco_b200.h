@@ -1,0 +1,171 @@
+/*
+ * taco_b200.h -- C-ABI of libtaco_b200.so: the B200 (sm_100a) hot path of the Tacotron
+ * mel/linear-spectrogram model (reference: barronalex/Tacotron, models/tacotron.py, models/ops.py).
+ *
+ * The reference has no FFI boundary of its own (it is 100% Python over TensorFlow 1.2); the
+ * boundary a maintainer binds is therefore the set of TF-1.2 library calls its hot path makes.
+ * Each entry point below names the reference call site(s) it replaces.  The Python host
+ * (tacotron_b200/models/{ops,tacotron}.py) reaches these through ctypes -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no C++/torch types.
+ *   - every function returns 0 on success, non-zero on error; taco_last_error() gives the
+ *     message for the calling thread.  Nothing throws across the boundary.
+ *   - all tensors are caller-owned DEVICE pointers (fp32 unless noted), contiguous in their
+ *     last dimension, 16-byte aligned.  The library allocates nothing on the hot path; the
+ *     caller passes workspaces where needed.
+ *   - all launches are asynchronous on the caller's stream (cudaStream_t passed as void*).
+ *   - activations are NWC: x[B][T][C] (TF layout); dense weights are W[in][out]; conv weights
+ *     W[k][Cin][Cout]; GRU weights gates[in+n][2n] (r then u), candidate[in+n][n]  (TF 1.2).
+ */
+#ifndef TACO_B200_H
+#define TACO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TACO_VERSION 100
+
+enum { TACO_ACT_NONE = 0, TACO_ACT_RELU = 1, TACO_ACT_SIGMOID = 2, TACO_ACT_TANH = 3 };
+enum { TACO_IMPL_TC = 0,   /* tcgen05 tensor cores, TF32 multiplies, fp32 accumulate (TMA-fed) */
+       TACO_IMPL_SIMT = 1  /* fp32 FFMA, exact fp32 products                                  */ };
+enum { TACO_EPI_NORMAL = 0,
+       TACO_EPI_HIGHWAY = 1 /* N = 2U: cols [0,U) = H pre-act, [U,2U) = T pre-act; Y[M][U] =
+                               relu(H)*sig(T) + X*(1-sig(T)), X = hx (models/ops.py:32-45)   */ };
+enum { TACO_DEC_INFER = 0, TACO_DEC_TEACHER = 1, TACO_DEC_SCHED = 2 };
+
+const char* taco_last_error(void);
+int         taco_version(void);
+/* Number of SMs of the current device and whether the TMA/tcgen05 path is usable (cc 10.x). */
+int         taco_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * taco_linear_fwd -- one fused contraction + epilogue.  Replaces, depending on the fields:
+ *   tf.layers.dense            models/ops.py:30,32,39  models/tacotron.py:40,42,148
+ *   tf.layers.conv1d('same')   models/ops.py:54-62 (bank: all K filters in ONE call), :80-85
+ *   tf.layers.batch_normalization (inference affine, folded into scale/shift)  ops.py:64,87
+ *   tf.layers.dropout          models/tacotron.py:41,43   (explicit keep mask)
+ *   residual add               models/ops.py:92
+ *   highway gate               models/ops.py:32-45 (TACO_EPI_HIGHWAY)
+ * Y[b,t,n] = epi( sum_{j<taps} sum_{c<C} X[b, t+tap0+j, c] * W[j,c,n] ),  zero outside [0,T).
+ * epi(v) = (act(v + bias[n]) * scale[n] + shift[n]) * keep[b,t,n]*keep_scale + residual[b,t,n]
+ * Bank mode (bank_K > 0): N = bank_K*bank_cout; output columns [(k-1)*cout, k*cout) come from
+ * filter k (k taps, tap0 = -(k-1)/2).  W then points at the K filters stored back to back
+ * (W1 [1][C][cout], W2 [2][C][cout], ...), Wp at the packed form made by taco_pack_weight.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct taco_linear_desc {
+    const float*   X;        /* [B][T][ldx] activations, C valid channels                    */
+    int64_t        ldx;      /* floats between consecutive (b,t) rows                        */
+    int32_t        B, T, C;
+    int32_t        taps;     /* 1 = dense                                                    */
+    int32_t        tap0;     /* -(taps-1)/2 for TF 'same'                                    */
+    int32_t        N;        /* output channels (total)                                      */
+    int32_t        bank_K;   /* 0, or number of bank filters                                 */
+    int32_t        bank_cout;
+    const float*   W;        /* TF layout [taps*C][N] row-major (SIMT path)                  */
+    const float*   Wp;       /* packed K-major [N][ldwp] TF32-rounded (tensor-core path)     */
+    int64_t        ldwp;     /* floats per packed row = max_taps * round_up(C,32)            */
+    float*         Y;        /* [B*T][ldy]                                                   */
+    int64_t        ldy;
+    const float*   bias;     /* [N] or NULL                                                  */
+    int32_t        act;      /* TACO_ACT_*                                                   */
+    const float*   scale;    /* [N] or NULL   (BN: gamma/sqrt(var+1e-3))                     */
+    const float*   shift;    /* [N] or NULL   (BN: beta - mean*scale)                        */
+    const uint8_t* keep;     /* [B*T][N] dropout keep mask or NULL                           */
+    float          keep_scale;
+    const float*   residual; /* [B*T][ldr] or NULL                                           */
+    int64_t        ldr;
+    int32_t        epilogue; /* TACO_EPI_*                                                   */
+    const float*   hx;       /* highway carry input X [B*T][ldhx]                            */
+    int64_t        ldhx;
+    int32_t        pool;     /* 1: fuse max_pooling1d(2,1,'same') over t after the affine    */
+                             /*    (models/ops.py:66-71); tensor-core path only              */
+    int32_t        impl;     /* TACO_IMPL_*                                                  */
+} taco_linear_desc;
+
+int taco_linear_fwd(const taco_linear_desc* d, void* stream);
+
+/* Pack one TF-layout weight W[taps][C][N] into the tensor-core operand layout: row n of dst
+ * (dst + (n)*ld_dst) holds, for tap j and channel c, W[j][c][n] at column j*round_up(C,32)+c,
+ * rounded to TF32 (round-to-nearest); padding channels are zero.                             */
+int taco_pack_weight(const float* W, int taps, int C, int N, float* dst, int64_t ld_dst, void* stream);
+
+/* tf.layers.max_pooling1d(pool 2, stride 1, 'same') over t  (models/ops.py:66-71)            */
+int taco_maxpool_fwd(const float* X, float* Y, int B, int T, int C, void* stream);
+
+/* Embedding-style row gather with optional dropout keep mask:
+ * Y[i][:] = table[ids[i]][:] * keep[i][:]*keep_scale   (tf.nn.embedding_lookup, tacotron.py:114) */
+int taco_gather_rows(const float* table, const int32_t* ids, int rows, int width, int vocab,
+                     const uint8_t* keep, float keep_scale, float* Y, void* stream);
+
+/* values[b][j][:] = memory[b][j][:] if j < length[b] else 0   (BahdanauAttention _prepare_memory,
+ * tacotron.py:48-52)                                                                          */
+int taco_mask_rows(const float* X, const int32_t* length, float* Y, int B, int T, int C, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * taco_bigru_fwd -- tf.nn.bidirectional_dynamic_rnn(GRUCell(128), GRUCell(128)) without
+ * sequence_length (models/ops.py:118-128).  The input-side products are hoisted out of the
+ * loop by the caller (one taco_linear_fwd):
+ *   xp[b][t][0:256]   = x.Wg_fw[0:128,:] + bg_fw     xp[b][t][256:384] = x.Wc_fw[0:128,:] + bc_fw
+ *   xp[b][t][384:640] = x.Wg_bw[0:128,:] + bg_bw     xp[b][t][640:768] = x.Wc_bw[0:128,:] + bc_bw
+ * wh_fw / wh_bw point at the h-side rows: Wg[128:256][256] followed by Wc[128:256][128] are
+ * passed separately.  out[b][t][0:128] = fw state, [128:256] = bw state.
+ * One persistent CTA per (utterance, direction), recurrent weights register-resident.
+ * ------------------------------------------------------------------------------------------ */
+int taco_bigru_fwd(const float* xp, const float* Wg_h_fw, const float* Wc_h_fw,
+                   const float* Wg_h_bw, const float* Wc_h_bw,
+                   float* out, int B, int T, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Decoder: tacotron.py:46-105 create_decoder + :136-138 dynamic_decode, i.e. per step
+ *   pre_net(last frame) ++ attention -> InputProjection -> 3x GRUCell(256) -> Residual ->
+ *   OutputProjection(80r) -> BahdanauAttention(query = cell output) -> attention layer.
+ * The whole T-step loop runs in ONE persistent cooperative kernel.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct taco_decoder_weights {   /* all TF layout, device pointers */
+    const float *pre_W1, *pre_b1, *pre_W2, *pre_b2;      /* [80][256],[256],[256][128],[128]   */
+    const float *in_W, *in_b;                            /* [384][256],[256]                   */
+    const float *gru_Wg[3], *gru_bg[3], *gru_Wc[3], *gru_bc[3]; /* [512][512],[512],[512][256],[256] */
+    const float *out_W, *out_b;                          /* [256][80r],[80r]                   */
+    const float *att_Wq, *att_v, *att_Wa;                /* [80r][256],[256],[80r+256][256]    */
+} taco_decoder_weights;
+
+/* bytes of the packed-weight buffer / of the workspace taco_decoder_fwd needs */
+size_t taco_decoder_packed_bytes(int r);
+size_t taco_decoder_workspace_bytes(int B, int Tx, int T, int r);
+/* re-lay the weights per CTA column slice (call once per weight update) */
+int taco_decoder_pack(const taco_decoder_weights* w, int r, float* packed, void* stream);
+
+typedef struct taco_decoder_args {
+    const taco_decoder_weights* weights; /* HOST pointer; biases and attention_v are read from here */
+    const float*   packed;       /* from taco_decoder_pack                                    */
+    const float*   keys;         /* [B][Tx][256]  values . W_mem                              */
+    const float*   values;       /* [B][Tx][256]  length-masked memory                        */
+    const int32_t* text_length;  /* [B]                                                       */
+    const float*   mel;          /* [B][T][80r] teacher inputs (TEACHER / SCHED) or NULL      */
+    const uint8_t* sample_mask;  /* [T][B] 1 = feed own output (SCHED) or NULL                */
+    const uint8_t* keep1;        /* [T][B][256] pre-net dropout keep masks or NULL            */
+    const uint8_t* keep2;        /* [T][B][128]                                               */
+    float          keep_scale;   /* 1/(1-rate)                                                */
+    int32_t        mode;         /* TACO_DEC_*                                                */
+    int32_t        B, Tx, T, r;
+    float*         y;            /* [B][T][80r]   seq2seq_output                              */
+    float*         align;        /* [B][T][Tx]    alignment history                           */
+    void*          workspace;    /* taco_decoder_workspace_bytes                              */
+    uint64_t*      step_ns;      /* [T] device buffer: %globaltimer at the start of each step, or NULL */
+} taco_decoder_args;
+
+int taco_decoder_fwd(const taco_decoder_args* a, void* stream);
+
+/* tacotron.py:156-160: partial[0] = sum|a-b| over n elements (deterministic two-stage).       */
+int taco_l1_loss_fwd(const float* a, const float* b, int64_t n, float* partial_ws, float* out, void* stream);
+int taco_l1_partial_count(void);   /* floats partial_ws must hold */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TACO_B200_H */

@@ -1,0 +1,366 @@
+// gemm_tc.cu -- tcgen05 / TMA implementation of taco_linear_fwd (TACO_IMPL_TC), sm_100a.
+//
+// One kernel serves every feed-forward contraction of the model (conv bank as ONE grouped
+// implicit GEMM, conv projections, highway, GRU input products, attention memory layer,
+// post dense):  Y[(b,t), n] = epi( sum_j sum_c X[b, t+tap0+j, c] * W[j,c,n] ).
+//
+//  * A operand: activations stay in their NWC layout in HBM; a 3-D TMA tensor map (C, T, B)
+//    with a {32 ch, 128 rows, 1} box loads the tile for tap j at time offset t0+tap0+j.
+//    TMA out-of-bounds zero fill IS the TF 'same' padding (rows < 0 or >= T, per utterance),
+//    and also pads C up to a multiple of 32 (C=80 in the post-net).
+//  * B operand: weights pre-packed K-major [N][taps*Cpad], TF32-rounded (taco_pack_weight).
+//  * both land in shared memory in the 128B-swizzled K-major canonical UMMA layout; one
+//    elected thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8), accumulators in TMEM.
+//  * bank mode: CTA n-tile = filter k (BN == bank_cout), K loop runs over that filter's k taps
+//    only -- no zero-padded taps are multiplied.
+//  * warp roles: warp0 TMA producer, warp1 MMA issuer + TMEM owner, warps2-5 epilogue
+//    (tcgen05.ld 32x32b -> smem transpose -> fused epilogue -> coalesced 128B row stores).
+//  * 96 KB of pipeline smem per CTA -> 2 CTAs/SM, so one CTA's epilogue overlaps the other's
+//    main loop without a persistent scheduler.
+#include <cuda.h>
+#include "epilogue.cuh"
+
+namespace {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;                       // floats: one 128-byte swizzle row
+constexpr int A_STAGE_BYTES = TC_BM * TC_BK * 4;   // 16 KB
+
+struct TcArgs {
+    int B, T;
+    int cchunks;       // round_up(C,32)/32
+    int Cpad;
+    int taps, tap0;    // dense / plain conv
+    int bank;          // 1: taps = n_tile+1, tap0 = -(taps-1)/2
+    int N;             // valid output columns (highway: 2U)
+    int tiles_per_seq; // M tiles per utterance
+    int tile_stride;   // 128, or 127 when pooling
+    int pool;
+    EpiParams e;
+};
+
+template <int BN, int STAGES>
+struct SmemLayout {
+    static constexpr int B_STAGE_BYTES = BN * TC_BK * 4;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
+    static constexpr int BAR_OFFSET = PIPE_BYTES;
+    static constexpr int TOTAL = PIPE_BYTES + 128 + 1024;   // barriers + alignment slack
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    // K-major, SWIZZLE_128B canonical layout: 8-row groups 1024 B apart (SBO), LBO unused.
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address, 14 bits
+    d |= (uint64_t)1 << 16;                           // leading byte offset (ignored for SW128 K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                 // stride byte offset
+    d |= (uint64_t)1 << 46;                           // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                           // SWIZZLE_128B
+    return d;
+}
+
+template <int BN>
+__device__ __forceinline__ uint32_t make_idesc() {
+    uint32_t d = 0;
+    d |= 1u << 4;                 // accumulator F32
+    d |= 2u << 7;                 // A = TF32
+    d |= 2u << 10;                // B = TF32
+    d |= (uint32_t)(BN >> 3) << 17;
+    d |= (uint32_t)(TC_BM >> 4) << 24;
+    return d;
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// MODE 0: normal epilogue (optional fused max-pool), MODE 1: highway (BN = 2U = 256)
+template <int BN, int STAGES, int MODE>
+__global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                      const __grid_constant__ CUtensorMap tmB, TcArgs a) {
+    using L = SmemLayout<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full = empty_bar + STAGES;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // tile coordinates
+    const int n_tile = blockIdx.x;
+    const int m_tile = blockIdx.y;
+    const int b = m_tile / a.tiles_per_seq;
+    const int t0 = (m_tile % a.tiles_per_seq) * a.tile_stride;
+    const int n0 = n_tile * BN;
+    int taps = a.taps, tap0 = a.tap0;
+    if (a.bank) { taps = n_tile + 1; tap0 = -((taps - 1) / 2); }
+    const int n_iters = taps * a.cchunks;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full, 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        constexpr uint32_t cols = (BN <= 32) ? 32 : (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(cols)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            for (int it = 0; it < n_iters; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* As = smem + s * L::STAGE_BYTES;
+                uint8_t* Bs = As + A_STAGE_BYTES;
+                const int j = it / a.cchunks;
+                const int c0 = (it - j * a.cchunks) * TC_BK;
+                mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
+                tma_load_3d(As, &tmA, &full_bar[s], c0, t0 + tap0 + j, b);
+                tma_load_2d(Bs, &tmB, &full_bar[s], j * a.Cpad + c0, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc<BN>();
+            for (int it = 0; it < n_iters; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+                const uint64_t adesc = make_smem_desc(a_addr);
+                const uint64_t bdesc = make_smem_desc(a_addr + A_STAGE_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 8; ++k) {
+                    // advance 8 tf32 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
+                    tc_mma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                (it > 0 || k > 0) ? 1u : 0u);
+                }
+                tc_commit(&empty_bar[s]);      // frees the stage once these MMAs have read it
+            }
+            tc_commit(tmem_full);              // accumulator complete
+        }
+    } else {
+        // ================= epilogue warps (2..5) =================
+        const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        // scratch aliases the (now idle) pipeline buffers: [4 quarters][MODE?2:1][32][33] floats
+        float* scratch_base = reinterpret_cast<float*>(smem);
+        constexpr int SCR = 32 * 33;
+        float* my_scr = scratch_base + q * (MODE == 1 ? 2 : 1) * SCR;
+        const int64_t seq_row0 = (int64_t)b * a.T;
+        constexpr int NCHUNK = (MODE == 1) ? (BN / 2) / 32 : BN / 32;
+
+        for (int ch = 0; ch < NCHUNK; ++ch) {
+            uint32_t v[32];
+            tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+            tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) my_scr[lane * 33 + j] = __uint_as_float(v[j]);
+            if (MODE == 1) {
+                tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN / 2 + ch * 32), v);
+                tc_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) my_scr[SCR + lane * 33 + j] = __uint_as_float(v[j]);
+            }
+            if (a.pool) named_bar_sync(1, 128); else __syncwarp();
+
+            const int col = n0 + ch * 32 + lane;     // MODE 1: n0 == 0, col in [0,U)
+            if (MODE == 1) {
+                const int U = BN / 2;
+                for (int rr = 0; rr < 32; ++rr) {
+                    const int t = t0 + q * 32 + rr;
+                    if (t >= a.T) break;
+                    const int64_t row = seq_row0 + t;
+                    float o = epi_highway(a.e, row, col, U, my_scr[rr * 33 + lane], my_scr[SCR + rr * 33 + lane]);
+                    a.e.Y[row * a.e.ldy + col] = o;
+                }
+            } else if (!a.pool) {
+                if (col < a.N) {
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const int t = t0 + q * 32 + rr;
+                        if (t >= a.T) break;
+                        const int64_t row = seq_row0 + t;
+                        a.e.Y[row * a.e.ldy + col] = epi_value(a.e, row, col, my_scr[rr * 33 + lane]);
+                    }
+                }
+            } else {
+                // fused max_pooling1d(2,1,'same') over t (models/ops.py:66-71): out[t] = max(e[t], e[t+1]),
+                // out[T-1] = e[T-1].  Tiles advance by 127 rows so row r+1 is always in this tile.
+                if (col < a.N) {
+                    const float* nxt_scr = scratch_base + ((q + 1) & 3) * SCR;   // first row of the next quarter
+                    float cur = 0.f;
+                    {
+                        const int t = t0 + q * 32;
+                        if (t < a.T) cur = epi_value(a.e, seq_row0 + t, col, my_scr[lane]);
+                    }
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const int r = q * 32 + rr;
+                        const int t = t0 + r;
+                        if (t >= a.T) break;
+                        float nxt = 0.f;
+                        const bool has_next = (t + 1 < a.T) && (r + 1 < TC_BM);
+                        if (has_next) {
+                            const float raw = (rr < 31) ? my_scr[(rr + 1) * 33 + lane] : nxt_scr[lane];
+                            nxt = epi_value(a.e, seq_row0 + t + 1, col, raw);
+                        }
+                        // rows 0..126 of the tile are produced here; row 127 only if it is the sequence end
+                        const bool emit = (r < TC_BM - 1) || (t == a.T - 1);
+                        if (emit) {
+                            const float o = (t + 1 < a.T) ? fmaxf(cur, nxt) : cur;
+                            a.e.Y[(seq_row0 + t) * a.e.ldy + col] = o;
+                        }
+                        cur = nxt;
+                    }
+                }
+            }
+            if (a.pool) named_bar_sync(1, 128); else __syncwarp();
+        }
+        tc_fence_before();
+    }
+
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        constexpr uint32_t cols = (BN <= 32) ? 32 : (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(cols) : "memory");
+    }
+}
+
+// ---- weight packing: TF [taps][C][N] -> K-major [N][taps*Cpad], TF32 round-to-nearest ----
+__global__ void pack_weight_kernel(const float* __restrict__ W, int taps, int C, int N, int Cpad,
+                                   float* __restrict__ dst, int64_t ld) {
+    // one thread per (n, j, cpad-index); reads are strided by N but this runs once per weight update
+    int64_t total = (int64_t)N * taps * Cpad;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % Cpad);
+        int64_t r = i / Cpad;
+        int j = (int)(r % taps);
+        int n = (int)(r / taps);
+        float v = 0.0f;
+        if (c < C) {
+            v = W[((int64_t)j * C + c) * N + n];
+            uint32_t u;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+            v = __uint_as_float(u);
+        }
+        dst[(int64_t)n * ld + (int64_t)j * Cpad + c] = v;
+    }
+}
+
+// ---- driver entry point for cuTensorMapEncodeTiled (no link-time libcuda dependency) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !p) return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+template <int BN, int STAGES, int MODE>
+int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, dim3 grid, cudaStream_t st) {
+    using L = SmemLayout<BN, STAGES>;
+    static bool configured = false;
+    if (!configured) {
+        TACO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        configured = true;
+    }
+    gemm_tc_kernel<BN, STAGES, MODE><<<grid, 192, L::TOTAL, st>>>(tmA, tmB, a);
+    TACO_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // namespace
+
+int taco_pack_weight_impl(const float* W, int taps, int C, int N, float* dst, int64_t ld_dst, cudaStream_t st) {
+    const int Cpad = (C + 31) / 32 * 32;
+    TACO_CHECK(ld_dst >= (int64_t)taps * Cpad, "taco_pack_weight: ld_dst %lld < taps*Cpad %d", (long long)ld_dst, taps * Cpad);
+    int64_t total = (int64_t)N * taps * Cpad;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    pack_weight_kernel<<<blocks, 256, 0, st>>>(W, taps, C, N, Cpad, dst, ld_dst);
+    TACO_LAUNCH_CHECK();
+    return 0;
+}
+
+int taco_linear_tc(const taco_linear_desc* d, cudaStream_t st) {
+    TACO_CHECK(d->Wp != nullptr, "taco_linear_fwd(TC): Wp (packed weights) is NULL");
+    TACO_CHECK(taco_aligned16(d->X) && taco_aligned16(d->Wp), "taco_linear_fwd(TC): X / Wp must be 16-byte aligned");
+    TACO_CHECK((d->ldx % 4) == 0 && (d->ldwp % 4) == 0, "taco_linear_fwd(TC): ldx and ldwp must be multiples of 4 floats (TMA 16B strides)");
+    EncodeTiledFn enc = get_encode_fn();
+    TACO_CHECK(enc != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
+    const int64_t M = (int64_t)d->B * d->T;
+    if (M == 0 || d->N == 0) return 0;
+
+    const bool highway = d->epilogue == TACO_EPI_HIGHWAY;
+    const int BN = highway ? 256 : 128;
+    if (highway) TACO_CHECK(d->N == 256 && d->taps == 1 && d->bank_K == 0 && d->hx, "highway (TC): needs N == 256 (U = 128), dense, hx");
+    if (d->bank_K > 0) TACO_CHECK(d->bank_cout == 128 && d->N == d->bank_K * 128, "bank (TC): bank_cout must be 128");
+    if (d->pool) TACO_CHECK(!highway, "pool + highway not supported");
+
+    TcArgs a;
+    a.B = d->B; a.T = d->T;
+    a.Cpad = (d->C + 31) / 32 * 32;
+    a.cchunks = a.Cpad / 32;
+    a.taps = d->taps; a.tap0 = d->tap0; a.bank = d->bank_K > 0 ? 1 : 0;
+    a.N = d->N;
+    a.pool = d->pool ? 1 : 0;
+    a.tile_stride = a.pool ? (TC_BM - 1) : TC_BM;
+    a.tiles_per_seq = a.pool ? ((d->T - 1 + a.tile_stride - 1) / a.tile_stride) : ((d->T + TC_BM - 1) / TC_BM);
+    if (a.tiles_per_seq < 1) a.tiles_per_seq = 1;
+    a.e.Y = d->Y; a.e.ldy = d->ldy; a.e.bias = d->bias; a.e.scale = d->scale; a.e.shift = d->shift;
+    a.e.keep = d->keep; a.e.keep_scale = d->keep_scale; a.e.residual = d->residual; a.e.ldr = d->ldr;
+    a.e.hx = d->hx; a.e.ldhx = d->ldhx; a.e.act = d->act; a.e.N = highway ? d->N / 2 : d->N;
+
+    const int max_taps = d->bank_K > 0 ? d->bank_K : d->taps;
+    TACO_CHECK(d->ldwp >= (int64_t)max_taps * a.Cpad, "taco_linear_fwd(TC): ldwp too small for taps*Cpad");
+
+    CUtensorMap tmA, tmB;
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)d->C, (cuuint64_t)d->T, (cuuint64_t)d->B};
+        cuuint64_t strides[2] = {(cuuint64_t)d->ldx * 4, (cuuint64_t)d->T * (cuuint64_t)d->ldx * 4};
+        cuuint32_t box[3] = {TC_BK, TC_BM, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(d->X), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        TACO_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A) failed: %d (C=%d T=%d B=%d ldx=%lld)", (int)r, d->C, d->T, d->B, (long long)d->ldx);
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)d->ldwp, (cuuint64_t)d->N};
+        cuuint64_t strides[1] = {(cuuint64_t)d->ldwp * 4};
+        cuuint32_t box[2] = {TC_BK, (cuuint32_t)BN};
+        cuuint32_t es[2] = {1, 1};
+        CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(d->Wp), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        TACO_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed: %d (N=%d ldwp=%lld)", (int)r, d->N, (long long)d->ldwp);
+    }
+    dim3 grid((d->N + BN - 1) / BN, (unsigned)(a.tiles_per_seq * d->B));
+    if (highway) return launch_tc<256, 2, 1>(tmA, tmB, a, grid, st);
+    return launch_tc<128, 3, 0>(tmA, tmB, a, grid, st);
+}

@@ -1,0 +1,180 @@
+"""Host-side mirror of the reference's ``models/tacotron.py`` (Config, Tacotron) over the sm_100a
+C-ABI.  Eager equivalent of the TF-1.2 graph: ``Tacotron(config, inputs, train)`` owns the
+variables (one flat device buffer, TF layouts) and ``inference`` / ``add_loss_op`` run the hand
+written kernels; the attribute names the reference drivers fetch (``seq2seq_output``, ``output``,
+``alignments``, ``loss``) are kept (models/tacotron.py:187-195, train.py:60-72, test.py:52-56).
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import _lib as L
+from ..params import ParamStore, model_shapes
+from . import ops
+
+
+class Config(object):
+    """models/tacotron.py:12-33, with the values the reference derives from module globals or
+    injects at run time (r, vocab_size, max_decode_iter: train.py:20-22, tacotron.py:13) explicit."""
+    max_decode_iter = 108000 // (2 * 300)      # audio.maximum_audio_length // (audio.r * audio.hop_length)
+    attention_units = 256
+    decoder_units = 256
+    mel_features = 80
+    embed_dim = 256
+    fft_size = 1025
+
+    char_dropout_prob = 0.5
+    audio_dropout_prob = 0.5
+
+    num_speakers = 1
+    speaker_embed_dim = 16
+
+    scheduled_sample = 0.5
+
+    cap_grads = 5
+
+    init_lr = 0.0005
+    annealing_rate = 1
+
+    batch_size = 32
+
+    # injected by the drivers in the reference
+    r = 2
+    vocab_size = 64
+
+    # B200 path: 'tf32' = tcgen05 tensor cores (TF32 multiplies, fp32 accumulate) for the feed
+    # forward contractions; 'fp32' = exact fp32 FFMA everywhere.  Recurrent kernels are fp32 in both.
+    precision = "tf32"
+
+    def __init__(self, **kw):
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
+class Tacotron(object):
+    def __init__(self, config, inputs=None, train=True, device="cuda", seed=1):
+        """Reference signature ``Tacotron(config, inputs, train)`` (tacotron.py:187).  `inputs` may be
+        None (build only) or the input dict of tensors; when given the forward (and loss, if train)
+        is evaluated immediately so the result attributes exist as they do after a sess.run."""
+        if config.num_speakers != 1:
+            raise NotImplementedError("multi-speaker (tacotron.py:116-124) is out of scope")
+        if not torch.cuda.is_available():
+            raise RuntimeError("tacotron_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        L.lib()                                   # fail loudly if the extension is missing
+        self.config = config
+        self.train = train
+        self.device = torch.device(device)
+        self.store = ParamStore(model_shapes(config), self.device)
+        self.store.init_tf_default(seed)
+        self.runtime = ops.runtime(self.store, config.precision)
+        self.lr = config.init_lr
+        self.global_step = 0
+        self.seq2seq_output = self.output = self.alignments = self.loss = None
+        self.step_ns = None
+        if inputs is not None:
+            self(inputs)
+
+    # -- parameters ---------------------------------------------------------------------------
+    def load_params(self, params):
+        self.store.load(params)
+
+    def state_dict(self):
+        return self.store.state_dict()
+
+    # -- Tacotron.pre_net (tacotron.py:38-44) ---------------------------------------------------
+    def pre_net(self, inputs, units=[256, 128], dropout=0.5, train=True, masks=None, scope=None, ids=None):
+        return ops.pre_net(inputs, units=tuple(units), dropout=dropout, train=train, masks=masks, scope=scope, ids=ids)
+
+    # -- create_decoder + dynamic_decode (tacotron.py:46-105, 136-138) ---------------------------
+    def create_decoder(self, encoded, inputs, speaker_embed=None, train=True, T=None, dec_drop_masks=None,
+                       sample_mask=None):
+        """Returns a zero-argument callable that runs the whole decode (the BasicDecoder +
+        dynamic_decode pair of the reference) as one persistent kernel."""
+        cfg = self.config
+        if train:
+            mel = inputs["mel"]
+            T = mel.shape[1] if T is None else T
+            if cfg.scheduled_sample:                          # ScheduledOutputTrainingHelper (tacotron.py:83-85)
+                mode = L.DEC_SCHED
+                if sample_mask is None:
+                    sample_mask = (torch.rand(T, mel.shape[0], device=mel.device) < cfg.scheduled_sample).to(torch.uint8)
+            else:                                             # TrainingHelper (tacotron.py:87)
+                mode = L.DEC_TEACHER
+            if dec_drop_masks is None:
+                B = mel.shape[0]
+                dec_drop_masks = ((torch.rand(T, B, 256, device=mel.device) >= cfg.audio_dropout_prob).to(torch.uint8),
+                                  (torch.rand(T, B, 128, device=mel.device) >= cfg.audio_dropout_prob).to(torch.uint8))
+        else:
+            helper = ops.InferenceHelper(inputs["text"].shape[0], cfg.mel_features * cfg.r)   # tacotron.py:89-92
+            mode = helper.decoder_mode
+            mel = None
+            T = cfg.max_decode_iter if T is None else T
+            dec_drop_masks = None
+            sample_mask = None
+        sc = ops.Scope(self.store, "dec")
+        step_ns = self.step_ns
+
+        def run():
+            return ops.attention_decoder(encoded, inputs["text_length"], cfg.r, T, mode=mode, mel=mel,
+                                         sample_mask=sample_mask, drop_masks=dec_drop_masks,
+                                         dropout=cfg.audio_dropout_prob, scope=sc, step_ns=step_ns)
+        return run
+
+    # -- inference (tacotron.py:107-154) --------------------------------------------------------
+    def inference(self, inputs, train=True, T=None, enc_drop_masks=None, dec_drop_masks=None, sample_mask=None,
+                  trace=None):
+        """inputs: dict of CUDA tensors: 'text' int32 [B,Tx], 'text_length' int32 [B]; train adds
+        'mel' fp32 [B,T,80r] (and 'stft' for the loss).  Returns (seq2seq_output, output)."""
+        cfg = self.config
+        text = inputs["text"]
+        assert text.dtype == torch.int32 and text.is_cuda and text.is_contiguous()
+        B, Tx = text.shape
+        if Tx % 4 != 0:
+            raise ValueError(f"text width {Tx} must be a multiple of 4 (pad like the reference does: data_input.py:97-99)")
+        store = self.store
+        # embedding lookup fused with the first pre-net layer (tacotron.py:111-114, :128)
+        with ops.variable_scope(store, "enc"):
+            pre_out = self.pre_net(store["embedding"], dropout=cfg.char_dropout_prob, train=train, masks=enc_drop_masks,
+                                   ids=text)
+            encoded = ops.CBHG(pre_out, None, K=16, c=[128, 128, 128], gru_units=128, trace=trace)      # :131
+        # attention decoder (:135-138)
+        dec = self.create_decoder(encoded, inputs, None, train, T=T, dec_drop_masks=dec_drop_masks, sample_mask=sample_mask)
+        seq2seq_output, self.alignments = dec()
+        # post-processing CBHG + linear-spectrogram dense (:144-151); the reshapes are views
+        with ops.variable_scope(store, "post"):
+            post_input = seq2seq_output.view(B, -1, cfg.mel_features)
+            post = ops.CBHG(post_input, None, K=8, c=[128, 256, 80], gru_units=128, trace=trace)
+            W, b = store["post/dense/W"], store["post/dense/b"]
+            rt = self.runtime
+            dense = ops.linear(rt, post, W, ops.packed_weight(rt, "post/dense/W", W, 1, 256, cfg.fft_size), cfg.fft_size,
+                               bias=b, tag="post/dense/out")
+        output = dense.view(B, -1, cfg.fft_size * cfg.r)
+        if trace is not None:
+            trace["enc/prenet_out"] = pre_out
+            trace["encoded"] = encoded
+        return seq2seq_output, output
+
+    # -- add_loss_op (tacotron.py:156-165) -------------------------------------------------------
+    def add_loss_op(self, seq2seq_output, output, mel, linear):
+        lib = L.lib()
+        rt = self.runtime
+        part = rt.buf("loss/partial", (lib.taco_l1_partial_count(),))
+        res = rt.buf("loss/out", (2,))
+        L.check(lib.taco_l1_loss_fwd(L.ptr(seq2seq_output), L.ptr(mel), seq2seq_output.numel(), L.ptr(part),
+                                     L.ptr(res[0:1]), L.current_stream()), "taco_l1_loss_fwd")
+        part2 = rt.buf("loss/partial2", (lib.taco_l1_partial_count(),))
+        L.check(lib.taco_l1_loss_fwd(L.ptr(output), L.ptr(linear), output.numel(), L.ptr(part2), L.ptr(res[1:2]),
+                                     L.current_stream()), "taco_l1_loss_fwd")
+        self.seq2seq_loss = res[0]
+        self.output_loss = res[1]
+        return res[0] + res[1]
+
+    def add_train_op(self, loss):
+        raise NotImplementedError("backward / Adam (tacotron.py:167-185) is not part of this round's path")
+
+    # -- the eager stand-in for sess.run([...]) ---------------------------------------------------
+    def __call__(self, inputs, **kw):
+        self.seq2seq_output, self.output = self.inference(inputs, self.train, **kw)
+        if self.train and "stft" in inputs:
+            self.loss = self.add_loss_op(self.seq2seq_output, self.output, inputs["mel"], inputs["stft"])
+        return self.seq2seq_output, self.output

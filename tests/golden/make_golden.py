@@ -1,0 +1,79 @@
+"""Generates the committed golden fixtures.  Run IN THE BUILD CONTAINER only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+1. reshape_frames.npz -- outputs of the REFERENCE's own audio.reshape_frames (audio.py:23-35),
+   obtained by importing /root/reference/audio.py with its unavailable top-level imports
+   (librosa, tensorflow, tqdm) stubbed out; the function itself is pure numpy and runs unmodified.
+   This is the only function on/around the hot path the reference's code base can execute here.
+2. oracle_small_r{2,5}.npz -- end-to-end outputs of the CPU oracle (oracle/tacotron_oracle.py) on
+   seeded weights/inputs at B=2, Tx=12, T=6.  These pin the oracle against regressions and give the
+   GPU tests a fixture that does not depend on re-running the oracle; they are NOT reference
+   outputs (TensorFlow 1.2 cannot run here -- parity unpinned, see oracle/tf12.py).
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+
+def reference_reshape_frames():
+    for name in ("librosa", "tensorflow", "tqdm"):
+        m = types.ModuleType(name)
+        if name == "tqdm":
+            m.tqdm = lambda x, **k: x
+        sys.modules[name] = m
+    sys.path.insert(0, "/root/reference")
+    import audio as ref_audio                      # the reference module, unmodified
+    out = {}
+    rng = np.random.RandomState(0)
+    for r in (2, 5):
+        ref_audio.r = r                            # module global the function reads (audio.py:17)
+        x = rng.randn(7, 361).astype(np.float32)   # [F, n_frames]; 361 = 108000/300 + 1 as in the reference
+        fwd = ref_audio.reshape_frames(x)
+        inv = ref_audio.reshape_frames(fwd, forward=False)
+        out[f"x_r{r}"] = x
+        out[f"fwd_r{r}"] = fwd
+        out[f"inv_r{r}"] = inv
+    # the reference's own self-test (audio.py:106-115), r = 2
+    ref_audio.r = 2
+    test = np.repeat(np.arange(40)[:, None] + 1, 7, axis=1)
+    o = ref_audio.reshape_frames(test.T)
+    inv = ref_audio.reshape_frames(o, forward=False)
+    assert np.array_equal(test, inv)
+    out["selftest_in"] = test
+    out["selftest_fwd"] = o
+    np.savez_compressed(os.path.join(HERE, "reshape_frames.npz"), **out)
+    print("reshape_frames.npz", {k: v.shape for k, v in out.items()})
+
+
+def oracle_small():
+    from oracle import tacotron_oracle as O
+    for r in (2, 5):
+        cfg = O.OracleConfig(r=r, max_decode_iter=6, vocab_size=20)
+        p = O.init_params(cfg, seed=1, trained_like=True)
+        inp = O.synthetic_inputs(cfg, 2, 12, 6, seed=0, ragged=True)
+        enc_m, dec_m = O.dropout_masks(cfg, 2, 12, 6, seed=2)
+        sm = O.sched_mask(cfg, 2, 6, seed=3)
+        y_i, o_i, a_i = O.inference(p, inp, cfg, train=False)
+        y_t, o_t, a_t = O.inference(p, inp, cfg, train=True, enc_drop_masks=enc_m, dec_drop_masks=dec_m)
+        y_s, o_s, a_s = O.inference(p, inp, cfg, train=True, enc_drop_masks=enc_m, dec_drop_masks=dec_m, sample_mask=sm)
+        loss, ls, lo = O.loss(y_t, o_t, inp["mel"], inp["stft"])
+        np.savez_compressed(
+            os.path.join(HERE, f"oracle_small_r{r}.npz"),
+            y_infer=y_i.numpy(), out_infer=o_i.numpy(), align_infer=a_i.numpy(),
+            y_teacher=y_t.numpy(), out_teacher=o_t.numpy(), align_teacher=a_t.numpy(),
+            y_sched=y_s.numpy(), out_sched=o_s.numpy(), align_sched=a_s.numpy(),
+            loss_teacher=np.array([float(loss), float(ls), float(lo)]))
+        print(f"oracle_small_r{r}.npz written")
+
+
+if __name__ == "__main__":
+    reference_reshape_frames()
+    oracle_small()

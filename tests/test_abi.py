@@ -1,0 +1,69 @@
+"""The C-ABI library loads and exports every symbol include/taco_b200.h declares (no compute, no GPU)."""
+import ctypes
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "taco_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(taco_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from tacotron_b200 import _lib
+    lib = _lib.lib()
+    names = _declared()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in taco_b200.h but not exported"
+    assert sorted(_lib.EXPORTS) == names
+
+
+def test_version_and_error_string():
+    from tacotron_b200 import _lib
+    lib = _lib.lib()
+    assert lib.taco_version() == 100
+    assert isinstance(lib.taco_last_error(), bytes)
+
+
+def test_struct_sizes_match_header_layout():
+    """ctypes mirrors must have the C layout: compile a tiny probe with gcc against the header."""
+    import subprocess, tempfile
+    from tacotron_b200 import _lib
+    probe = r'''
+#include <stdio.h>
+#include "taco_b200.h"
+int main(void){ printf("%zu %zu %zu\n", sizeof(taco_linear_desc), sizeof(taco_decoder_weights), sizeof(taco_decoder_args)); return 0; }
+'''
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "p.c"); exe = os.path.join(d, "p")
+        open(c, "w").write(probe)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
+        a, b, cc = map(int, subprocess.check_output([exe]).split())
+    assert ctypes.sizeof(_lib.LinearDesc) == a
+    assert ctypes.sizeof(_lib.DecoderWeights) == b
+    assert ctypes.sizeof(_lib.DecoderArgs) == cc
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from tacotron_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    import pytest
+    with pytest.raises(_lib.TacoError):
+        _lib.lib()
+
+
+def test_decoder_sizes_host_only():
+    from tacotron_b200 import _lib
+    lib = _lib.lib()
+    # packed floats = 32 slices x sum_s K_s*NC_s
+    r5 = lib.taco_decoder_packed_bytes(5) // 4
+    r2 = lib.taco_decoder_packed_bytes(2) // 4
+    per_slice5 = 80*8 + 256*4 + 384*8 + 3*(512*16 + 512*8) + 256*16 + 400*8 + 656*8
+    per_slice2 = 80*8 + 256*4 + 384*8 + 3*(512*16 + 512*8) + 256*8 + 160*8 + 416*8
+    assert r5 == 32 * per_slice5 and r2 == 32 * per_slice2
+    assert lib.taco_decoder_workspace_bytes(32, 128, 200, 5) > 0

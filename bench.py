@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""bench.py -- mel frames/sec of the Tacotron hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--mode infer]
+
+A "step" is one pass of the hot path over one synthetic batch of BASELINE config 2:
+B=32 utterances, char length 128, 200 decoder steps, r=5  (32 000 mel frames), free-running
+inference forward (Tacotron.inference(train=False): encoder CBHG -> persistent attention decoder
+-> post-processing CBHG -> linear-spectrogram dense).
+
+Our arm: device-resident inputs, CUDA-event timing per step, L2 flushed between steps, max over
+ranks; plus `e2e` (host pinned inputs -> H2D -> public API -> D2H of output + alignments),
+`roofline` for the dominant kernel and `cpu_baseline` (the CPU oracle on the host cores).
+--impl reference: the reference's CPU path stand-in (the PyTorch-CPU oracle port; TensorFlow 1.2
+cannot be installed here) on the same config, all host threads.
+N > 1: inference shards by utterance with no exchange -> N independent replicas (weak scaling).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+B, TX, T, R = 32, 128, 200, 5
+FRAMES = B * T * R
+# forward FLOP (2*MAC), true unpadded contraction sizes, SURVEY.md section 8d / BASELINE.md section 3
+FWD_GFLOP = 168.05
+DECODER_GFLOP = 22.649 + 0.537          # decoder loop + attention memory layer (per launch at C2)
+METRIC = "mel frames/sec at batch 32 r=5; decoder-step p50 latency"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_step(params, inp, cfg):
+    from oracle import tacotron_oracle as O
+    import torch
+    with torch.no_grad():
+        return O.inference(params, inp, cfg, train=False)
+
+
+def time_cpu_oracle(iters):
+    """The reference's CPU path stand-in: PyTorch-CPU fp32 oracle, all host threads, C2 forward."""
+    import torch
+    from oracle import tacotron_oracle as O
+    cfg = O.OracleConfig(r=R, max_decode_iter=T)
+    params = O.init_params(cfg, seed=1)
+    inp = O.synthetic_inputs(cfg, B, TX, T, seed=0, with_targets=False)
+    cpu_oracle_step(params, inp, cfg)                        # warm-up
+    ts = []
+    for _ in range(iters):
+        t0 = time.perf_counter()
+        cpu_oracle_step(params, inp, cfg)
+        ts.append(time.perf_counter() - t0)
+    return ts, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 20))
+    ts, threads = time_cpu_oracle(steps)
+    sec = statistics.median(ts)
+    val = FRAMES / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "mel frames/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "C2 synthetic: B=32, char 128, 200 decoder steps, r=5, inference forward (free-running)",
+                   "note": "reference arm = CPU oracle port of the TF-1.2 graph (TF 1.2 not installable: py3.12, no network)"},
+        "cpu_baseline": {"value": val, "unit": "mel frames/s", "cores": threads, "kind": "port",
+                         "sample": f"{steps} full C2 forward passes (32000 frames each), median"},
+        "e2e": {"value": val, "unit": "mel frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from tacotron_b200 import Config, Tacotron, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.lib()
+
+    cfg = Config(r=R, vocab_size=64, max_decode_iter=T, precision=args.precision)
+    model = Tacotron(cfg, None, train=False, seed=1)
+    g = torch.Generator().manual_seed(rank)
+    text_h = torch.randint(1, 64, (B, TX), generator=g, dtype=torch.int32).pin_memory()
+    len_h = torch.full((B,), TX, dtype=torch.int32).pin_memory()
+    inp = {"text": text_h.cuda(), "text_length": len_h.cuda()}
+    model.step_ns = torch.zeros(T, dtype=torch.int64, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")   # > 126 MB L2
+    out_h = torch.empty((B, T, 1025 * R), dtype=torch.float32).pin_memory()
+    align_h = torch.empty((B, T, TX), dtype=torch.float32).pin_memory()
+
+    def step():
+        return model.inference(inp, train=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---------------- device-resident timing: K steps, per-step events, L2 flushed between steps ----------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    dec_ms, enc_ms, post_ms, step_lat = [], [], [], []
+    launches0 = lib.taco_launch_count()
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()
+        model._marks = []
+        starts[i].record()
+        step()
+        ends[i].record()
+        marks = model._marks
+        model._marks = None
+        torch.cuda.synchronize()
+        tt = {n: e for n, e in marks}
+        enc_ms.append(tt["start"].elapsed_time(tt["encoder"]))
+        dec_ms.append(tt["encoder"].elapsed_time(tt["decoder"]))
+        post_ms.append(tt["decoder"].elapsed_time(tt["postnet"]))
+        ns = model.step_ns.cpu().numpy()
+        step_lat.extend(((ns[1:] - ns[:-1]) / 1e3).tolist())
+    barrier()
+    launches = lib.taco_launch_count() - launches0
+    clocks = sampler.stop() if sampler else None
+    total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * FRAMES / (ms_per_step / 1e3)
+
+    # ---------------- end to end through the public API with host buffers ----------------
+    e2e_steps = max(3, min(args.steps, 10))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ci = {"text": text_h.cuda(non_blocking=True), "text_length": len_h.cuda(non_blocking=True)}
+        y, out = model.inference(ci, train=False)
+        out_h.copy_(out, non_blocking=True)
+        align_h.copy_(model.alignments, non_blocking=True)
+        torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    e2e_t = torch.tensor([(t1 - t0) / e2e_steps], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_val = world * FRAMES / float(e2e_t.item())
+    h2d = text_h.numel() * 4 + len_h.numel() * 4
+    d2h = out_h.numel() * 4 + align_h.numel() * 4
+
+    if rank == 0:
+        pk = peaks()
+        dms = statistics.mean(dec_ms)
+        ach = DECODER_GFLOP / dms                      # GFLOP / ms = TFLOP/s
+        cpu = None
+        if not args.no_cpu_baseline:
+            ts, threads = time_cpu_oracle(3)
+            sec = statistics.median(ts)
+            cpu = {"value": FRAMES / sec, "unit": "mel frames/s", "cores": threads, "kind": "port",
+                   "sample": "3 full C2 forward passes of the PyTorch-CPU oracle (32000 frames each), median"}
+        line = {
+            "metric": METRIC, "value": value, "unit": "mel frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (tf32 tensor-core multiplies, fp32 accumulate; recurrent kernels fp32)" if args.precision == "tf32" else "f32",
+            "data": "synthetic",
+            "config": {"workload": "C2 synthetic: B=32, char 128, 200 decoder steps, r=5, inference forward (free-running)",
+                       "frames_per_step": FRAMES, "l2": "256 MB flush write between timed steps", "parallelism": f"replicas x{world}",
+                       "precision": args.precision},
+            "decoder_step_p50_us": statistics.median(step_lat) if step_lat else None,
+            "sections_ms": {"encoder": statistics.mean(enc_ms), "decoder": dms, "postnet": statistics.mean(post_ms)},
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "mel frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": float(e2e_t.item()) * 1e3},
+            "gpu_launches": int(launches),
+            "roofline": {"kernel": "decoder_kernel (persistent, 200 steps)", "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"],
+                         "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"],
+                         "algorithmic_gflop_per_launch": DECODER_GFLOP,
+                         "whole_step": {"achieved": FWD_GFLOP / ms_per_step, "frac": FWD_GFLOP / ms_per_step / pk["bf16_tflops"]}},
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -165,6 +165,9 @@ int taco_decoder_fwd(const taco_decoder_args* a, void* stream);
 int taco_l1_loss_fwd(const float* a, const float* b, int64_t n, float* partial_ws, float* out, void* stream);
 int taco_l1_partial_count(void);   /* floats partial_ws must hold */
 
+/* number of kernels this library has launched so far in this process (for bench.py's gpu_launches) */
+unsigned long long taco_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,7 +69,7 @@ EXPORTS = [
     "taco_last_error", "taco_version", "taco_device_info", "taco_linear_fwd", "taco_pack_weight",
     "taco_maxpool_fwd", "taco_gather_rows", "taco_mask_rows", "taco_bigru_fwd",
     "taco_decoder_packed_bytes", "taco_decoder_workspace_bytes", "taco_decoder_pack", "taco_decoder_fwd",
-    "taco_l1_loss_fwd", "taco_l1_partial_count",
+    "taco_l1_loss_fwd", "taco_l1_partial_count", "taco_launch_count",
 ]
 
 
@@ -101,6 +101,7 @@ def lib():
     L.taco_decoder_fwd.argtypes = [C.POINTER(DecoderArgs), C.c_void_p]
     L.taco_l1_loss_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.taco_l1_partial_count.restype = C.c_int
+    L.taco_launch_count.restype = C.c_ulonglong
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int and name not in ("taco_version", "taco_l1_partial_count"):

@@ -4,6 +4,7 @@
 #include "common.cuh"
 
 static thread_local char g_err[1024] = "";
+unsigned long long g_taco_launches = 0;
 
 void taco_set_error(const char* fmt, ...) {
     va_list ap;
@@ -180,5 +181,7 @@ int taco_l1_loss_fwd(const float* a, const float* b, int64_t n, float* partial_w
 }
 
 int taco_l1_partial_count(void) { return L1_BLOCKS; }
+
+unsigned long long taco_launch_count(void) { return g_taco_launches; }
 
 }  // extern "C"

@@ -28,8 +28,11 @@ void taco_set_error(const char* fmt, ...);
         }                                                                                   \
     } while (0)
 
+extern unsigned long long g_taco_launches;   // kernels launched by this library (bench.py reports it)
+
 #define TACO_LAUNCH_CHECK()                                                                 \
     do {                                                                                    \
+        ++g_taco_launches;                                                                  \
         cudaError_t _e = cudaGetLastError();                                                \
         if (_e != cudaSuccess) {                                                            \
             taco_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \

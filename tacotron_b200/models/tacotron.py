@@ -71,8 +71,15 @@ class Tacotron(object):
         self.global_step = 0
         self.seq2seq_output = self.output = self.alignments = self.loss = None
         self.step_ns = None
+        self._marks = None                        # bench.py: list of (name, cuda event) section boundaries
         if inputs is not None:
             self(inputs)
+
+    def _mark(self, name):
+        if self._marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self._marks.append((name, ev))
 
     # -- parameters ---------------------------------------------------------------------------
     def load_params(self, params):
@@ -132,14 +139,17 @@ class Tacotron(object):
         if Tx % 4 != 0:
             raise ValueError(f"text width {Tx} must be a multiple of 4 (pad like the reference does: data_input.py:97-99)")
         store = self.store
+        self._mark("start")
         # embedding lookup fused with the first pre-net layer (tacotron.py:111-114, :128)
         with ops.variable_scope(store, "enc"):
             pre_out = self.pre_net(store["embedding"], dropout=cfg.char_dropout_prob, train=train, masks=enc_drop_masks,
                                    ids=text)
             encoded = ops.CBHG(pre_out, None, K=16, c=[128, 128, 128], gru_units=128, trace=trace)      # :131
+        self._mark("encoder")
         # attention decoder (:135-138)
         dec = self.create_decoder(encoded, inputs, None, train, T=T, dec_drop_masks=dec_drop_masks, sample_mask=sample_mask)
         seq2seq_output, self.alignments = dec()
+        self._mark("decoder")
         # post-processing CBHG + linear-spectrogram dense (:144-151); the reshapes are views
         with ops.variable_scope(store, "post"):
             post_input = seq2seq_output.view(B, -1, cfg.mel_features)
@@ -149,6 +159,7 @@ class Tacotron(object):
             dense = ops.linear(rt, post, W, ops.packed_weight(rt, "post/dense/W", W, 1, 256, cfg.fft_size), cfg.fft_size,
                                bias=b, tag="post/dense/out")
         output = dense.view(B, -1, cfg.fft_size * cfg.r)
+        self._mark("postnet")
         if trace is not None:
             trace["enc/prenet_out"] = pre_out
             trace["encoded"] = encoded

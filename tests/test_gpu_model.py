@@ -1,0 +1,114 @@
+"""-m gpu: end-to-end Tacotron.inference / loss parity against the committed oracle fixtures and the
+oracle itself, for both precision modes, plus size-independent properties at the BASELINE C2 shape."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import tacotron_oracle as O
+from tests.util import assert_close, make_model, ocfg, to_cuda
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+# stated tolerances (max-abs error / max|ref|):
+#   fp32 mode: every product exact fp32, differences = summation order + fast-math sigmoid/tanh
+#   tf32 mode: feed-forward contractions use TF32 multiplies (10-bit mantissa), fp32 accumulation
+TOL = {"fp32": 2e-4, "tf32": 5e-3}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("r", [2, 5])
+def test_small_golden(precision, r):
+    g = np.load(os.path.join(GOLD, f"oracle_small_r{r}.npz"))
+    cfg = O.OracleConfig(r=r, max_decode_iter=6, vocab_size=20)
+    p = O.init_params(cfg, seed=1, trained_like=True)
+    inp = O.synthetic_inputs(cfg, 2, 12, 6, seed=0, ragged=True)
+    enc_m, dec_m = O.dropout_masks(cfg, 2, 12, 6, seed=2)
+    sm = O.sched_mask(cfg, 2, 6, seed=3)
+    m = make_model(cfg, p, precision)
+    ci = to_cuda(inp)
+    y, out = m.inference(ci, train=False)
+    torch.cuda.synchronize()
+    assert_close(y, torch.from_numpy(g["y_infer"]), TOL[precision], "y infer")
+    assert_close(out, torch.from_numpy(g["out_infer"]), TOL[precision], "out infer")
+    assert_close(m.alignments, torch.from_numpy(g["align_infer"]), TOL[precision], "align infer")
+    cm = lambda t: tuple(x.cuda() for x in t)
+    m.config.scheduled_sample = 0.0
+    m.train = True
+    y, out = m(ci, enc_drop_masks=cm(enc_m), dec_drop_masks=cm(dec_m))
+    torch.cuda.synchronize()
+    assert_close(y, torch.from_numpy(g["y_teacher"]), TOL[precision], "y teacher")
+    assert_close(out, torch.from_numpy(g["out_teacher"]), TOL[precision], "out teacher")
+    lt = g["loss_teacher"]
+    assert abs(float(m.loss) - lt[0]) / lt[0] < TOL[precision]
+    m.config.scheduled_sample = 0.5
+    y, out = m(ci, enc_drop_masks=cm(enc_m), dec_drop_masks=cm(dec_m), sample_mask=sm.cuda())
+    torch.cuda.synchronize()
+    assert_close(y, torch.from_numpy(g["y_sched"]), TOL[precision], "y sched")
+    assert_close(out, torch.from_numpy(g["out_sched"]), TOL[precision], "out sched")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_c2_shape_inference(precision):
+    """BASELINE config 2: B=32, Tx=128 (ragged lengths), T=200, r=5, free-running, trained-like weights."""
+    cfg = ocfg(r=5, T=200)
+    p = O.init_params(cfg, seed=1, trained_like=True)
+    inp = O.synthetic_inputs(cfg, 32, 128, 200, seed=0, ragged=True, with_targets=False)
+    trace = {}
+    y_ref, out_ref, a_ref = O.inference(p, inp, cfg, train=False, trace=trace)
+    m = make_model(cfg, p, precision)
+    tr = {}
+    y, out = m.inference(to_cuda(inp), train=False, trace=tr)
+    torch.cuda.synchronize()
+    assert_close(tr["encoded"], trace["encoded"], TOL[precision], "encoded")
+    assert_close(y, y_ref, TOL[precision], "seq2seq_output")
+    assert_close(m.alignments, a_ref, TOL[precision], "alignments")
+    assert_close(tr["post/cbhg/out"], trace["post/cbhg/out"], TOL[precision], "post cbhg")
+    assert_close(out, out_ref, TOL[precision], "output")
+    assert out.shape == (32, 200, 5125) and y.shape == (32, 200, 400)
+
+
+def test_c3_shape_sched_sampling_r2():
+    """BASELINE config 3: r=2, scheduled sampling 0.5, dropout on, B=32."""
+    cfg = ocfg(r=2, T=200)
+    p = O.init_params(cfg, seed=1, trained_like=False)
+    inp = O.synthetic_inputs(cfg, 32, 128, 200, seed=4)
+    enc_m, dec_m = O.dropout_masks(cfg, 32, 128, 200, seed=2)
+    sm = O.sched_mask(cfg, 32, 200, seed=3)
+    y_ref, out_ref, a_ref = O.inference(p, inp, cfg, train=True, enc_drop_masks=enc_m, dec_drop_masks=dec_m, sample_mask=sm)
+    loss_ref = O.loss(y_ref, out_ref, inp["mel"], inp["stft"])[0]
+    m = make_model(cfg, p, "tf32")
+    m.train = True
+    cm = lambda t: tuple(x.cuda() for x in t)
+    y, out = m(to_cuda(inp), enc_drop_masks=cm(enc_m), dec_drop_masks=cm(dec_m), sample_mask=sm.cuda())
+    torch.cuda.synchronize()
+    assert_close(y, y_ref, TOL["tf32"], "y")
+    assert_close(out, out_ref, TOL["tf32"], "out")
+    assert abs(float(m.loss) - float(loss_ref)) / float(loss_ref) < 1e-3
+
+
+def test_properties_at_full_size():
+    """Size-independent properties at C2: (1) utterances are independent -- a batch of 32 equals the
+    same utterances run as 2 x 16; (2) alignments are probability rows that vanish past text_length;
+    (3) the run is deterministic (bit-identical repeat)."""
+    cfg = ocfg(r=5, T=200)
+    p = O.init_params(cfg, seed=7, trained_like=True)
+    inp = O.synthetic_inputs(cfg, 32, 128, 200, seed=1, ragged=True, with_targets=False)
+    m = make_model(cfg, p, "tf32")
+    ci = to_cuda(inp)
+    y, out = m.inference(ci, train=False)
+    y = y.clone(); out = out.clone(); al = m.alignments.clone()
+    y2, out2 = m.inference(ci, train=False)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y2) and torch.equal(out, out2)
+    half = {k: v[:16].contiguous() for k, v in ci.items()}
+    yh, outh = m.inference(half, train=False)
+    torch.cuda.synchronize()
+    assert torch.equal(yh, y[:16]) and torch.equal(outh, out[:16])
+    s = al.sum(-1)
+    assert torch.allclose(s, torch.ones_like(s), atol=1e-5)
+    tl = ci["text_length"]
+    pad = torch.arange(128, device="cuda")[None, None, :] >= tl[:, None, None]
+    assert float((al * pad).abs().max()) == 0.0

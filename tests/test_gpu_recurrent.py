@@ -1,0 +1,84 @@
+"""-m gpu: persistent bi-GRU and persistent decoder kernels against the CPU oracle."""
+import pytest
+import torch
+
+from oracle import tf12
+from oracle import tacotron_oracle as O
+from tests.util import assert_close, ocfg
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("B,T", [(1, 1), (2, 37), (32, 128), (3, 1000)])
+def test_bigru(B, T):
+    from tacotron_b200.models import ops
+    from tacotron_b200.params import ParamStore
+    shapes = []
+    for d in ("gru_fw", "gru_bw"):
+        shapes += [(f"c/{d}/Wg", (256, 256), "dense"), (f"c/{d}/bg", (256,), "ones"), (f"c/{d}/Wc", (256, 128), "dense"),
+                   (f"c/{d}/bc", (128,), "zeros")]
+    st = ParamStore(shapes, "cuda")
+    g = torch.Generator().manual_seed(T)
+    p = {n: (torch.randn(s, generator=g) * (0.08 if len(s) == 2 else 0.5)) for n, (s, _) in st.shapes.items()}
+    st.load(p)
+    ops.runtime(st, "fp32")
+    x = torch.randn(B, T, 128, generator=g)
+    fw = tuple(p[f"c/gru_fw/{n}"] for n in ("Wg", "bg", "Wc", "bc"))
+    bw = tuple(p[f"c/gru_bw/{n}"] for n in ("Wg", "bg", "Wc", "bc"))
+    ref = tf12.bidirectional_gru(x, fw, bw)
+    y = ops.bidirectional_gru(x.cuda(), 128, scope=ops.Scope(st, "c"))
+    torch.cuda.synchronize()
+    assert_close(y, ref, 5e-5, f"bigru B={B} T={T}")
+
+
+def _decoder_case(r, B, Tx, T, mode, ragged=True, seed=0):
+    from tacotron_b200.models import ops
+    from tacotron_b200.params import ParamStore, model_shapes
+    from tacotron_b200 import Config, _lib as L
+    cfg = ocfg(r=r, T=T, vocab=20)
+    p = O.init_params(cfg, seed=1, trained_like=True)
+    g = torch.Generator().manual_seed(seed)
+    encoded = torch.randn(B, Tx, 256, generator=g) * 0.5
+    inp = O.synthetic_inputs(cfg, B, Tx, T, seed=seed, ragged=ragged)
+    _, dec_m = O.dropout_masks(cfg, B, Tx, T, seed=2)
+    sm = O.sched_mask(cfg, B, T, seed=3)
+    omode = {"infer": "infer", "teacher": "teacher", "sched": "sched"}[mode]
+    drop = None if mode == "infer" else dec_m
+    y_ref, a_ref = O.decoder(encoded, inp["text_length"], p, cfg, omode, T, mel=inp["mel"], drop_masks=drop,
+                             sample_mask=sm if mode == "sched" else None)
+    st = ParamStore(model_shapes(Config(r=r, vocab_size=20)), "cuda")
+    st.load(p)
+    ops.runtime(st, "fp32")
+    lmode = {"infer": L.DEC_INFER, "teacher": L.DEC_TEACHER, "sched": L.DEC_SCHED}[mode]
+    y, a = ops.attention_decoder(encoded.cuda(), inp["text_length"].cuda(), r, T, mode=lmode,
+                                 mel=None if mode == "infer" else inp["mel"].cuda(),
+                                 sample_mask=sm.cuda() if mode == "sched" else None,
+                                 drop_masks=None if drop is None else (drop[0].cuda(), drop[1].cuda()),
+                                 scope=ops.Scope(st, "dec"))
+    torch.cuda.synchronize()
+    return y, a, y_ref, a_ref
+
+
+@pytest.mark.parametrize("mode", ["infer", "teacher", "sched"])
+@pytest.mark.parametrize("r,B,Tx,T", [(2, 3, 12, 6), (5, 32, 128, 20), (5, 9, 64, 7)])
+def test_decoder(mode, r, B, Tx, T):
+    y, a, y_ref, a_ref = _decoder_case(r, B, Tx, T, mode)
+    assert_close(y, y_ref, 1e-4, f"decoder y {mode} r={r}")
+    assert_close(a, a_ref, 1e-4, f"decoder align {mode} r={r}")
+    # alignments are a softmax over the unmasked positions
+    s = a.sum(-1).cpu()
+    assert torch.allclose(s, torch.ones_like(s), atol=1e-5)
+
+
+def test_decoder_full_length_free_running():
+    """C2 decoder shape (B=32, Tx=128, T=200, r=5), free-running: errors feed back for 200 steps."""
+    y, a, y_ref, a_ref = _decoder_case(5, 32, 128, 200, "infer")
+    assert_close(y, y_ref, 5e-4, "decoder y free-running 200 steps")
+    assert_close(a, a_ref, 5e-4, "decoder align free-running 200 steps")
+
+
+def test_decoder_rejects_bad_args():
+    from tacotron_b200 import _lib as L
+    import ctypes as C
+    a = L.DecoderArgs()
+    assert L.lib().taco_decoder_fwd(C.byref(a), None) != 0

@@ -215,10 +215,15 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
             __syncthreads();
             if (arow < B) {
                 const int dsl = tid & 7;
-                for (int j = tid >> 3; j < Tq; j += NTHR / 8) {
+                // warp-uniform trip count (each warp covers 4 consecutive j per pass): the full-mask
+                // shuffles below must be executed by all 32 lanes even when Tq is not a multiple of 4
+                for (int j0 = warp * 4; j0 < Tq; j0 += NTHR / 8) {
+                    const int j = j0 + (lane >> 3);
+                    const bool valid = j < Tq;
                     float acc = 0.f;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
+                        if (!valid) break;
                         const int d0 = i * 32 + dsl * 4;
                         float4 kk = *reinterpret_cast<const float4*>(keys_s + j * KV_LD + d0);
                         float4 qq = *reinterpret_cast<const float4*>(q_s + d0);
@@ -231,7 +236,7 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
                     acc += __shfl_xor_sync(0xffffffffu, acc, 1);
                     acc += __shfl_xor_sync(0xffffffffu, acc, 2);
                     acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-                    if (dsl == 0) e_s[j] = (aq * Tq + j < my_len) ? acc : -INFINITY;
+                    if (valid && dsl == 0) e_s[j] = (aq * Tq + j < my_len) ? acc : -INFINITY;
                 }
             }
             __syncthreads();

@@ -146,20 +146,24 @@ def test_small_kernels():
     lib = L.lib()
     g = torch.Generator().manual_seed(9)
     x = torch.randn(3, 17, 64, generator=g)
+    xd = x.cuda()
     y = torch.empty_like(x).cuda()
-    L.check(lib.taco_maxpool_fwd(L.ptr(x.cuda()), L.ptr(y), 3, 17, 64, L.current_stream()))
+    L.check(lib.taco_maxpool_fwd(L.ptr(xd), L.ptr(y), 3, 17, 64, L.current_stream()))
     assert torch.equal(y.cpu(), tf12.max_pool_2_1_same(x))
     ln = torch.tensor([17, 0, 5], dtype=torch.int32)
-    L.check(lib.taco_mask_rows(L.ptr(x.cuda()), L.ptr(ln.cuda()), L.ptr(y), 3, 17, 64, L.current_stream()))
+    lnd = ln.cuda()
+    L.check(lib.taco_mask_rows(L.ptr(xd), L.ptr(lnd), L.ptr(y), 3, 17, 64, L.current_stream()))
     ref = x * (torch.arange(17)[None, :, None] < ln[:, None, None])
     assert torch.equal(y.cpu(), ref)
     table = torch.randn(20, 32, generator=g); ids = torch.randint(0, 20, (50,), generator=g, dtype=torch.int32)
     out = torch.empty(50, 32).cuda()
-    L.check(lib.taco_gather_rows(L.ptr(table.cuda()), L.ptr(ids.cuda()), 50, 32, 20, None, 1.0, L.ptr(out), L.current_stream()))
+    td, idd = table.cuda(), ids.cuda()           # keep the device tensors alive across the async launch
+    L.check(lib.taco_gather_rows(L.ptr(td), L.ptr(idd), 50, 32, 20, None, 1.0, L.ptr(out), L.current_stream()))
     assert torch.equal(out.cpu(), table[ids.long()])
     a = torch.randn(100003, generator=g); b = torch.randn(100003, generator=g)
     part = torch.empty(lib.taco_l1_partial_count()).cuda(); res = torch.empty(1).cuda()
-    L.check(lib.taco_l1_loss_fwd(L.ptr(a.cuda()), L.ptr(b.cuda()), a.numel(), L.ptr(part), L.ptr(res), L.current_stream()))
+    ad, bd = a.cuda(), b.cuda()
+    L.check(lib.taco_l1_loss_fwd(L.ptr(ad), L.ptr(bd), a.numel(), L.ptr(part), L.ptr(res), L.current_stream()))
     ref = (a.double() - b.double()).abs().sum()
     assert abs(float(res) - float(ref)) / float(ref) < 1e-6
 

@@ -1,8 +1,11 @@
 #!/bin/bash
-# ncu passes (1 GPU): launch list of one bench-like run, then --set full of every kernel of one step.
+# ncu passes (1 GPU).  profile_step.py runs 3 steps; per kernel family we skip the launches of the first
+# two steps (setup + warm) and capture the third.
 mkdir -p gpurun_out
-ncu --metrics gpu__time_duration.sum --clock-control none -s 26 -c 52 --csv --log-file gpurun_out/launches.csv \
-    python scripts/profile_step.py 3 > gpurun_out/launches.log 2>&1
-ncu --set full --clock-control none --import-source on -s 26 -c 26 -f -o gpurun_out/prof_step \
-    python scripts/profile_step.py 2 > gpurun_out/prof_step.log 2>&1
+P="python scripts/profile_step.py 3"
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'gemm_tc|bigru|decoder_kernel|maxpool|mask_rows|gather' \
+    --csv --log-file gpurun_out/launches.csv $P > gpurun_out/launches.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:decoder_kernel -s 2 -c 1 -f -o gpurun_out/prof_decoder $P > gpurun_out/prof_decoder.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:bigru_kernel -s 4 -c 2 -f -o gpurun_out/prof_gru $P > gpurun_out/prof_gru.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 42 -c 21 -f -o gpurun_out/prof_gemm $P > gpurun_out/prof_gemm.log 2>&1
 ls -la gpurun_out/

@@ -182,51 +182,73 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
             if (a.pool) named_bar_sync(1, 128); else __syncwarp();
 
             const int col = n0 + ch * 32 + lane;     // MODE 1: n0 == 0, col in [0,U)
+            int nrows = a.T - (t0 + q * 32);          // valid rows of this warp's quarter
+            nrows = nrows < 0 ? 0 : (nrows > 32 ? 32 : nrows);
+            const int64_t row0 = seq_row0 + t0 + q * 32;
+            // The row loops below are written "all loads of a batch first, then math + stores" so that 8
+            // independent global loads are in flight per lane (a naive row-at-a-time loop serialises on
+            // L2 latency: measured 80 us of epilogue for a 2 us main loop).
             if (MODE == 1) {
                 const int U = BN / 2;
-                for (int rr = 0; rr < 32; ++rr) {
-                    const int t = t0 + q * 32 + rr;
-                    if (t >= a.T) break;
-                    const int64_t row = seq_row0 + t;
-                    float o = epi_highway(a.e, row, col, U, my_scr[rr * 33 + lane], my_scr[SCR + rr * 33 + lane]);
-                    a.e.Y[row * a.e.ldy + col] = o;
-                }
-            } else if (!a.pool) {
-                if (col < a.N) {
-                    for (int rr = 0; rr < 32; ++rr) {
-                        const int t = t0 + q * 32 + rr;
-                        if (t >= a.T) break;
-                        const int64_t row = seq_row0 + t;
-                        a.e.Y[row * a.e.ldy + col] = epi_value(a.e, row, col, my_scr[rr * 33 + lane]);
+                const float bH = a.e.bias ? __ldg(a.e.bias + col) : 0.f;
+                const float bT = a.e.bias ? __ldg(a.e.bias + U + col) : 0.f;
+                for (int rr0 = 0; rr0 < nrows; rr0 += 8) {
+                    float xin[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        xin[i] = (rr0 + i < nrows) ? __ldg(a.e.hx + (row0 + rr0 + i) * a.e.ldhx + col) : 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (rr0 + i < nrows) {
+                            const float H = fmaxf(my_scr[(rr0 + i) * 33 + lane] + bH, 0.f);
+                            const float Tg = sigmoidf_acc(my_scr[SCR + (rr0 + i) * 33 + lane] + bT);
+                            a.e.Y[(row0 + rr0 + i) * a.e.ldy + col] = H * Tg + xin[i] * (1.0f - Tg);
+                        }
                     }
                 }
             } else {
-                // fused max_pooling1d(2,1,'same') over t (models/ops.py:66-71): out[t] = max(e[t], e[t+1]),
-                // out[T-1] = e[T-1].  Tiles advance by 127 rows so row r+1 is always in this tile.
-                if (col < a.N) {
-                    const float* nxt_scr = scratch_base + ((q + 1) & 3) * SCR;   // first row of the next quarter
-                    float cur = 0.f;
-                    {
-                        const int t = t0 + q * 32;
-                        if (t < a.T) cur = epi_value(a.e, seq_row0 + t, col, my_scr[lane]);
+                const bool cvalid = col < a.N;
+                const float cb = (cvalid && a.e.bias) ? __ldg(a.e.bias + col) : 0.f;
+                const float csc = (cvalid && a.e.scale) ? __ldg(a.e.scale + col) : 1.f;
+                const float csh = (cvalid && a.e.shift) ? __ldg(a.e.shift + col) : 0.f;
+                const int act = a.e.act;
+                auto affine = [&](float v) { return apply_act(v + cb, act) * csc + csh; };
+                if (!a.pool) {
+                    if (cvalid) {
+                        for (int rr0 = 0; rr0 < nrows; rr0 += 8) {
+                            float res[8];
+                            float kp[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const bool ok = rr0 + i < nrows;
+                                res[i] = (ok && a.e.residual) ? __ldg(a.e.residual + (row0 + rr0 + i) * a.e.ldr + col) : 0.f;
+                                kp[i] = (ok && a.e.keep) ? (a.e.keep[(row0 + rr0 + i) * (int64_t)a.e.N + col] ? a.e.keep_scale : 0.f) : 1.f;
+                            }
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                if (rr0 + i < nrows)
+                                    a.e.Y[(row0 + rr0 + i) * a.e.ldy + col] = affine(my_scr[(rr0 + i) * 33 + lane]) * kp[i] + res[i];
+                            }
+                        }
                     }
-                    for (int rr = 0; rr < 32; ++rr) {
-                        const int r = q * 32 + rr;
-                        const int t = t0 + r;
-                        if (t >= a.T) break;
-                        float nxt = 0.f;
-                        const bool has_next = (t + 1 < a.T) && (r + 1 < TC_BM);
-                        if (has_next) {
-                            const float raw = (rr < 31) ? my_scr[(rr + 1) * 33 + lane] : nxt_scr[lane];
-                            nxt = epi_value(a.e, seq_row0 + t + 1, col, raw);
+                } else {
+                    // fused max_pooling1d(2,1,'same') over t (models/ops.py:66-71): out[t] = max(e[t], e[t+1]),
+                    // out[T-1] = e[T-1].  Tiles advance by 127 rows so row r+1 is always in this tile.
+                    if (cvalid && nrows > 0) {
+                        const float* nxt_scr = scratch_base + ((q + 1) & 3) * SCR;   // first row of the next quarter
+                        float cur = affine(my_scr[lane]);
+#pragma unroll 8
+                        for (int rr = 0; rr < nrows; ++rr) {
+                            const int r = q * 32 + rr;
+                            const int t = t0 + r;
+                            const bool has_next = (t + 1 < a.T) && (r + 1 < TC_BM);
+                            float nxt = 0.f;
+                            if (has_next) nxt = affine((rr < 31) ? my_scr[(rr + 1) * 33 + lane] : nxt_scr[lane]);
+                            // rows 0..126 of the tile are produced here; row 127 only if it is the sequence end
+                            if ((r < TC_BM - 1) || (t == a.T - 1))
+                                a.e.Y[(seq_row0 + t) * a.e.ldy + col] = (t + 1 < a.T) ? fmaxf(cur, nxt) : cur;
+                            cur = nxt;
                         }
-                        // rows 0..126 of the tile are produced here; row 127 only if it is the sequence end
-                        const bool emit = (r < TC_BM - 1) || (t == a.T - 1);
-                        if (emit) {
-                            const float o = (t + 1 < a.T) ? fmaxf(cur, nxt) : cur;
-                            a.e.Y[(seq_row0 + t) * a.e.ldy + col] = o;
-                        }
-                        cur = nxt;
                     }
                 }
             }
@@ -320,7 +342,7 @@ int taco_linear_tc(const taco_linear_desc* d, cudaStream_t st) {
     const int BN = highway ? 256 : 128;
     if (highway) TACO_CHECK(d->N == 256 && d->taps == 1 && d->bank_K == 0 && d->hx, "highway (TC): needs N == 256 (U = 128), dense, hx");
     if (d->bank_K > 0) TACO_CHECK(d->bank_cout == 128 && d->N == d->bank_K * 128, "bank (TC): bank_cout must be 128");
-    if (d->pool) TACO_CHECK(!highway, "pool + highway not supported");
+    if (d->pool) TACO_CHECK(!highway && !d->residual && !d->keep, "pool cannot be combined with highway / residual / dropout");
 
     TcArgs a;
     a.B = d->B; a.T = d->T;

@@ -9,21 +9,52 @@
 // big tensor-core GEMM done by the caller (xp, 768 columns = fw gates|fw cand|bw gates|bw cand).
 // The serial part is one CTA per (utterance, direction): 64 CTAs at B=32, no inter-CTA
 // communication at all.  The recurrent weights (128x256 + 128x128 fp32 = 192 KB) live in the
-// REGISTER FILE of the CTA's 512 threads (96 floats each) for the whole sequence; only the
-// 128-float state vector moves through shared memory.  Two dependent mat-vecs per step
-// (gates, then candidate on r*h), two __syncthreads per step.
+// REGISTER FILE of the CTA's 512 threads (96 floats each) for the whole sequence.
+//
+// Thread mapping (v2): shared-memory -> register bandwidth (128 B/clk/SM) was the bottleneck of
+// the first version, where every thread re-read half of h each step (131 KB/step).  Now the 32
+// lanes of a warp split K: lane l owns k = 4l..4l+3 (ONE 16-byte LDS of h per mat-vec), warp w
+// owns 16 gate columns (8 candidate columns), and the per-column partial sums are combined with a
+// halving butterfly (16 -> 8 -> 4 -> 2 -> 1 values over shfl_xor 16, 8, 4, 2, 1: 16 shuffles).
 #include "common.cuh"
 
 namespace {
 
 constexpr int H = 128;
 
+// Reduce N per-lane partial sums (N = 16 or 8) across the 32 lanes.  Each round halves the number of
+// live values: a lane keeps the half selected by its lane bit and receives the partner's
+// contribution for that half.  On return p[0] holds the full sum of column
+//   N=16: c = 8*b4 + 4*b3 + 2*b2 + b1      N=8: c = 4*b4 + 2*b3 + b2      (b_i = bit i of lane)
+template <int N>
+__device__ __forceinline__ float butterfly(float (&p)[N], int lane) {
+    int n = N;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        if (n > 1) {
+            const bool hi = (lane & off) != 0;
+            n >>= 1;
+#pragma unroll
+            for (int j = 0; j < N / 2; ++j) {
+                if (j < n) {
+                    const float send = hi ? p[j] : p[j + n];
+                    const float keep = hi ? p[j + n] : p[j];
+                    p[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+            }
+        } else {
+            p[0] += __shfl_xor_sync(0xffffffffu, p[0], off);
+        }
+    }
+    return p[0];
+}
+
 __global__ void __launch_bounds__(512, 1)
 bigru_kernel(const float* __restrict__ xp, const float* __restrict__ Wg_fw, const float* __restrict__ Wc_fw,
              const float* __restrict__ Wg_bw, const float* __restrict__ Wc_bw, float* __restrict__ out, int T) {
     const int b = blockIdx.x;
     const int dir = blockIdx.y;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const float* Wg = dir ? Wg_bw : Wg_fw;     // [128][256]  h-side rows of the gates kernel
     const float* Wc = dir ? Wc_bw : Wc_fw;     // [128][128]  (r*h)-side rows of the candidate kernel
 
@@ -31,14 +62,20 @@ bigru_kernel(const float* __restrict__ xp, const float* __restrict__ Wg_fw, cons
     __shared__ __align__(16) float rh_s[H];
     __shared__ float u_s[H];
 
-    // gates: column gcol (0..255), k half gk (64 k each); candidate: column ccol (0..127), k quarter ck (32 each)
-    const int gcol = tid >> 1, gk = tid & 1;
-    const int ccol = tid >> 2, ck = tid & 3;
-    float wg[64], wc[32];
+    // weights: lane owns k = 4*lane + i; warp owns gate columns [16w,16w+16) and candidate columns [8w,8w+8)
+    float wg[4][16], wc[4][8];
 #pragma unroll
-    for (int i = 0; i < 64; ++i) wg[i] = __ldg(Wg + (int64_t)(gk * 64 + i) * 256 + gcol);
+    for (int i = 0; i < 4; ++i) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) wc[i] = __ldg(Wc + (int64_t)(ck * 32 + i) * 128 + ccol);
+        for (int c = 0; c < 16; ++c) wg[i][c] = __ldg(Wg + (int64_t)(4 * lane + i) * 256 + warp * 16 + c);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) wc[i][c] = __ldg(Wc + (int64_t)(4 * lane + i) * 128 + warp * 8 + c);
+    }
+    // after the butterflies: which column this lane finalises
+    const int gcol = warp * 16 + (((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1));
+    const bool g_owner = (lane & 1) == 0;
+    const int ccol = warp * 8 + (((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1));
+    const bool c_owner = (lane & 3) == 0;
 
     if (tid < H) h_s[tid] = 0.0f;               // zero initial state (ops.py:112-115, s is None)
     __syncthreads();
@@ -46,59 +83,60 @@ bigru_kernel(const float* __restrict__ xp, const float* __restrict__ Wg_fw, cons
     const int64_t seq = (int64_t)b * T;
     auto xrow = [&](int step) { int t = dir ? (T - 1 - step) : step; return xp + (seq + t) * 768 + dir * 384; };
 
-    float xg_n = 0.f, xc_n = 0.f;
-    if (T > 0) {
-        const float* x0 = xrow(0);
-        if (gk == 0) xg_n = __ldg(x0 + gcol);
-        if (ck == 0) xc_n = __ldg(x0 + 256 + ccol);
-    }
+    // input products are prefetched two steps ahead (they do not depend on h)
+    float xg0 = 0.f, xc0 = 0.f, xg1 = 0.f, xc1 = 0.f;
+    if (T > 0) { const float* x = xrow(0); if (g_owner) xg0 = __ldg(x + gcol); if (c_owner) xc0 = __ldg(x + 256 + ccol); }
+    if (T > 1) { const float* x = xrow(1); if (g_owner) xg1 = __ldg(x + gcol); if (c_owner) xc1 = __ldg(x + 256 + ccol); }
+
     for (int step = 0; step < T; ++step) {
         const int t = dir ? (T - 1 - step) : step;
-        const float xg = xg_n, xc = xc_n;
-        if (step + 1 < T) {                     // prefetch next step's input products (independent of h)
-            const float* xn = xrow(step + 1);
-            if (gk == 0) xg_n = __ldg(xn + gcol);
-            if (ck == 0) xc_n = __ldg(xn + 256 + ccol);
+        const float xg = xg0, xc = xc0;
+        xg0 = xg1; xc0 = xc1;
+        if (step + 2 < T) {
+            const float* xn = xrow(step + 2);
+            if (g_owner) xg1 = __ldg(xn + gcol);
+            if (c_owner) xc1 = __ldg(xn + 256 + ccol);
         }
         // ---- gates: h . Wg_h ----
-        float a0 = 0.f, a1 = 0.f;
-        const float4* h4 = reinterpret_cast<const float4*>(h_s + gk * 64);
+        {
+            const float4 hv = *reinterpret_cast<const float4*>(h_s + 4 * lane);
+            float p[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            float4 hv = h4[i];
-            a0 = fmaf(hv.x, wg[4 * i + 0], a0);
-            a1 = fmaf(hv.y, wg[4 * i + 1], a1);
-            a0 = fmaf(hv.z, wg[4 * i + 2], a0);
-            a1 = fmaf(hv.w, wg[4 * i + 3], a1);
-        }
-        float acc = a0 + a1;
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        if (gk == 0) {
-            float g = sigmoidf_acc(acc + xg);
-            if (gcol < H) rh_s[gcol] = g * h_s[gcol];   // r * h
-            else u_s[gcol - H] = g;                      // u
+            for (int c = 0; c < 16; ++c) p[c] = hv.x * wg[0][c];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) p[c] = fmaf(hv.y, wg[1][c], p[c]);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) p[c] = fmaf(hv.z, wg[2][c], p[c]);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) p[c] = fmaf(hv.w, wg[3][c], p[c]);
+            const float acc = butterfly<16>(p, lane);
+            if (g_owner) {
+                const float g = sigmoidf_acc(acc + xg);
+                if (gcol < H) rh_s[gcol] = g * h_s[gcol];   // r * h
+                else u_s[gcol - H] = g;                      // u
+            }
         }
         __syncthreads();
         // ---- candidate: (r*h) . Wc_h ----
-        float c0 = 0.f, c1 = 0.f;
-        const float4* r4 = reinterpret_cast<const float4*>(rh_s + ck * 32);
+        {
+            const float4 rv = *reinterpret_cast<const float4*>(rh_s + 4 * lane);
+            float p[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float4 rv = r4[i];
-            c0 = fmaf(rv.x, wc[4 * i + 0], c0);
-            c1 = fmaf(rv.y, wc[4 * i + 1], c1);
-            c0 = fmaf(rv.z, wc[4 * i + 2], c0);
-            c1 = fmaf(rv.w, wc[4 * i + 3], c1);
-        }
-        float cacc = c0 + c1;
-        cacc += __shfl_xor_sync(0xffffffffu, cacc, 1);
-        cacc += __shfl_xor_sync(0xffffffffu, cacc, 2);
-        if (ck == 0) {
-            float c = tanhf_acc(cacc + xc);
-            float u = u_s[ccol];
-            float hn = u * h_s[ccol] + (1.0f - u) * c;
-            h_s[ccol] = hn;
-            out[(seq + t) * 256 + dir * H + ccol] = hn;
+            for (int c = 0; c < 8; ++c) p[c] = rv.x * wc[0][c];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) p[c] = fmaf(rv.y, wc[1][c], p[c]);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) p[c] = fmaf(rv.z, wc[2][c], p[c]);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) p[c] = fmaf(rv.w, wc[3][c], p[c]);
+            const float cacc = butterfly<8>(p, lane);
+            if (c_owner) {
+                const float c = tanhf_acc(cacc + xc);
+                const float u = u_s[ccol];
+                const float hn = u * h_s[ccol] + (1.0f - u) * c;
+                h_s[ccol] = hn;
+                out[(seq + t) * 256 + dir * H + ccol] = hn;
+            }
         }
         __syncthreads();
     }

@@ -14,24 +14,28 @@
 //   AL  attn = [y_t, ctx] . W_a                            AttentionWrapper attention_layer (no bias)
 //   next input: InferenceHelper -> y_t ; TrainingHelper -> mel[:, t+1] ; ScheduledOutput -> per-row mix
 //
-// Design v2 (B <= 32 utterances per launch), driven by the v1 measurements (58 us / step, all of it
-// grid-barrier latency + shared-memory operand traffic):
+// Design v3 (B <= 32 utterances per launch).  History: v1 (grid barrier between stages, FFMA 1x4
+// tiles) ran 58 us/step, 45% of it barrier wait; v2 (flag-in-data exchange, FFMA 8x4 tiles +
+// shuffle butterfly) 48 us/step and turned out instruction bound (80% of 77 K warp-instructions per
+// CTA-step were not FFMA: polling loops, index math, butterfly).  v3:
 //   * grid = 128 CTAs x 256 threads, co-resident (cooperative launch), alive for all T steps.
 //     Dense stage [32 x K].[K x N]: CTA (rg, cs) owns rows 8rg..8rg+7 and the cs-th of 32 column slices.
-//   * NO grid barrier.  Every exchanged activation is a 64-bit word {fp32 value, step tag} written with
-//     one st.b64 and read with polling 128-bit volatile loads: data and flag travel together ("LL"
-//     protocol), so a stage boundary costs one L2 write->read latency, no fences, no atomics.  A buffer
-//     is re-written only one full step later, which the dependency chain itself guarantees to be after
-//     all of its readers have consumed it.
-//   * compute mapping: thread tile 8 rows x 4 columns, the 32 lanes of a warp split K in 16-byte
-//     chunks (12 LDS.128 per 128 FMA instead of 5 per 16 in v1 -- shared-memory->register bandwidth
-//     was the limiter), lane partials combined by a 32->1 halving butterfly (31 shuffles), warps of
-//     the same column quad by a 1 KB shared-memory exchange.
+//   * NO grid barrier: every exchanged activation is a 64-bit word {fp32 value, step tag} written with
+//     one st.b64 and read with polling 128-bit volatile loads ("LL" protocol): a stage boundary costs one
+//     L2 write->read latency, no fences, no atomics.  A buffer is re-written one full step later, which
+//     the dependency chain guarantees to be after all of its readers have consumed it.
+//   * the contraction runs on the tensor pipe with fp32-grade accuracy: mma.sync m16n8k8 TF32 with the
+//     3xTF32 error-compensated split (x = hi + lo: hi.hi + lo.hi + hi.lo, fp32 accumulate).  M = the 8
+//     utterance rows (+8 zero rows), N = 8 weight columns, K split over the 8 warps.  The A fragments
+//     are loaded STRAIGHT from the LL words in L2 into registers (the exchange buffers are stored in
+//     fragment order: k and k+4 adjacent), no shared-memory staging, no ingest barrier; the B
+//     fragments (weights) come from shared memory pre-packed in fragment order (one LDS.64 per MMA).
 //   * GRU gate columns are permuted so that CTA cs owns r and u of the SAME 8 hidden units: u, the
 //     previous state and z never leave the CTA.
-//   * K x NC weight slices are contiguous in the packed buffer (taco_decoder_pack) and are either
-//     RESIDENT in shared memory or streamed from L2 by cp.async.bulk + mbarrier, double buffered,
-//     issued one stage ahead.
+//   * pre-net of step t+1 is scheduled between OUT/Q and Q/ATT of step t, off the critical chain:
+//     11 dependent hops per step instead of 13.
+//   * weight slices are RESIDENT in shared memory or streamed from L2 by cp.async.bulk + mbarrier
+//     (double buffered, issued ahead).
 //   * attention: CTA (utterance, quarter of Tx) keeps its keys/values slice in shared memory for all
 //     steps; scores + partial softmax + partial context per quarter, flash-style merge by the consumer.
 //   * %globaltimer stamp per step for the decoder-step latency metric.
@@ -41,6 +45,7 @@ namespace {
 
 constexpr int NCTA = 128;
 constexpr int NTHR = 256;
+constexpr int NWARP = 8;
 constexpr int RG = 4;          // row groups
 constexpr int RPG = 8;         // rows per group
 constexpr int NS = 32;         // column slices
@@ -50,17 +55,21 @@ constexpr int AU = 256;        // attention units
 constexpr int ENC = 256;       // memory depth
 constexpr int MF = 80;
 constexpr int NSTAGE = 13;
-constexpr int ACT_LD = 660;    // 656 + 4 floats: row stride of the staged activations
 constexpr int KV_LD = 260;     // padded row stride for keys in smem
-constexpr int STREAM_FLOATS = 512 * 16;   // largest weight slice (K=512, NC=16)
-constexpr int YLD = 512;       // row stride (elements) of the y exchange buffer
+constexpr int STREAM_FLOATS = 512 * 16;   // largest weight slice (K=512, 16 columns)
+constexpr int YLD = 512;       // row stride (words) of the y exchange buffer
+constexpr int MAXT = 8;        // max k-tiles per warp per segment (segment width <= 512)
 
 enum StageKind { K_P1 = 0, K_P2, K_IN, K_G1, K_C1, K_G2, K_C2, K_G3, K_C3, K_OUT, K_Q, K_ATT, K_AL };
+// execution order inside a step (P1/P2 belong to step t+1); two prologue slots P1(0), P2(0) come first
+__constant__ int c_order[NSTAGE] = {K_IN, K_G1, K_C1, K_G2, K_C2, K_G3, K_C3, K_OUT, K_P1, K_Q, K_P2, K_ATT, K_AL};
+static const int h_order[NSTAGE] = {K_IN, K_G1, K_C1, K_G2, K_C2, K_G3, K_C3, K_OUT, K_P1, K_Q, K_P2, K_ATT, K_AL};
 
 struct StageDesc {
-    int K0, K1;        // K = K0 + K1 (two concatenated sources)
+    int K0, K1;        // K = K0 + K1 (two concatenated sources), multiples of 8
     int N;             // true output width
-    int NC;            // columns per slice (4, 8 or 16); padded width = NC*32
+    int NCV;           // valid columns per slice (4, 8 or 16)
+    int NT;            // 8-column MMA tiles per slice (1 or 2)
     int64_t w_off;     // float offset of slice 0 in the packed buffer
     int res_off;       // float offset inside the resident smem region, or -1 = streamed
 };
@@ -80,25 +89,34 @@ struct DecParams {
     int smem_kv_off, smem_res_off, smem_stream_off, smem_total_floats;
 };
 
-__host__ __device__ inline void stage_dims(int kind, int OUT, int& K0, int& K1, int& N, int& NC) {
+__host__ __device__ inline void stage_dims(int kind, int OUT, int& K0, int& K1, int& N, int& NCV) {
     switch (kind) {
-        case K_P1: K0 = MF;  K1 = 0;   N = 256; NC = 8;  break;
-        case K_P2: K0 = 256; K1 = 0;   N = 128; NC = 4;  break;
-        case K_IN: K0 = 128; K1 = AU;  N = U;   NC = 8;  break;
-        case K_G1: case K_G2: case K_G3: K0 = U; K1 = U; N = 2 * U; NC = 16; break;
-        case K_C1: case K_C2: case K_C3: K0 = U; K1 = U; N = U;     NC = 8;  break;
-        case K_OUT: K0 = U;  K1 = 0;   N = OUT; NC = (OUT + NS - 1) / NS; NC = (NC <= 4) ? 4 : (NC <= 8) ? 8 : 16; break;
-        case K_Q:  K0 = OUT; K1 = 0;   N = AU;  NC = 8;  break;
-        case K_AL: K0 = OUT; K1 = ENC; N = AU;  NC = 8;  break;
-        default:   K0 = K1 = N = 0; NC = 4; break;      // K_ATT has no weight slice
+        case K_P1: K0 = MF;  K1 = 0;   N = 256; NCV = 8;  break;
+        case K_P2: K0 = 256; K1 = 0;   N = 128; NCV = 4;  break;
+        case K_IN: K0 = 128; K1 = AU;  N = U;   NCV = 8;  break;
+        case K_G1: case K_G2: case K_G3: K0 = U; K1 = U; N = 2 * U; NCV = 16; break;
+        case K_C1: case K_C2: case K_C3: K0 = U; K1 = U; N = U;     NCV = 8;  break;
+        case K_OUT: K0 = U;  K1 = 0;   N = OUT; NCV = (OUT + NS - 1) / NS; NCV = (NCV <= 4) ? 4 : (NCV <= 8) ? 8 : 16; break;
+        case K_Q:  K0 = OUT; K1 = 0;   N = AU;  NCV = 8;  break;
+        case K_AL: K0 = OUT; K1 = ENC; N = AU;  NCV = 8;  break;
+        default:   K0 = K1 = N = 0; NCV = 8; break;      // K_ATT has no weight slice
     }
 }
 
-// global column computed by local column j of slice cs.  GRU gates: slice cs owns r (j < 8) and u
-// (j >= 8) of hidden units 8cs..8cs+7.
-__host__ __device__ inline int stage_col(int kind, int cs, int j, int NC) {
+// global column computed by local column j of slice cs (-1 = padding).  GRU gates: slice cs owns
+// r (j < 8) and u (j >= 8) of hidden units 8cs..8cs+7.
+__host__ __device__ inline int stage_col(int kind, int cs, int j, int NCV, int N) {
     if (kind == K_G1 || kind == K_G2 || kind == K_G3) return (j < 8) ? (8 * cs + j) : (U + 8 * cs + (j - 8));
-    return cs * NC + j;
+    if (j >= NCV) return -1;
+    const int c = cs * NCV + j;
+    return c < N ? c : -1;
+}
+
+// physical position of logical column k inside an exchange buffer row: within each group of 8,
+// k and k+4 are adjacent so that one 16-byte load yields the (a0, a2) pair of an MMA A fragment.
+__host__ __device__ inline int perm8(int k) {
+    const int kk = k & 7;
+    return (k & ~7) | ((kk < 4) ? 2 * kk : 2 * (kk - 4) + 1);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -114,78 +132,88 @@ __device__ __forceinline__ ulonglong2 ll_load2(const uint64_t* p) {
     return v;
 }
 __device__ __forceinline__ bool ll_ok(const ulonglong2& v, uint32_t tag) {
-    return (uint32_t)(v.x >> 32) == tag && (uint32_t)(v.y >> 32) == tag;
+    return (((uint32_t)(v.x >> 32) ^ tag) | ((uint32_t)(v.y >> 32) ^ tag)) == 0u;
 }
-// Wait for two consecutive LL words carrying `tag`; bounded so that a protocol bug traps instead of hanging.
-__device__ __forceinline__ float2 ll_wait2(const uint64_t* p, uint32_t tag) {
-    ulonglong2 v = ll_load2(p);
+// Spin until both words carry `tag`; bounded so that a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void ll_spin(ulonglong2& v, const uint64_t* p, uint32_t tag) {
     uint32_t spins = 0;
     while (!ll_ok(v, tag)) {
         if (++spins > (1u << 24)) __trap();
         v = ll_load2(p);
     }
+}
+__device__ __forceinline__ float2 ll_wait2(const uint64_t* p, uint32_t tag) {
+    ulonglong2 v = ll_load2(p);
+    ll_spin(v, p, tag);
     return make_float2(__uint_as_float((uint32_t)v.x), __uint_as_float((uint32_t)v.y));
 }
 
-// rows [row0, row0+8) x W columns of an LL buffer (row stride ld words) -> act_s[r][dst0 + c]
-__device__ __forceinline__ void ingest(float* act_s, int dst0, const uint64_t* buf, int ld, int row0, int W, uint32_t tag) {
-    const int wp = W >> 1;                 // pairs per row
-    const int npairs = RPG * wp;
-    for (int base = threadIdx.x; base < npairs; base += NTHR * 4) {
-        ulonglong2 v[4];
-        const uint64_t* ptr[4];
-        int r[4], c[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int p = base + u * NTHR;
-            r[u] = p / wp; c[u] = (p - r[u] * wp) * 2;
-            ptr[u] = buf + (int64_t)(row0 + r[u]) * ld + c[u];
-            if (p < npairs) v[u] = ll_load2(ptr[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int p = base + u * NTHR;
-            if (p < npairs) {
-                uint32_t spins = 0;
-                while (!ll_ok(v[u], tag)) {
-                    if (++spins > (1u << 24)) __trap();
-                    v[u] = ll_load2(ptr[u]);
-                }
-                *reinterpret_cast<float2*>(act_s + r[u] * ACT_LD + dst0 + c[u]) =
-                    make_float2(__uint_as_float((uint32_t)v[u].x), __uint_as_float((uint32_t)v[u].y));
-            }
-        }
-    }
+// ---------------------------------------------------------------------------------------------
+// 3xTF32 tensor-core contraction pieces
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    const float r = x - __uint_as_float(hi);
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
 }
-__device__ __forceinline__ void ingest_zero(float* act_s, int dst0, int W) {
-    for (int i = threadIdx.x; i < RPG * W; i += NTHR) act_s[(i / W) * ACT_LD + dst0 + (i % W)] = 0.f;
+// D[16x8] += A[16x8] . B[8x8]; rows 8..15 of A are zero (a1 = a3 = 0)
+__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+}
+// one k-tile: A pair (x[g][8kt+tg], x[g][8kt+tg+4]) against NT weight tiles
+template <int NT>
+__device__ __forceinline__ void ktile_mma(float (&acc)[2][4], float xa, float xb, const float* wfrag /* tile base + lane*2 */) {
+    uint32_t ah0, al0, ah2, al2;
+    split_tf32(xa, ah0, al0);
+    split_tf32(xb, ah2, al2);
+    __syncwarp();                                   // lanes may arrive from divergent polling loops
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+        const float2 w = *reinterpret_cast<const float2*>(wfrag + nt * 64);
+        uint32_t bh0, bl0, bh1, bl1;
+        split_tf32(w.x, bh0, bl0);
+        split_tf32(w.y, bh1, bl1);
+        mma_tf32(acc[nt], al0, al2, bh0, bh1);      // small terms first
+        mma_tf32(acc[nt], ah0, ah2, bl0, bl1);
+        mma_tf32(acc[nt], ah0, ah2, bh0, bh1);
+    }
 }
 
-// 32 -> 1 halving butterfly: on return lane l holds the warp-wide sum of element l.
-__device__ __forceinline__ float butterfly32(float (&p)[32], int lane) {
+// A segment of the K dimension whose activations live in an LL exchange buffer.
+//   buf: row pointer base (buffer + row*ld), ntiles = width/8, wt0 = first k-tile of the segment in the
+//   weight slice.  Warp w owns tiles w, w+8, ...  All loads are issued before the first tag check.
+template <int NT>
+__device__ __forceinline__ void seg_ll(float (&acc)[2][4], const uint64_t* rowp, int ntiles, int wt0, uint32_t tag,
+                                       const float* Wsl, int warp, int lane) {
+    const int tg = lane & 3;
+    ulonglong2 v[MAXT];
 #pragma unroll
-    for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
-        const bool hi = (lane & off) != 0;
+    for (int i = 0; i < MAXT; ++i) {
+        const int kt = warp + NWARP * i;
+        if (kt < ntiles) v[i] = ll_load2(rowp + kt * 8 + 2 * tg);
+    }
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            if (j < n) {
-                const float send = hi ? p[j] : p[j + n];
-                const float keep = hi ? p[j + n] : p[j];
-                p[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-            }
+    for (int i = 0; i < MAXT; ++i) {
+        const int kt = warp + NWARP * i;
+        if (kt < ntiles) {
+            ll_spin(v[i], rowp + kt * 8 + 2 * tg, tag);
+            ktile_mma<NT>(acc, __uint_as_float((uint32_t)v[i].x), __uint_as_float((uint32_t)v[i].y),
+                          Wsl + (size_t)(wt0 + kt) * NT * 64 + lane * 2);
         }
     }
-    return p[0];
 }
 
 __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
     extern __shared__ __align__(16) float smem[];
-    // smem map (floats): [0,64) mbarriers | act_s 8*ACT_LD | part_s 8*32 | loc 512 | small 1024 | kv | stream 2x | resident
+    // smem map (floats): [0,64) mbarriers | part_s 2*8*2*64 | loc 512 | bias 13*16 (256) | small 1024 | kv | stream 2x | resident
     uint64_t* wbar = reinterpret_cast<uint64_t*>(smem);          // [0],[1] stream buffers, [2] resident preload
-    float* act_s = smem + 64;
-    float* part_s = act_s + RPG * ACT_LD;                         // [8 warps][32]
-    float* loc_s = part_s + 8 * 32;                               // h_loc[3][64] | u_loc[64] | z_loc[64]
-    float* small_s = loc_s + 512;                                 // q_s[256] | v_s[256] | e_s[64] | p_s[64] | misc
+    float* part_s = smem + 64;                                    // [2 parity][8 warps][2 nt][8 rows][8 cols]
+    float* loc_s = part_s + 2 * NWARP * 128;                      // h_loc[3][64] | u_loc[64] | z_loc[64]
+    float* bias_s = loc_s + 512;                                  // [13][16]
+    float* small_s = bias_s + 256;                                // q_s[256] | v_s[256] | e_s[64] | p_s[64] | misc
     float* keys_s = smem + P.smem_kv_off;
     float* vals_s = keys_s + P.Tq * KV_LD;
     float* res_s = smem + P.smem_res_off;
@@ -195,6 +223,7 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
     float* z_loc = loc_s + 256;       // [8][8]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tg = lane & 3;            // MMA fragment coordinates: row g, k / column pair tg
     const int cta = blockIdx.x;
     const int rg = cta & 3, cs = cta >> 2;             // dense stages
     const int arow = cta >> 2, aq = cta & 3;           // attention stage: utterance, quarter
@@ -202,12 +231,34 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
     uint64_t* ws = reinterpret_cast<uint64_t*>(A.workspace);
     const int B = A.B, T = A.T, OUT = P.OUT, Tq = P.Tq, Tx = A.Tx;
     const int row0 = rg * RPG;
+    const int myrow = row0 + g;                        // the utterance row this lane's A fragments belong to
 
     if (tid == 0) {
         mbar_init(&wbar[0], 1); mbar_init(&wbar[1], 1); mbar_init(&wbar[2], 1);
         mbar_fence_init();
     }
     for (int i = tid; i < 512; i += NTHR) loc_s[i] = 0.f;          // zero initial GRU states (cell.zero_state)
+    // biases of this CTA's columns -> smem
+    if (tid < NSTAGE * 16) {
+        const int s = tid >> 4, j = tid & 15;
+        const StageDesc& d = P.st[s];
+        float bv = 0.f;
+        if (s != K_ATT) {
+            const int col = stage_col(s, cs, j, d.NCV, d.N);
+            const float* bp = nullptr;
+            switch (s) {
+                case K_P1: bp = P.pre_b1; break;
+                case K_P2: bp = P.pre_b2; break;
+                case K_IN: bp = P.in_b; break;
+                case K_G1: case K_G2: case K_G3: bp = P.gru_bg[(s - K_G1) / 2]; break;
+                case K_C1: case K_C2: case K_C3: bp = P.gru_bc[(s - K_C1) / 2]; break;
+                case K_OUT: bp = P.out_b; break;
+                default: break;
+            }
+            if (bp && col >= 0) bv = __ldg(bp + col);
+        }
+        bias_s[tid] = bv;
+    }
     __syncthreads();
 
     // ---- one-time preload: resident weight slices (bulk copies) ----
@@ -216,15 +267,15 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
         for (int s = 0; s < NSTAGE; ++s) {
             const StageDesc& d = P.st[s];
             if (s == K_ATT || d.res_off < 0) continue;
-            bytes += (uint32_t)((d.K0 + d.K1) * d.NC * 4);
+            bytes += (uint32_t)((d.K0 + d.K1) * d.NT * 8 * 4);
         }
         if (bytes) {
             mbar_arrive_expect_tx(&wbar[2], bytes);
             for (int s = 0; s < NSTAGE; ++s) {
                 const StageDesc& d = P.st[s];
                 if (s == K_ATT || d.res_off < 0) continue;
-                const uint32_t nb = (uint32_t)((d.K0 + d.K1) * d.NC * 4);
-                bulk_load(res_s + d.res_off, A.packed + d.w_off + (int64_t)cs * (d.K0 + d.K1) * d.NC, nb, &wbar[2]);
+                const int fl = (d.K0 + d.K1) * d.NT * 8;
+                bulk_load(res_s + d.res_off, A.packed + d.w_off + (int64_t)cs * fl, (uint32_t)fl * 4, &wbar[2]);
             }
         } else {
             mbar_arrive(&wbar[2]);
@@ -235,9 +286,9 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
         const int j = i / (ENC / 4), d4 = (i % (ENC / 4)) * 4;
         float4 kk = make_float4(0, 0, 0, 0), vv = kk;
         if (arow < B) {
-            const int64_t g = ((int64_t)arow * Tx + aq * Tq + j) * ENC + d4;
-            kk = __ldg(reinterpret_cast<const float4*>(A.keys + g));
-            vv = __ldg(reinterpret_cast<const float4*>(A.values + g));
+            const int64_t gi = ((int64_t)arow * Tx + aq * Tq + j) * ENC + d4;
+            kk = __ldg(reinterpret_cast<const float4*>(A.keys + gi));
+            vv = __ldg(reinterpret_cast<const float4*>(A.values + gi));
         }
         *reinterpret_cast<float4*>(keys_s + j * KV_LD + d4) = kk;
         *reinterpret_cast<float4*>(vals_s + j * ENC + d4) = vv;
@@ -247,36 +298,38 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
     mbar_wait(&wbar[2], 0);
     __syncthreads();
 
+    // slot -> stage kind.  Slots 0,1 = P1(0), P2(0); then 13 per step in c_order.
+    const int total_slots = 2 + T * NSTAGE;
+    auto slot_kind = [&](int sl) { return sl < 2 ? sl : c_order[(sl - 2) % NSTAGE]; };
     // streamed-slice bookkeeping: issue order == consume order; buffer = (index) & 1.  At most two slices
-    // are in flight.  A buffer is re-filled only at the top of an iteration, when every thread has passed
-    // the post-compute __syncthreads of the iteration that last read it.
+    // are in flight.  A buffer is re-filled only at the top of a slot, when every thread has passed the
+    // post-compute __syncthreads of the slot that last read it.
     uint32_t n_issued = 0, n_consumed = 0;
-    const int total_iters = T * NSTAGE;
-    int next_issue_it = 0;
+    int next_issue = 0;
     auto is_streamed = [&](int s) { return s != K_ATT && P.st[s].res_off < 0; };
     auto pump = [&]() {
         while (n_issued - n_consumed < 2) {
-            while (next_issue_it < total_iters && !is_streamed(next_issue_it % NSTAGE)) ++next_issue_it;
-            if (next_issue_it >= total_iters) break;
+            while (next_issue < total_slots && !is_streamed(slot_kind(next_issue))) ++next_issue;
+            if (next_issue >= total_slots) break;
             if (tid == 0) {
-                const StageDesc& d = P.st[next_issue_it % NSTAGE];
-                const uint32_t nb = (uint32_t)((d.K0 + d.K1) * d.NC * 4);
+                const StageDesc& d = P.st[slot_kind(next_issue)];
+                const int fl = (d.K0 + d.K1) * d.NT * 8;
                 const int buf = n_issued & 1;
                 fence_proxy_async();
-                mbar_arrive_expect_tx(&wbar[buf], nb);
-                bulk_load(stream_s + buf * STREAM_FLOATS, A.packed + d.w_off + (int64_t)cs * (d.K0 + d.K1) * d.NC, nb, &wbar[buf]);
+                mbar_arrive_expect_tx(&wbar[buf], (uint32_t)fl * 4);
+                bulk_load(stream_s + buf * STREAM_FLOATS, A.packed + d.w_off + (int64_t)cs * fl, (uint32_t)fl * 4, &wbar[buf]);
             }
-            ++n_issued; ++next_issue_it;
+            ++n_issued; ++next_issue;
         }
     };
 
-    for (int it = 0; it < total_iters; ++it) {
-        const int t = it / NSTAGE;
-        const int s = it - t * NSTAGE;
-        const uint32_t tag_now = (uint32_t)t + 1;      // values produced during step t
-        const uint32_t tag_prev = (uint32_t)t;         // values produced during step t-1 (t = 0: initial zeros)
+    for (int sl = 0; sl < total_slots; ++sl) {
+        const int s = slot_kind(sl);
+        const int t = sl < 2 ? -1 : (sl - 2) / NSTAGE;           // decoder step this slot executes in (-1 = prologue)
+        const int tb = (s == K_P1 || s == K_P2) ? t + 1 : t;      // decoder step the OUTPUT of this slot belongs to
+        const uint32_t tag_out = (uint32_t)tb + 1;                // tag of everything produced for step tb
         pump();
-        if (s == 0 && cta == 0 && tid == 0 && A.step_ns) A.step_ns[t] = globaltimer_ns();
+        if (s == K_IN && cta == 0 && tid == 0 && A.step_ns) A.step_ns[t] = globaltimer_ns();
 
         if (s == K_ATT) {
             // =============== attention scores / partial softmax / partial context ===============
@@ -284,11 +337,11 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
             float* v_s = small_s + 256;       // [256] (loaded once)
             float* e_s = small_s + 512;       // [Tq]
             float* p_s = small_s + 512 + 64;  // [Tq]  (kept until the K_AL stage)
-            if (arow < B) {
-                if (tid < AU / 2) {
-                    const float2 qq = ll_wait2(ws + P.ws.q + (int64_t)arow * AU + 2 * tid, tag_now);
-                    q_s[2 * tid] = qq.x; q_s[2 * tid + 1] = qq.y;
-                }
+            if (arow < B && tid < AU / 2) {
+                // physical pair (2p, 2p+1) holds logical k0 = 8*(p/4) + p%4 and k0 + 4
+                const float2 qq = ll_wait2(ws + P.ws.q + (int64_t)arow * AU + 2 * tid, tag_out);
+                const int k0 = ((tid >> 2) << 3) + (tid & 3);
+                q_s[k0] = qq.x; q_s[k0 + 4] = qq.y;
             }
             __syncthreads();
             if (arow < B) {
@@ -334,122 +387,22 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
                 for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
                 if (lane == 0) {
                     uint64_t* ms = ws + P.ws.att_ms + ((int64_t)arow * 4 + aq) * 2;
-                    ll_store(ms, m, tag_now);
-                    ll_store(ms + 1, ssum, tag_now);
+                    ll_store(ms, m, tag_out);
+                    ll_store(ms + 1, ssum, tag_out);
                 }
             }
             __syncthreads();
             if (arow < B) {
                 float c = 0.f;
                 for (int j = 0; j < Tq; ++j) c = fmaf(p_s[j], vals_s[j * ENC + tid], c);
-                ll_store(ws + P.ws.att_ctx + ((int64_t)arow * 4 + aq) * ENC + tid, c, tag_now);
+                ll_store(ws + P.ws.att_ctx + ((int64_t)arow * 4 + aq) * ENC + perm8(tid), c, tag_out);
             }
             continue;
         }
 
         const StageDesc& d = P.st[s];
-        const int K0 = d.K0, K1 = d.K1, K = K0 + K1, NC = d.NC;
-
-        // =============== stage inputs: rows row0..row0+7 of the sources -> act_s (polling LL loads) ===============
-        switch (s) {
-            case K_P1: {
-                // decoder input for step t, last mel frame of the r-group (tacotron.py:66-67; helpers A.8-A.10)
-                for (int i = tid; i < RPG * (MF / 2); i += NTHR) {
-                    const int r = i / (MF / 2), c2 = (i % (MF / 2)) * 2;
-                    const int row = row0 + r;
-                    float2 v = make_float2(0.f, 0.f);
-                    if (row < B) {
-                        bool from_y;
-                        if (A.mode == TACO_DEC_INFER) from_y = true;
-                        else if (A.mode == TACO_DEC_TEACHER) from_y = false;
-                        else from_y = (t > 0) && (A.sample_mask[(int64_t)(t - 1) * B + row] != 0);
-                        if (from_y) {
-                            if (t > 0) v = ll_wait2(ws + P.ws.ybuf + (int64_t)row * YLD + (OUT - MF) + c2, tag_prev);
-                        } else {
-                            v = __ldg(reinterpret_cast<const float2*>(A.mel + ((int64_t)row * T + t) * OUT + (OUT - MF) + c2));
-                        }
-                    }
-                    *reinterpret_cast<float2*>(act_s + r * ACT_LD + c2) = v;
-                }
-            } break;
-            case K_P2: ingest(act_s, 0, ws + P.ws.p1, 256, row0, 256, tag_now); break;
-            case K_IN:
-                ingest(act_s, 0, ws + P.ws.p2, 128, row0, 128, tag_now);
-                if (t > 0) ingest(act_s, 128, ws + P.ws.attn, AU, row0, AU, tag_prev); else ingest_zero(act_s, 128, AU);
-                break;
-            case K_G1: case K_G2: case K_G3: {
-                const int gi = (s - K_G1) / 2;
-                const uint64_t* xsrc = (gi == 0) ? ws + P.ws.z : ws + P.ws.h[gi - 1];
-                ingest(act_s, 0, xsrc, U, row0, U, tag_now);
-                if (t > 0) ingest(act_s, U, ws + P.ws.h[gi], U, row0, U, tag_prev); else ingest_zero(act_s, U, U);
-            } break;
-            case K_C1: case K_C2: case K_C3: {
-                const int gi = (s - K_C1) / 2;          // x part is still in act_s[.., 0:256) from the gate stage
-                ingest(act_s, U, ws + P.ws.rh[gi], U, row0, U, tag_now);
-            } break;
-            case K_OUT: ingest(act_s, 0, ws + P.ws.s, U, row0, U, tag_now); break;
-            case K_Q: ingest(act_s, 0, ws + P.ws.ybuf, YLD, row0, OUT, tag_now); break;
-            case K_AL: {
-                // y is still in act_s[.., 0:OUT) from the K_Q stage (K_ATT does not touch act_s).
-                // ctx = flash-style merge of the four quarter partials.  First the (max, sum) pairs of the 8 rows
-                // of this row group and of this CTA's own attention row -> shared memory (36 threads poll).
-                float* ms_s = small_s + 704;          // [9][4][2]: rows 0..7 = row group, row 8 = arow
-                if (tid < 36) {
-                    const int rsel = tid >> 2, qd = tid & 3;
-                    const int row = (rsel < 8) ? row0 + rsel : arow;
-                    float2 x = make_float2(-INFINITY, 0.f);
-                    if (row < B) x = ll_wait2(ws + P.ws.att_ms + (int64_t)row * 8 + 2 * qd, tag_now);
-                    ms_s[tid * 2] = x.x; ms_s[tid * 2 + 1] = x.y;
-                }
-                __syncthreads();
-                for (int i = tid; i < RPG * (ENC / 2); i += NTHR) {
-                    const int r = i / (ENC / 2), c2 = (i % (ENC / 2)) * 2;
-                    const int row = row0 + r;
-                    float2 acc = make_float2(0.f, 0.f);
-                    if (row < B) {
-                        float M = -INFINITY;
-#pragma unroll
-                        for (int qd = 0; qd < 4; ++qd) M = fmaxf(M, ms_s[(r * 4 + qd) * 2]);
-                        float S = 0.f, w[4];
-#pragma unroll
-                        for (int qd = 0; qd < 4; ++qd) {
-                            const float m = ms_s[(r * 4 + qd) * 2];
-                            w[qd] = (m == -INFINITY) ? 0.f : __expf(m - M);
-                            S += w[qd] * ms_s[(r * 4 + qd) * 2 + 1];
-                        }
-                        const float inv = 1.0f / S;
-                        float2 c[4];
-#pragma unroll
-                        for (int qd = 0; qd < 4; ++qd)
-                            c[qd] = ll_wait2(ws + P.ws.att_ctx + ((int64_t)row * 4 + qd) * ENC + c2, tag_now);
-#pragma unroll
-                        for (int qd = 0; qd < 4; ++qd) {
-                            const float ww = w[qd] * inv;
-                            acc.x = fmaf(ww, c[qd].x, acc.x); acc.y = fmaf(ww, c[qd].y, acc.y);
-                        }
-                    }
-                    *reinterpret_cast<float2*>(act_s + r * ACT_LD + K0 + c2) = acc;
-                }
-                // finalise this CTA's slice of the alignments: a_j = p_j * exp(m_q - M) / S
-                if (arow < B) {
-                    float M = -INFINITY;
-#pragma unroll
-                    for (int qd = 0; qd < 4; ++qd) M = fmaxf(M, ms_s[(32 + qd) * 2]);
-                    float S = 0.f;
-#pragma unroll
-                    for (int qd = 0; qd < 4; ++qd) {
-                        const float m = ms_s[(32 + qd) * 2];
-                        S += ((m == -INFINITY) ? 0.f : __expf(m - M)) * ms_s[(32 + qd) * 2 + 1];
-                    }
-                    const float mq = ms_s[(32 + aq) * 2];
-                    const float sc = ((mq == -INFINITY) ? 0.f : __expf(mq - M)) / S;
-                    const float* p_s = small_s + 512 + 64;
-                    for (int j = tid; j < Tq; j += NTHR)
-                        A.align[((int64_t)arow * T + t) * Tx + aq * Tq + j] = p_s[j] * sc;
-                }
-            } break;
-        }
-        // ---- this stage's weight slice ----
+        const int NT = d.NT;
+        // ---- this stage's weight slice (fragment order [k-tile][nt][lane][2]) ----
         const float* Wsl;
         if (d.res_off >= 0) {
             Wsl = res_s + d.res_off;
@@ -459,112 +412,200 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
             Wsl = stream_s + buf * STREAM_FLOATS;
             ++n_consumed;
         }
-        __syncthreads();
 
-        // =============== partial products: thread tile = 8 rows x 4 columns, lanes split K ===============
-        const int NQ = NC >> 2;                 // column quads in the slice: 1, 2 or 4
-        const int nkp = 8 / NQ;                 // warps (k parts) per quad
-        const int cq = warp % NQ;
-        const int kp = warp / NQ;
-        const int NCH = K >> 2;                 // 16-byte k chunks
-        float acc[32];
+        float acc[2][4];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-        // packed slice layout: [i = k%4][cq][chunk][4 cols]  -> lanes read consecutive 16-byte words
-        const float4* W4 = reinterpret_cast<const float4*>(Wsl);
-        for (int c = kp * 32 + lane; c < NCH; c += nkp * 32) {
-            const float4 w0 = W4[(0 * NQ + cq) * NCH + c];
-            const float4 w1 = W4[(1 * NQ + cq) * NCH + c];
-            const float4 w2 = W4[(2 * NQ + cq) * NCH + c];
-            const float4 w3 = W4[(3 * NQ + cq) * NCH + c];
+        for (int i = 0; i < 2; ++i)
 #pragma unroll
-            for (int r = 0; r < RPG; ++r) {
-                const float4 x = *reinterpret_cast<const float4*>(act_s + r * ACT_LD + 4 * c);
-                acc[4 * r + 0] = fmaf(x.x, w0.x, acc[4 * r + 0]); acc[4 * r + 1] = fmaf(x.x, w0.y, acc[4 * r + 1]);
-                acc[4 * r + 2] = fmaf(x.x, w0.z, acc[4 * r + 2]); acc[4 * r + 3] = fmaf(x.x, w0.w, acc[4 * r + 3]);
-                acc[4 * r + 0] = fmaf(x.y, w1.x, acc[4 * r + 0]); acc[4 * r + 1] = fmaf(x.y, w1.y, acc[4 * r + 1]);
-                acc[4 * r + 2] = fmaf(x.y, w1.z, acc[4 * r + 2]); acc[4 * r + 3] = fmaf(x.y, w1.w, acc[4 * r + 3]);
-                acc[4 * r + 0] = fmaf(x.z, w2.x, acc[4 * r + 0]); acc[4 * r + 1] = fmaf(x.z, w2.y, acc[4 * r + 1]);
-                acc[4 * r + 2] = fmaf(x.z, w2.z, acc[4 * r + 2]); acc[4 * r + 3] = fmaf(x.z, w2.w, acc[4 * r + 3]);
-                acc[4 * r + 0] = fmaf(x.w, w3.x, acc[4 * r + 0]); acc[4 * r + 1] = fmaf(x.w, w3.y, acc[4 * r + 1]);
-                acc[4 * r + 2] = fmaf(x.w, w3.z, acc[4 * r + 2]); acc[4 * r + 3] = fmaf(x.w, w3.w, acc[4 * r + 3]);
-            }
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+        const uint32_t tag_now = (uint32_t)t + 1;      // values produced during step t
+        const uint32_t tag_prev = (uint32_t)t;         // values produced during step t-1 (t = 0: initial zeros -> skipped)
+        const int64_t rowoff = (int64_t)myrow;
+#define SEG(bufoff, ld, width, wt0, tag)                                                              \
+        do {                                                                                          \
+            if (NT == 2) seg_ll<2>(acc, ws + (bufoff) + rowoff * (ld), (width) / 8, (wt0), (tag), Wsl, warp, lane); \
+            else         seg_ll<1>(acc, ws + (bufoff) + rowoff * (ld), (width) / 8, (wt0), (tag), Wsl, warp, lane); \
+        } while (0)
+
+        switch (s) {
+            case K_P1: {
+                // decoder input of step tb: last mel frame of the r-group (tacotron.py:66-67; helpers A.8-A.10)
+                //   INFER: y(tb-1) (zeros for tb = 0); TEACHER: mel[:, tb]; SCHED: per row, mask[tb-1] ? y(tb-1) : mel[:, tb]
+                bool from_y = true;
+                if (A.mode == TACO_DEC_TEACHER) from_y = false;
+                else if (A.mode == TACO_DEC_SCHED) from_y = (tb > 0) && (myrow < B) && (A.sample_mask[(int64_t)(tb - 1) * B + myrow] != 0);
+                const bool have = (myrow < B) && (tb < T) && (from_y ? (tb > 0) : true);
+                for (int kt = warp; kt < MF / 8; kt += NWARP) {
+                    float xa = 0.f, xb = 0.f;
+                    if (have) {
+                        if (from_y) {
+                            const float2 v = ll_wait2(ws + P.ws.ybuf + rowoff * YLD + (OUT - MF) + kt * 8 + 2 * tg, (uint32_t)tb);
+                            xa = v.x; xb = v.y;
+                        } else {
+                            const float* mp = A.mel + ((int64_t)myrow * T + tb) * OUT + (OUT - MF) + kt * 8 + tg;
+                            xa = __ldg(mp); xb = __ldg(mp + 4);
+                        }
+                    }
+                    ktile_mma<1>(acc, xa, xb, Wsl + (size_t)kt * 64 + lane * 2);
+                }
+            } break;
+            case K_P2: SEG(P.ws.p1, 256, 256, 0, tag_out); break;
+            case K_IN:
+                SEG(P.ws.p2, 128, 128, 0, tag_now);
+                if (t > 0) SEG(P.ws.attn, AU, AU, 16, tag_prev);
+                break;
+            case K_G1: case K_G2: case K_G3: {
+                const int gi = (s - K_G1) / 2;
+                const int64_t xoff = (gi == 0) ? P.ws.z : P.ws.h[gi - 1];
+                SEG(xoff, U, U, 0, tag_now);
+                if (t > 0) SEG(P.ws.h[gi], U, U, 32, tag_prev);
+            } break;
+            case K_C1: case K_C2: case K_C3: {
+                const int gi = (s - K_C1) / 2;
+                const int64_t xoff = (gi == 0) ? P.ws.z : P.ws.h[gi - 1];
+                SEG(xoff, U, U, 0, tag_now);
+                SEG(P.ws.rh[gi], U, U, 32, tag_now);
+            } break;
+            case K_OUT: SEG(P.ws.s, U, U, 0, tag_now); break;
+            case K_Q: SEG(P.ws.ybuf, YLD, OUT, 0, tag_now); break;
+            case K_AL: {
+                SEG(P.ws.ybuf, YLD, OUT, 0, tag_now);
+                // ctx = flash-style merge of the four quarter partials, built directly in fragment form.
+                // (rows >= B have no partials: their lanes feed zeros; the MMAs below are warp-collective,
+                //  so every lane runs the same loop.)
+                {
+                    const bool live = myrow < B;
+                    float w[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (live) {
+                        const uint64_t* ms = ws + P.ws.att_ms + rowoff * 8;
+                        float m[4], sq[4], M = -INFINITY;
+#pragma unroll
+                        for (int qd = 0; qd < 4; ++qd) {
+                            const float2 x = ll_wait2(ms + 2 * qd, tag_now);
+                            m[qd] = x.x; sq[qd] = x.y; M = fmaxf(M, x.x);
+                        }
+                        float S = 0.f;
+#pragma unroll
+                        for (int qd = 0; qd < 4; ++qd) { w[qd] = (m[qd] == -INFINITY) ? 0.f : __expf(m[qd] - M); S += w[qd] * sq[qd]; }
+                        const float inv = 1.0f / S;
+#pragma unroll
+                        for (int qd = 0; qd < 4; ++qd) w[qd] *= inv;
+                    }
+                    const uint64_t* cp = ws + P.ws.att_ctx + rowoff * 4 * ENC + 2 * tg;
+                    const int wt0 = OUT / 8;
+                    for (int kt = warp; kt < ENC / 8; kt += NWARP) {
+                        float xa = 0.f, xb = 0.f;
+                        if (live) {
+                            ulonglong2 v[4];
+#pragma unroll
+                            for (int qd = 0; qd < 4; ++qd) v[qd] = ll_load2(cp + qd * ENC + kt * 8);
+#pragma unroll
+                            for (int qd = 0; qd < 4; ++qd) {
+                                ll_spin(v[qd], cp + qd * ENC + kt * 8, tag_now);
+                                xa = fmaf(w[qd], __uint_as_float((uint32_t)v[qd].x), xa);
+                                xb = fmaf(w[qd], __uint_as_float((uint32_t)v[qd].y), xb);
+                            }
+                        }
+                        ktile_mma<1>(acc, xa, xb, Wsl + (size_t)(wt0 + kt) * 64 + lane * 2);
+                    }
+                }
+                // finalise this CTA's slice of the alignments: a_j = p_j * exp(m_q - M) / S
+                if (arow < B && tid < Tq) {
+                    const uint64_t* ms = ws + P.ws.att_ms + (int64_t)arow * 8;
+                    float m[4], sq[4], M = -INFINITY;
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd) {
+                        const float2 x = ll_wait2(ms + 2 * qd, tag_now);
+                        m[qd] = x.x; sq[qd] = x.y; M = fmaxf(M, x.x);
+                    }
+                    float S = 0.f;
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd) S += ((m[qd] == -INFINITY) ? 0.f : __expf(m[qd] - M)) * sq[qd];
+                    const float sc = ((m[aq] == -INFINITY) ? 0.f : __expf(m[aq] - M)) / S;
+                    const float* p_s = small_s + 512 + 64;
+                    A.align[((int64_t)arow * T + t) * Tx + aq * Tq + tid] = p_s[tid] * sc;
+                }
+            } break;
         }
-        // lane l ends up with the warp-wide sum of element l = 4*row + col
-        const float wsum = butterfly32(acc, lane);
-        part_s[warp * 32 + lane] = wsum;
+#undef SEG
+        // ---- per-warp partial tiles -> shared memory (rows 0..7 of the 16x8 accumulator are the real rows) ----
+        float* part = part_s + (sl & 1) * (NWARP * 128);
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+            if (nt < NT) *reinterpret_cast<float2*>(part + (warp * 2 + nt) * 64 + g * 8 + 2 * tg) = make_float2(acc[nt][0], acc[nt][1]);
         __syncthreads();
 
         // =============== cross-warp sum + stage epilogue: one thread per output ===============
-        if (tid < 32 * NQ) {
-            const int oq = tid >> 5, idx = tid & 31;
+        if (tid < 64 * NT) {
+            const int nt = tid >> 6, rr = (tid >> 3) & 7, c = tid & 7;
             float v = 0.f;
-            for (int k2 = 0; k2 < nkp; ++k2) v += part_s[(k2 * NQ + oq) * 32 + idx];
-            const int rr = idx >> 2;
-            const int j = oq * 4 + (idx & 3);                 // local column in the slice
+#pragma unroll
+            for (int w = 0; w < NWARP; ++w) v += part[(w * 2 + nt) * 64 + rr * 8 + c];
+            const int j = nt * 8 + c;                       // local column in the slice
             const int row = row0 + rr;
-            const int col = stage_col(s, cs, j, NC);
+            const int col = stage_col(s, cs, j, d.NCV, d.N);
             const int64_t ro = (int64_t)row;
-            switch (s) {
-                case K_P1: {
-                    v = fmaxf(v + __ldg(P.pre_b1 + col), 0.f);
-                    if (A.keep1 && row < B) v = A.keep1[((int64_t)t * B + row) * 256 + col] ? v * A.keep_scale : 0.f;
-                    ll_store(ws + P.ws.p1 + ro * 256 + col, v, tag_now);
-                } break;
-                case K_P2: {
-                    v = fmaxf(v + __ldg(P.pre_b2 + col), 0.f);
-                    if (A.keep2 && row < B) v = A.keep2[((int64_t)t * B + row) * 128 + col] ? v * A.keep_scale : 0.f;
-                    ll_store(ws + P.ws.p2 + ro * 128 + col, v, tag_now);
-                } break;
-                case K_IN: {
-                    v += __ldg(P.in_b + col);
-                    z_loc[rr * 8 + j] = v;
-                    ll_store(ws + P.ws.z + ro * U + col, v, tag_now);
-                } break;
-                case K_G1: case K_G2: case K_G3: {
-                    const int gi = (s - K_G1) / 2;
-                    const float g = sigmoidf_acc(v + __ldg(P.gru_bg[gi] + col));
-                    if (j < 8) ll_store(ws + P.ws.rh[gi] + ro * U + col, g * h_loc[gi * 64 + rr * 8 + j], tag_now);   // r * h
-                    else u_loc[rr * 8 + (j - 8)] = g;                                                                 // u stays local
-                } break;
-                case K_C1: case K_C2: case K_C3: {
-                    const int gi = (s - K_C1) / 2;
-                    const float c = tanhf_acc(v + __ldg(P.gru_bc[gi] + col));
-                    const float uu = u_loc[rr * 8 + j];
-                    const float hn = uu * h_loc[gi * 64 + rr * 8 + j] + (1.0f - uu) * c;
-                    h_loc[gi * 64 + rr * 8 + j] = hn;
-                    ll_store(ws + P.ws.h[gi] + ro * U + col, hn, tag_now);
-                    if (gi == 2) ll_store(ws + P.ws.s + ro * U + col, z_loc[rr * 8 + j] + hn, tag_now);
-                } break;
-                case K_OUT: {
-                    if (col < OUT) {
-                        const float y = v + __ldg(P.out_b + col);
-                        ll_store(ws + P.ws.ybuf + ro * YLD + col, y, tag_now);
-                        if (row < B) A.y[((int64_t)row * T + t) * OUT + col] = y;
-                    }
-                } break;
-                case K_Q: ll_store(ws + P.ws.q + ro * AU + col, v, tag_now); break;
-                case K_AL: ll_store(ws + P.ws.attn + ro * AU + col, v, tag_now); break;
+            v += bias_s[s * 16 + j];
+            if (col >= 0) {
+                switch (s) {
+                    case K_P1: {
+                        v = fmaxf(v, 0.f);
+                        if (A.keep1 && row < B && tb < T) v = A.keep1[((int64_t)tb * B + row) * 256 + col] ? v * A.keep_scale : 0.f;
+                        ll_store(ws + P.ws.p1 + ro * 256 + perm8(col), v, tag_out);
+                    } break;
+                    case K_P2: {
+                        v = fmaxf(v, 0.f);
+                        if (A.keep2 && row < B && tb < T) v = A.keep2[((int64_t)tb * B + row) * 128 + col] ? v * A.keep_scale : 0.f;
+                        ll_store(ws + P.ws.p2 + ro * 128 + perm8(col), v, tag_out);
+                    } break;
+                    case K_IN: {
+                        z_loc[rr * 8 + j] = v;
+                        ll_store(ws + P.ws.z + ro * U + perm8(col), v, tag_out);
+                    } break;
+                    case K_G1: case K_G2: case K_G3: {
+                        const int gi = (s - K_G1) / 2;
+                        const float gt = sigmoidf_acc(v);
+                        if (j < 8) ll_store(ws + P.ws.rh[gi] + ro * U + perm8(col), gt * h_loc[gi * 64 + rr * 8 + j], tag_out);   // r * h
+                        else u_loc[rr * 8 + (j - 8)] = gt;                                                                       // u stays local
+                    } break;
+                    case K_C1: case K_C2: case K_C3: {
+                        const int gi = (s - K_C1) / 2;
+                        const float cnd = tanhf_acc(v);
+                        const float uu = u_loc[rr * 8 + j];
+                        const float hn = uu * h_loc[gi * 64 + rr * 8 + j] + (1.0f - uu) * cnd;
+                        h_loc[gi * 64 + rr * 8 + j] = hn;
+                        ll_store(ws + P.ws.h[gi] + ro * U + perm8(col), hn, tag_out);
+                        if (gi == 2) ll_store(ws + P.ws.s + ro * U + perm8(col), z_loc[rr * 8 + j] + hn, tag_out);
+                    } break;
+                    case K_OUT: {
+                        ll_store(ws + P.ws.ybuf + ro * YLD + perm8(col), v, tag_out);
+                        if (row < B) A.y[((int64_t)row * T + t) * OUT + col] = v;
+                    } break;
+                    case K_Q: ll_store(ws + P.ws.q + ro * AU + perm8(col), v, tag_out); break;
+                    case K_AL: ll_store(ws + P.ws.attn + ro * AU + perm8(col), v, tag_out); break;
+                }
             }
         }
-        // u_loc / h_loc / z_loc / part_s / act_s hazards: the next stage's post-ingest __syncthreads orders them
+        // hazards: part_s alternates by slot parity; loc arrays are ordered by the next slot's __syncthreads
     }
 }
 
-// ---- packing: TF [K][N] -> per-slice [cs][i = k%4][cq][chunk = k/4][4 cols], optional gate permutation ----
-__global__ void pack_stage_kernel(const float* __restrict__ W, int K, int N, int NC, int kind, float* __restrict__ dst) {
-    const int NQ = NC / 4, NCH = K / 4;
-    const int64_t total = (int64_t)NS * K * NC;
+// ---- packing: TF [K][N] -> per-slice MMA B fragments [cs][k-tile][nt][lane][2], optional gate permutation ----
+__global__ void pack_stage_kernel(const float* __restrict__ W, int K, int N, int NCV, int NT, int kind, float* __restrict__ dst) {
+    const int KT = K / 8;
+    const int64_t total = (int64_t)NS * KT * NT * 64;
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int jj = (int)(idx % 4);
-        int64_t rest = idx / 4;
-        const int c = (int)(rest % NCH); rest /= NCH;
-        const int cq = (int)(rest % NQ); rest /= NQ;
-        const int i = (int)(rest % 4);
-        const int cs = (int)(rest / 4);
-        const int k = 4 * c + i;
-        const int col = stage_col(kind, cs, cq * 4 + jj, NC);
-        dst[idx] = (col < N) ? W[(int64_t)k * N + col] : 0.0f;
+        const int e = (int)(idx & 1);
+        const int lane = (int)((idx >> 1) & 31);
+        int64_t rest = idx >> 6;
+        const int nt = (int)(rest % NT); rest /= NT;
+        const int kt = (int)(rest % KT);
+        const int cs = (int)(rest / KT);
+        const int g = lane >> 2, tg = lane & 3;
+        const int k = kt * 8 + tg + 4 * e;                    // b0: k = tg, b1: k = tg + 4 ; column n = g
+        const int col = stage_col(kind, cs, nt * 8 + g, NCV, N);
+        dst[idx] = (col >= 0) ? W[(int64_t)k * N + col] : 0.0f;
     }
 }
 
@@ -572,10 +613,11 @@ void build_stage_table(int r, StageDesc* st, int64_t* total_floats) {
     const int OUT = MF * r;
     int64_t off = 0;
     for (int s = 0; s < NSTAGE; ++s) {
-        int K0, K1, N, NC;
-        stage_dims(s, OUT, K0, K1, N, NC);
-        st[s].K0 = K0; st[s].K1 = K1; st[s].N = N; st[s].NC = NC; st[s].w_off = off; st[s].res_off = -1;
-        off += (int64_t)NS * (K0 + K1) * NC;
+        int K0, K1, N, NCV;
+        stage_dims(s, OUT, K0, K1, N, NCV);
+        st[s].K0 = K0; st[s].K1 = K1; st[s].N = N; st[s].NCV = NCV; st[s].NT = (NCV + 7) / 8;
+        st[s].w_off = off; st[s].res_off = -1;
+        off += (int64_t)NS * (K0 + K1) * st[s].NT * 8;
     }
     *total_floats = off;
 }
@@ -616,9 +658,9 @@ extern "C" int taco_decoder_pack(const taco_decoder_weights* w, int r, float* pa
         if (s == K_ATT) continue;
         TACO_CHECK(src[s] != nullptr, "taco_decoder_pack: weight %d is NULL", s);
         const int K = st[s].K0 + st[s].K1;
-        const int64_t total = (int64_t)NS * K * st[s].NC;
+        const int64_t total = (int64_t)NS * K * st[s].NT * 8;
         const int blocks = (int)((total + 255) / 256);
-        pack_stage_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src[s], K, st[s].N, st[s].NC, s, packed + st[s].w_off);
+        pack_stage_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src[s], K, st[s].N, st[s].NCV, st[s].NT, s, packed + st[s].w_off);
         TACO_LAUNCH_CHECK();
     }
     return 0;
@@ -631,7 +673,7 @@ extern "C" int taco_decoder_fwd(const taco_decoder_args* a, void* stream) {
     TACO_CHECK(a->B >= 1 && a->B <= BPAD, "taco_decoder_fwd: B=%d must be in [1,%d] per launch", a->B, BPAD);
     TACO_CHECK(a->T >= 1, "taco_decoder_fwd: T=%d", a->T);
     TACO_CHECK(a->Tx >= 4 && (a->Tx % 4) == 0 && a->Tx <= 256, "taco_decoder_fwd: Tx=%d must be a multiple of 4, <= 256", a->Tx);
-    TACO_CHECK(a->r >= 1 && MF * a->r + ENC <= ACT_LD - 4, "taco_decoder_fwd: r=%d unsupported (80r + 256 must be <= %d)", a->r, ACT_LD - 4);
+    TACO_CHECK(a->r >= 1 && MF * a->r <= 512 - 8, "taco_decoder_fwd: r=%d unsupported (80r must be <= 504)", a->r);
     TACO_CHECK(a->packed && a->keys && a->values && a->text_length && a->y && a->align && a->workspace, "taco_decoder_fwd: NULL pointer");
     TACO_CHECK((reinterpret_cast<uintptr_t>(a->workspace) & 15) == 0, "taco_decoder_fwd: workspace must be 16-byte aligned");
     if (a->mode != TACO_DEC_INFER) TACO_CHECK(a->mel != nullptr, "taco_decoder_fwd: teacher/sched mode needs mel");
@@ -648,11 +690,12 @@ extern "C" int taco_decoder_fwd(const taco_decoder_args* a, void* stream) {
     P.OUT = MF * a->r;
     P.Tq = a->Tx / 4;
     TACO_CHECK(P.Tq <= 64, "taco_decoder_fwd: Tx/4 = %d > 64", P.Tq);
+    TACO_CHECK(P.OUT / 8 <= MAXT * NWARP, "taco_decoder_fwd: 80r too wide for the fragment pipeline");
     P.pre_b1 = g_dec_w.pre_b1; P.pre_b2 = g_dec_w.pre_b2; P.in_b = g_dec_w.in_b; P.out_b = g_dec_w.out_b; P.att_v = g_dec_w.att_v;
     for (int i = 0; i < 3; ++i) { P.gru_bg[i] = g_dec_w.gru_bg[i]; P.gru_bc[i] = g_dec_w.gru_bc[i]; }
 
     // shared-memory plan
-    int off = 64 + RPG * ACT_LD + 8 * 32 + 512 + 1024;
+    int off = 64 + 2 * NWARP * 128 + 512 + 256 + 1024;
     off = (off + 31) / 32 * 32;
     P.smem_kv_off = off;
     off += P.Tq * KV_LD + P.Tq * ENC;
@@ -663,15 +706,16 @@ extern "C" int taco_decoder_fwd(const taco_decoder_args* a, void* stream) {
     const int max_floats = (227 * 1024) / 4;
     const int budget = max_floats - off;
     // greedy residency: biggest per-step traffic first (GRU gates, candidates, attention layer, ...)
-    const int order[] = {K_G1, K_G2, K_G3, K_C1, K_C2, K_C3, K_AL, K_IN, K_OUT, K_Q, K_P1, K_P2};
+    const int order[] = {K_G1, K_G2, K_G3, K_C1, K_C2, K_C3, K_AL, K_IN, K_OUT, K_Q, K_P2, K_P1};
     int res = 0;
     for (int i = 0; i < 12; ++i) {
         StageDesc& d = P.st[order[i]];
-        const int fl = (d.K0 + d.K1) * d.NC;
+        const int fl = (d.K0 + d.K1) * d.NT * 8;
         if (fl <= budget - res) { d.res_off = res; res += fl; }
     }
     P.smem_total_floats = off + res;
     const size_t smem_bytes = (size_t)P.smem_total_floats * 4;
+    (void)h_order;
 
     static bool configured = false;
     if (!configured) {

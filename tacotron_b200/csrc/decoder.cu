@@ -39,6 +39,7 @@
 //   * attention: CTA (utterance, quarter of Tx) keeps its keys/values slice in shared memory for all
 //     steps; scores + partial softmax + partial context per quarter, flash-style merge by the consumer.
 //   * %globaltimer stamp per step for the decoder-step latency metric.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -122,10 +123,13 @@ __host__ __device__ inline int perm8(int k) {
 // ---------------------------------------------------------------------------------------------
 // LL words: {value, tag}
 // ---------------------------------------------------------------------------------------------
+// strong (relaxed, gpu-scope) accesses: the words are read by other CTAs while the kernel runs
 __device__ __forceinline__ void ll_store(uint64_t* p, float v, uint32_t tag) {
     const uint64_t w = (uint64_t)__float_as_uint(v) | ((uint64_t)tag << 32);
-    asm volatile("st.global.cg.b64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+    asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
+// polling load: ld.volatile measured 306 cycles per dependent L2 access on B200, ld.relaxed.gpu 467
+// (scripts/ubench/latency.cu); both always observe L2.
 __device__ __forceinline__ ulonglong2 ll_load2(const uint64_t* p) {
     ulonglong2 v;
     asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
@@ -151,10 +155,12 @@ __device__ __forceinline__ float2 ll_wait2(const uint64_t* p, uint32_t tag) {
 // ---------------------------------------------------------------------------------------------
 // 3xTF32 tensor-core contraction pieces
 // ---------------------------------------------------------------------------------------------
+// x = hi + lo with hi = the TF32-representable head (low 13 mantissa bits cleared) and lo = the exact
+// remainder (the tensor core ignores lo's own low 13 bits: <= 2^-21 |x| dropped).  Two instructions per
+// value; cvt.rna.tf32 expands to ~14 SASS instructions on sm_100 and made v3.0 conversion-bound.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-    const float r = x - __uint_as_float(hi);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
 }
 // D[16x8] += A[16x8] . B[8x8]; rows 8..15 of A are zero (a1 = a3 = 0)
 __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
@@ -163,45 +169,97 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a2
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
 }
-// one k-tile: A pair (x[g][8kt+tg], x[g][8kt+tg+4]) against NT weight tiles
+// one k-tile: A pair (x[g][8kt+tg], x[g][8kt+tg+4]) against NT weight tiles (B fragments w[nt]).
+// The three 3xTF32 products go to three independent accumulators so that consecutive MMAs do not
+// serialise on the accumulator latency; they are summed once per stage.
 template <int NT>
-__device__ __forceinline__ void ktile_mma(float (&acc)[2][4], float xa, float xb, const float* wfrag /* tile base + lane*2 */) {
+__device__ __forceinline__ void ktile_mma(float (&acc)[3][2][4], float xa, float xb, const float2 (&w)[NT]) {
     uint32_t ah0, al0, ah2, al2;
     split_tf32(xa, ah0, al0);
     split_tf32(xb, ah2, al2);
     __syncwarp();                                   // lanes may arrive from divergent polling loops
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) {
-        const float2 w = *reinterpret_cast<const float2*>(wfrag + nt * 64);
         uint32_t bh0, bl0, bh1, bl1;
-        split_tf32(w.x, bh0, bl0);
-        split_tf32(w.y, bh1, bl1);
-        mma_tf32(acc[nt], al0, al2, bh0, bh1);      // small terms first
-        mma_tf32(acc[nt], ah0, ah2, bl0, bl1);
-        mma_tf32(acc[nt], ah0, ah2, bh0, bh1);
+        split_tf32(w[nt].x, bh0, bl0);
+        split_tf32(w[nt].y, bh1, bl1);
+        mma_tf32(acc[0][nt], al0, al2, bh0, bh1);
+        mma_tf32(acc[1][nt], ah0, ah2, bl0, bl1);
+        mma_tf32(acc[2][nt], ah0, ah2, bh0, bh1);
     }
+}
+template <int NT>
+__device__ __forceinline__ void load_w(float2 (&w)[NT], const float* wfrag) {
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) w[nt] = *reinterpret_cast<const float2*>(wfrag + nt * 64);
 }
 
 // A segment of the K dimension whose activations live in an LL exchange buffer.
-//   buf: row pointer base (buffer + row*ld), ntiles = width/8, wt0 = first k-tile of the segment in the
-//   weight slice.  Warp w owns tiles w, w+8, ...  All loads are issued before the first tag check.
+//   rowp: buffer + row*ld, ntiles = width/8, wt0 = first k-tile of the segment in the weight slice.
+//   Warp w owns tiles w, w+8, ...  All LL loads and all weight-fragment loads are issued before the
+//   first tag check, so the only exposed latency is the arrival of the data itself.
 template <int NT>
-__device__ __forceinline__ void seg_ll(float (&acc)[2][4], const uint64_t* rowp, int ntiles, int wt0, uint32_t tag,
+__device__ __forceinline__ void seg_ll(float (&acc)[3][2][4], const uint64_t* rowp, int ntiles, int wt0, uint32_t tag,
                                        const float* Wsl, int warp, int lane) {
-    const int tg = lane & 3;
+    const uint64_t* p0 = rowp + warp * 8 + 2 * (lane & 3);
+    const float* w0 = Wsl + (size_t)(wt0 + warp) * NT * 64 + lane * 2;
     ulonglong2 v[MAXT];
 #pragma unroll
-    for (int i = 0; i < MAXT; ++i) {
-        const int kt = warp + NWARP * i;
-        if (kt < ntiles) v[i] = ll_load2(rowp + kt * 8 + 2 * tg);
-    }
+    for (int i = 0; i < MAXT; ++i)
+        if (warp + NWARP * i < ntiles) v[i] = ll_load2(p0 + i * (NWARP * 8));
 #pragma unroll
-    for (int i = 0; i < MAXT; ++i) {
-        const int kt = warp + NWARP * i;
-        if (kt < ntiles) {
-            ll_spin(v[i], rowp + kt * 8 + 2 * tg, tag);
-            ktile_mma<NT>(acc, __uint_as_float((uint32_t)v[i].x), __uint_as_float((uint32_t)v[i].y),
-                          Wsl + (size_t)(wt0 + kt) * NT * 64 + lane * 2);
+    for (int h = 0; h < MAXT; h += 4) {                 // weight fragments four tiles at a time (register budget)
+        float2 wf[4][NT];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (warp + NWARP * (h + i) < ntiles) load_w<NT>(wf[i], w0 + (size_t)(h + i) * (NWARP * NT * 64));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (warp + NWARP * (h + i) < ntiles) {
+                ll_spin(v[h + i], p0 + (h + i) * (NWARP * 8), tag);
+                ktile_mma<NT>(acc, __uint_as_float((uint32_t)v[h + i].x), __uint_as_float((uint32_t)v[h + i].y), wf[i]);
+            }
+        }
+    }
+}
+
+// Two segments at once (each <= 32 k-tiles, i.e. <= 4 per warp): all eight LL loads are in flight before
+// the first tag check, so a two-source stage exposes ONE L2 latency instead of two.
+template <int NT>
+__device__ __forceinline__ void seg2_ll(float (&acc)[3][2][4], const uint64_t* rowA, int ntA, int w0A, uint32_t tagA,
+                                        const uint64_t* rowB, int ntB, int w0B, uint32_t tagB, const float* Wsl, int warp, int lane) {
+    const int tg2 = 2 * (lane & 3);
+    const uint64_t* pA = rowA + warp * 8 + tg2;
+    const uint64_t* pB = rowB + warp * 8 + tg2;
+    const float* wA = Wsl + (size_t)(w0A + warp) * NT * 64 + lane * 2;
+    const float* wB = Wsl + (size_t)(w0B + warp) * NT * 64 + lane * 2;
+    ulonglong2 va[4], vb[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (warp + NWARP * i < ntA) va[i] = ll_load2(pA + i * (NWARP * 8));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (warp + NWARP * i < ntB) vb[i] = ll_load2(pB + i * (NWARP * 8));
+    {
+        float2 wf[4][NT];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (warp + NWARP * i < ntA) load_w<NT>(wf[i], wA + (size_t)i * (NWARP * NT * 64));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (warp + NWARP * i < ntA) {
+                ll_spin(va[i], pA + i * (NWARP * 8), tagA);
+                ktile_mma<NT>(acc, __uint_as_float((uint32_t)va[i].x), __uint_as_float((uint32_t)va[i].y), wf[i]);
+            }
+        }
+    }
+    {
+        float2 wf[4][NT];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (warp + NWARP * i < ntB) load_w<NT>(wf[i], wB + (size_t)i * (NWARP * NT * 64));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (warp + NWARP * i < ntB) {
+                ll_spin(vb[i], pB + i * (NWARP * 8), tagB);
+                ktile_mma<NT>(acc, __uint_as_float((uint32_t)vb[i].x), __uint_as_float((uint32_t)vb[i].y), wf[i]);
+            }
         }
     }
 }
@@ -329,7 +387,14 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
         const int tb = (s == K_P1 || s == K_P2) ? t + 1 : t;      // decoder step the OUTPUT of this slot belongs to
         const uint32_t tag_out = (uint32_t)tb + 1;                // tag of everything produced for step tb
         pump();
-        if (s == K_IN && cta == 0 && tid == 0 && A.step_ns) A.step_ns[t] = globaltimer_ns();
+        if (cta == 0 && tid == 0 && A.step_ns) {
+            const uint64_t now = globaltimer_ns();
+            if (s == K_IN) A.step_ns[t] = now;
+            ws[P.ws.total + sl] = now;                   // per-slot trace (debug / profiling): [2 + 13 T] stamps after the LL buffers
+        }
+        const bool tracer = (cta == 0 && tid == 0 && A.step_ns != nullptr);
+        uint64_t* ctrace = ws + P.ws.total + total_slots + 16 + (int64_t)sl * 4;   // clock64 at 4 points of the slot (CTA 0, thread 0)
+        if (tracer) ctrace[0] = (uint64_t)clock64();
 
         if (s == K_ATT) {
             // =============== attention scores / partial softmax / partial context ===============
@@ -413,43 +478,31 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
             ++n_consumed;
         }
 
-        float acc[2][4];
+        float acc[3][2][4];
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
+        for (int a3 = 0; a3 < 3; ++a3)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[a3][i][j] = 0.f;
 
         const uint32_t tag_now = (uint32_t)t + 1;      // values produced during step t
         const uint32_t tag_prev = (uint32_t)t;         // values produced during step t-1 (t = 0: initial zeros -> skipped)
         const int64_t rowoff = (int64_t)myrow;
+        // Segment descriptors first, ONE generic execution loop after: keeps the hot code small (the v3.0
+        // kernel inlined ~28 copies of the fragment pipeline, 164 KB of SASS, and thrashed the 32 KB
+        // instruction cache on every slot).
+        const uint64_t* sgA = nullptr; const uint64_t* sgB = nullptr;
+        int ntA = 0, ntB = 0, w0A = 0, w0B = 0, nsg = 0;
+        uint32_t tgA = 0, tgB = 0;
 #define SEG(bufoff, ld, width, wt0, tag)                                                              \
         do {                                                                                          \
-            if (NT == 2) seg_ll<2>(acc, ws + (bufoff) + rowoff * (ld), (width) / 8, (wt0), (tag), Wsl, warp, lane); \
-            else         seg_ll<1>(acc, ws + (bufoff) + rowoff * (ld), (width) / 8, (wt0), (tag), Wsl, warp, lane); \
+            if (nsg == 0) { sgA = ws + (bufoff) + rowoff * (ld); ntA = (width) / 8; w0A = (wt0); tgA = (tag); } \
+            else          { sgB = ws + (bufoff) + rowoff * (ld); ntB = (width) / 8; w0B = (wt0); tgB = (tag); } \
+            ++nsg;                                                                                    \
         } while (0)
 
         switch (s) {
-            case K_P1: {
-                // decoder input of step tb: last mel frame of the r-group (tacotron.py:66-67; helpers A.8-A.10)
-                //   INFER: y(tb-1) (zeros for tb = 0); TEACHER: mel[:, tb]; SCHED: per row, mask[tb-1] ? y(tb-1) : mel[:, tb]
-                bool from_y = true;
-                if (A.mode == TACO_DEC_TEACHER) from_y = false;
-                else if (A.mode == TACO_DEC_SCHED) from_y = (tb > 0) && (myrow < B) && (A.sample_mask[(int64_t)(tb - 1) * B + myrow] != 0);
-                const bool have = (myrow < B) && (tb < T) && (from_y ? (tb > 0) : true);
-                for (int kt = warp; kt < MF / 8; kt += NWARP) {
-                    float xa = 0.f, xb = 0.f;
-                    if (have) {
-                        if (from_y) {
-                            const float2 v = ll_wait2(ws + P.ws.ybuf + rowoff * YLD + (OUT - MF) + kt * 8 + 2 * tg, (uint32_t)tb);
-                            xa = v.x; xb = v.y;
-                        } else {
-                            const float* mp = A.mel + ((int64_t)myrow * T + tb) * OUT + (OUT - MF) + kt * 8 + tg;
-                            xa = __ldg(mp); xb = __ldg(mp + 4);
-                        }
-                    }
-                    ktile_mma<1>(acc, xa, xb, Wsl + (size_t)kt * 64 + lane * 2);
-                }
-            } break;
             case K_P2: SEG(P.ws.p1, 256, 256, 0, tag_out); break;
             case K_IN:
                 SEG(P.ws.p2, 128, 128, 0, tag_now);
@@ -469,8 +522,40 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
             } break;
             case K_OUT: SEG(P.ws.s, U, U, 0, tag_now); break;
             case K_Q: SEG(P.ws.ybuf, YLD, OUT, 0, tag_now); break;
-            case K_AL: {
-                SEG(P.ws.ybuf, YLD, OUT, 0, tag_now);
+            case K_AL: SEG(P.ws.ybuf, YLD, OUT, 0, tag_now); break;
+            default: break;
+        }
+#undef SEG
+        if (nsg == 2) {
+            if (NT == 2) seg2_ll<2>(acc, sgA, ntA, w0A, tgA, sgB, ntB, w0B, tgB, Wsl, warp, lane);
+            else         seg2_ll<1>(acc, sgA, ntA, w0A, tgA, sgB, ntB, w0B, tgB, Wsl, warp, lane);
+        } else if (nsg == 1) {
+            if (NT == 2) seg_ll<2>(acc, sgA, ntA, w0A, tgA, Wsl, warp, lane);
+            else         seg_ll<1>(acc, sgA, ntA, w0A, tgA, Wsl, warp, lane);
+        }
+        if (s == K_P1) {
+                // decoder input of step tb: last mel frame of the r-group (tacotron.py:66-67; helpers A.8-A.10)
+                //   INFER: y(tb-1) (zeros for tb = 0); TEACHER: mel[:, tb]; SCHED: per row, mask[tb-1] ? y(tb-1) : mel[:, tb]
+                bool from_y = true;
+                if (A.mode == TACO_DEC_TEACHER) from_y = false;
+                else if (A.mode == TACO_DEC_SCHED) from_y = (tb > 0) && (myrow < B) && (A.sample_mask[(int64_t)(tb - 1) * B + myrow] != 0);
+                const bool have = (myrow < B) && (tb < T) && (from_y ? (tb > 0) : true);
+                for (int kt = warp; kt < MF / 8; kt += NWARP) {
+                    float xa = 0.f, xb = 0.f;
+                    if (have) {
+                        if (from_y) {
+                            const float2 v = ll_wait2(ws + P.ws.ybuf + rowoff * YLD + (OUT - MF) + kt * 8 + 2 * tg, (uint32_t)tb);
+                            xa = v.x; xb = v.y;
+                        } else {
+                            const float* mp = A.mel + ((int64_t)myrow * T + tb) * OUT + (OUT - MF) + kt * 8 + tg;
+                            xa = __ldg(mp); xb = __ldg(mp + 4);
+                        }
+                    }
+                    float2 wf1[1];
+                    load_w<1>(wf1, Wsl + (size_t)kt * 64 + lane * 2);
+                    ktile_mma<1>(acc, xa, xb, wf1);
+                }
+        } else if (s == K_AL) {
                 // ctx = flash-style merge of the four quarter partials, built directly in fragment form.
                 // (rows >= B have no partials: their lanes feed zeros; the MMAs below are warp-collective,
                 //  so every lane runs the same loop.)
@@ -480,10 +565,13 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
                     if (live) {
                         const uint64_t* ms = ws + P.ws.att_ms + rowoff * 8;
                         float m[4], sq[4], M = -INFINITY;
+                        ulonglong2 mv[4];
+#pragma unroll
+                        for (int qd = 0; qd < 4; ++qd) mv[qd] = ll_load2(ms + 2 * qd);
 #pragma unroll
                         for (int qd = 0; qd < 4; ++qd) {
-                            const float2 x = ll_wait2(ms + 2 * qd, tag_now);
-                            m[qd] = x.x; sq[qd] = x.y; M = fmaxf(M, x.x);
+                            ll_spin(mv[qd], ms + 2 * qd, tag_now);
+                            m[qd] = __uint_as_float((uint32_t)mv[qd].x); sq[qd] = __uint_as_float((uint32_t)mv[qd].y); M = fmaxf(M, m[qd]);
                         }
                         float S = 0.f;
 #pragma unroll
@@ -492,22 +580,34 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
 #pragma unroll
                         for (int qd = 0; qd < 4; ++qd) w[qd] *= inv;
                     }
-                    const uint64_t* cp = ws + P.ws.att_ctx + rowoff * 4 * ENC + 2 * tg;
-                    const int wt0 = OUT / 8;
-                    for (int kt = warp; kt < ENC / 8; kt += NWARP) {
-                        float xa = 0.f, xb = 0.f;
-                        if (live) {
-                            ulonglong2 v[4];
+                    const uint64_t* cp = ws + P.ws.att_ctx + rowoff * 4 * ENC + 2 * tg + warp * 8;
+                    const float* wq = Wsl + (size_t)(OUT / 8 + warp) * 64 + lane * 2;
+                    // this warp's 4 ctx tiles (kt = warp + 8i), two at a time: 8 partial loads in flight
 #pragma unroll
-                            for (int qd = 0; qd < 4; ++qd) v[qd] = ll_load2(cp + qd * ENC + kt * 8);
+                    for (int ip = 0; ip < (ENC / 8) / NWARP; ip += 2) {
+                        ulonglong2 v[2][4];
+                        float2 wf1[2][1];
 #pragma unroll
-                            for (int qd = 0; qd < 4; ++qd) {
-                                ll_spin(v[qd], cp + qd * ENC + kt * 8, tag_now);
-                                xa = fmaf(w[qd], __uint_as_float((uint32_t)v[qd].x), xa);
-                                xb = fmaf(w[qd], __uint_as_float((uint32_t)v[qd].y), xb);
+                        for (int u = 0; u < 2; ++u) {
+                            load_w<1>(wf1[u], wq + (size_t)(ip + u) * (NWARP * 64));
+                            if (live) {
+#pragma unroll
+                                for (int qd = 0; qd < 4; ++qd) v[u][qd] = ll_load2(cp + qd * ENC + (ip + u) * (NWARP * 8));
                             }
                         }
-                        ktile_mma<1>(acc, xa, xb, Wsl + (size_t)(wt0 + kt) * 64 + lane * 2);
+#pragma unroll
+                        for (int u = 0; u < 2; ++u) {
+                            float xa = 0.f, xb = 0.f;
+                            if (live) {
+#pragma unroll
+                                for (int qd = 0; qd < 4; ++qd) {
+                                    ll_spin(v[u][qd], cp + qd * ENC + (ip + u) * (NWARP * 8), tag_now);
+                                    xa = fmaf(w[qd], __uint_as_float((uint32_t)v[u][qd].x), xa);
+                                    xb = fmaf(w[qd], __uint_as_float((uint32_t)v[u][qd].y), xb);
+                                }
+                            }
+                            ktile_mma<1>(acc, xa, xb, wf1[u]);
+                        }
                     }
                 }
                 // finalise this CTA's slice of the alignments: a_j = p_j * exp(m_q - M) / S
@@ -526,15 +626,16 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
                     const float* p_s = small_s + 512 + 64;
                     A.align[((int64_t)arow * T + t) * Tx + aq * Tq + tid] = p_s[tid] * sc;
                 }
-            } break;
         }
-#undef SEG
+        if (tracer) ctrace[1] = (uint64_t)clock64();
         // ---- per-warp partial tiles -> shared memory (rows 0..7 of the 16x8 accumulator are the real rows) ----
         float* part = part_s + (sl & 1) * (NWARP * 128);
 #pragma unroll
         for (int nt = 0; nt < 2; ++nt)
-            if (nt < NT) *reinterpret_cast<float2*>(part + (warp * 2 + nt) * 64 + g * 8 + 2 * tg) = make_float2(acc[nt][0], acc[nt][1]);
+            if (nt < NT) *reinterpret_cast<float2*>(part + (warp * 2 + nt) * 64 + g * 8 + 2 * tg) =
+                make_float2((acc[0][nt][0] + acc[1][nt][0]) + acc[2][nt][0], (acc[0][nt][1] + acc[1][nt][1]) + acc[2][nt][1]);
         __syncthreads();
+        if (tracer) ctrace[2] = (uint64_t)clock64();
 
         // =============== cross-warp sum + stage epilogue: one thread per output ===============
         if (tid < 64 * NT) {
@@ -587,6 +688,7 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
                 }
             }
         }
+        if (tracer) ctrace[3] = (uint64_t)clock64();
         // hazards: part_s alternates by slot parity; loc arrays are ordered by the next slot's __syncthreads
     }
 }
@@ -642,9 +744,9 @@ extern "C" size_t taco_decoder_packed_bytes(int r) {
 }
 
 extern "C" size_t taco_decoder_workspace_bytes(int B, int Tx, int T, int r) {
-    (void)B; (void)Tx; (void)T; (void)r;
+    (void)B; (void)Tx; (void)r;
     DecLayout L; build_ws_layout(&L);
-    return (size_t)L.total * 8;
+    return (size_t)(L.total + 5 * (2 + (int64_t)NSTAGE * (T > 0 ? T : 0)) + 32) * 8;
 }
 
 extern "C" int taco_decoder_pack(const taco_decoder_weights* w, int r, float* packed, void* stream) {

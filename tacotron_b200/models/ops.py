@@ -414,6 +414,7 @@ def attention_decoder(encoded, text_length, r, T, mode=L.DEC_INFER, mel=None, sa
         return dst
     packed = rt.get(("dec_pack", sc.prefix, r), build_pack)
     ws = rt.buf(sc.name("dec_ws"), (lib.taco_decoder_workspace_bytes(32, Tx, T, r) // 4,))
+    rt.dec_ws = ws                                               # (per-slot time stamps live in its tail; see decoder.cu)
     ks = 1.0 / (1.0 - dropout)
     for b0 in range(0, B, 32):                                   # the kernel handles <= 32 utterances per launch
         nb = min(32, B - b0)

@@ -45,6 +45,8 @@ class Config(object):
     # B200 path: 'tf32' = tcgen05 tensor cores (TF32 multiplies, fp32 accumulate) for the feed
     # forward contractions; 'fp32' = exact fp32 FFMA everywhere.  Recurrent kernels are fp32 in both.
     precision = "tf32"
+    # replay inference-mode calls from CUDA graphs (captured per input shape)
+    cuda_graph = False
 
     def __init__(self, **kw):
         for k, v in kw.items():
@@ -71,6 +73,8 @@ class Tacotron(object):
         self.global_step = 0
         self.seq2seq_output = self.output = self.alignments = self.loss = None
         self.step_ns = None
+        self.section_wait = None
+        self.last_graph_kernels = 0                # kernels inside the CUDA graphs replayed by the last call
         self._marks = None                        # bench.py: list of (name, cuda event) section boundaries
         if inputs is not None:
             self(inputs)
@@ -128,28 +132,21 @@ class Tacotron(object):
         return run
 
     # -- inference (tacotron.py:107-154) --------------------------------------------------------
-    def inference(self, inputs, train=True, T=None, enc_drop_masks=None, dec_drop_masks=None, sample_mask=None,
-                  trace=None):
-        """inputs: dict of CUDA tensors: 'text' int32 [B,Tx], 'text_length' int32 [B]; train adds
-        'mel' fp32 [B,T,80r] (and 'stft' for the loss).  Returns (seq2seq_output, output)."""
-        cfg = self.config
-        text = inputs["text"]
-        assert text.dtype == torch.int32 and text.is_cuda and text.is_contiguous()
-        B, Tx = text.shape
-        if Tx % 4 != 0:
-            raise ValueError(f"text width {Tx} must be a multiple of 4 (pad like the reference does: data_input.py:97-99)")
-        store = self.store
-        self._mark("start")
+    def _encoder(self, inputs, train, enc_drop_masks, trace):
+        cfg, store = self.config, self.store
         # embedding lookup fused with the first pre-net layer (tacotron.py:111-114, :128)
         with ops.variable_scope(store, "enc"):
             pre_out = self.pre_net(store["embedding"], dropout=cfg.char_dropout_prob, train=train, masks=enc_drop_masks,
-                                   ids=text)
+                                   ids=inputs["text"])
             encoded = ops.CBHG(pre_out, None, K=16, c=[128, 128, 128], gru_units=128, trace=trace)      # :131
-        self._mark("encoder")
-        # attention decoder (:135-138)
-        dec = self.create_decoder(encoded, inputs, None, train, T=T, dec_drop_masks=dec_drop_masks, sample_mask=sample_mask)
-        seq2seq_output, self.alignments = dec()
-        self._mark("decoder")
+        if trace is not None:
+            trace["enc/prenet_out"] = pre_out
+            trace["encoded"] = encoded
+        return encoded
+
+    def _postnet(self, seq2seq_output, trace):
+        cfg, store = self.config, self.store
+        B = seq2seq_output.shape[0]
         # post-processing CBHG + linear-spectrogram dense (:144-151); the reshapes are views
         with ops.variable_scope(store, "post"):
             post_input = seq2seq_output.view(B, -1, cfg.mel_features)
@@ -158,12 +155,83 @@ class Tacotron(object):
             rt = self.runtime
             dense = ops.linear(rt, post, W, ops.packed_weight(rt, "post/dense/W", W, 1, 256, cfg.fft_size), cfg.fft_size,
                                bias=b, tag="post/dense/out")
-        output = dense.view(B, -1, cfg.fft_size * cfg.r)
+        return dense.view(B, -1, cfg.fft_size * cfg.r)
+
+    def inference(self, inputs, train=True, T=None, enc_drop_masks=None, dec_drop_masks=None, sample_mask=None,
+                  trace=None):
+        """inputs: dict of CUDA tensors: 'text' int32 [B,Tx], 'text_length' int32 [B]; train adds
+        'mel' fp32 [B,T,80r] (and 'stft' for the loss).  Returns (seq2seq_output, output).
+        With config.cuda_graph the three sections (encoder / decoder / post-net) of an inference-mode call are
+        captured once per input shape and replayed: ~26 launches collapse into 3 graph launches."""
+        text = inputs["text"]
+        assert text.dtype == torch.int32 and text.is_cuda and text.is_contiguous()
+        B, Tx = text.shape
+        if Tx % 4 != 0:
+            raise ValueError(f"text width {Tx} must be a multiple of 4 (pad like the reference does: data_input.py:97-99)")
+        if getattr(self.config, "cuda_graph", False) and not train and trace is None:
+            return self._inference_graphed(inputs, T)
+        self._mark("start")
+        encoded = self._encoder(inputs, train, enc_drop_masks, trace)
+        self._mark("encoder")
+        # attention decoder (:135-138)
+        dec = self.create_decoder(encoded, inputs, None, train, T=T, dec_drop_masks=dec_drop_masks, sample_mask=sample_mask)
+        seq2seq_output, self.alignments = dec()
+        self._mark("decoder")
+        output = self._postnet(seq2seq_output, trace)
         self._mark("postnet")
-        if trace is not None:
-            trace["enc/prenet_out"] = pre_out
-            trace["encoded"] = encoded
         return seq2seq_output, output
+
+    def _inference_graphed(self, inputs, T):
+        T = self.config.max_decode_iter if T is None else T
+        key = (tuple(inputs["text"].shape), T, self.store.version)
+        g = self._graphs.get(key) if hasattr(self, "_graphs") else None
+        if g is None:
+            if not hasattr(self, "_graphs"):
+                self._graphs = {}
+            static = {"text": inputs["text"].clone(), "text_length": inputs["text_length"].clone()}
+            marks, self._marks = self._marks, None
+            cg_flag, self.config.cuda_graph = self.config.cuda_graph, False
+            try:
+                for _ in range(2):                                  # eager warm-up: allocates every scratch buffer, packs weights
+                    self.inference(static, train=False, T=T)
+                torch.cuda.synchronize()
+                graphs, outs = [], {}
+                n_launch0 = L.lib().taco_launch_count()
+                pool = torch.cuda.graph_pool_handle()
+                ge = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(ge, pool=pool):
+                    outs["encoded"] = self._encoder(static, False, None, None)
+                gd = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gd, pool=pool):
+                    dec = self.create_decoder(outs["encoded"], static, None, False, T=T)
+                    outs["y"], outs["align"] = dec()
+                gp = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gp, pool=pool):
+                    outs["out"] = self._postnet(outs["y"], None)
+                graphs = [ge, gd, gp]
+            finally:
+                self._marks = marks
+                self.config.cuda_graph = cg_flag
+            g = (static, graphs, outs, int(L.lib().taco_launch_count() - n_launch0))
+            self._graphs[key] = g
+        static, graphs, outs, _ = g
+        static["text"].copy_(inputs["text"], non_blocking=True)
+        static["text_length"].copy_(inputs["text_length"], non_blocking=True)
+        # optional events a pipelined caller sets so that a section does not overwrite a result buffer that an
+        # asynchronous device->host copy of the PREVIOUS call is still reading (bench.py e2e)
+        waits = getattr(self, "section_wait", None) or {}
+        cur = torch.cuda.current_stream()
+        self._mark("start")
+        graphs[0].replay(); self._mark("encoder")
+        if waits.get("decoder") is not None:
+            cur.wait_event(waits["decoder"])
+        graphs[1].replay(); self._mark("decoder")
+        if waits.get("postnet") is not None:
+            cur.wait_event(waits["postnet"])
+        graphs[2].replay(); self._mark("postnet")
+        self.alignments = outs["align"]
+        self.last_graph_kernels = g[3]
+        return outs["y"], outs["out"]
 
     # -- add_loss_op (tacotron.py:156-165) -------------------------------------------------------
     def add_loss_op(self, seq2seq_output, output, mel, linear):

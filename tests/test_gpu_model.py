@@ -112,3 +112,25 @@ def test_properties_at_full_size():
     tl = ci["text_length"]
     pad = torch.arange(128, device="cuda")[None, None, :] >= tl[:, None, None]
     assert float((al * pad).abs().max()) == 0.0
+
+
+def test_cuda_graph_replay_matches_eager():
+    cfg = ocfg(r=5, T=20)
+    p = O.init_params(cfg, seed=3, trained_like=True)
+    inp = O.synthetic_inputs(cfg, 8, 32, 20, seed=2, ragged=True, with_targets=False)
+    m = make_model(cfg, p, "tf32")
+    ci = to_cuda(inp)
+    y, out = m.inference(ci, train=False)
+    y = y.clone(); out = out.clone(); al = m.alignments.clone()
+    m.config.cuda_graph = True
+    for _ in range(2):
+        y2, out2 = m.inference(ci, train=False)
+    torch.cuda.synchronize()
+    assert torch.equal(y, y2) and torch.equal(out, out2) and torch.equal(al, m.alignments)
+    # a second batch through the same graphs
+    inp2 = O.synthetic_inputs(cfg, 8, 32, 20, seed=5, ragged=True, with_targets=False)
+    y_ref, out_ref, _ = O.inference(p, inp2, cfg, train=False)
+    y3, out3 = m.inference(to_cuda(inp2), train=False)
+    torch.cuda.synchronize()
+    assert_close(y3, y_ref, TOL["tf32"], "graph y")
+    assert_close(out3, out_ref, TOL["tf32"], "graph out")

@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         float* my_scr = scratch_base + q * (MODE == 1 ? 2 : 1) * SCR;
         const int64_t seq_row0 = (int64_t)b * a.T;
         constexpr int NCHUNK = (MODE == 1) ? (BN / 2) / 32 : BN / 32;
+        constexpr int EPB = (MODE == 1) ? 8 : 16;     // epilogue rows per load batch (independent global loads in flight per lane)
 
         for (int ch = 0; ch < NCHUNK; ++ch) {
             uint32_t v[32];
@@ -192,13 +193,13 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                 const int U = BN / 2;
                 const float bH = a.e.bias ? __ldg(a.e.bias + col) : 0.f;
                 const float bT = a.e.bias ? __ldg(a.e.bias + U + col) : 0.f;
-                for (int rr0 = 0; rr0 < nrows; rr0 += 8) {
-                    float xin[8];
+                for (int rr0 = 0; rr0 < nrows; rr0 += EPB) {
+                    float xin[EPB];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
+                    for (int i = 0; i < EPB; ++i)
                         xin[i] = (rr0 + i < nrows) ? __ldg(a.e.hx + (row0 + rr0 + i) * a.e.ldhx + col) : 0.f;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < EPB; ++i) {
                         if (rr0 + i < nrows) {
                             const float H = fmaxf(my_scr[(rr0 + i) * 33 + lane] + bH, 0.f);
                             const float Tg = sigmoidf_acc(my_scr[SCR + (rr0 + i) * 33 + lane] + bT);
@@ -215,17 +216,17 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                 auto affine = [&](float v) { return apply_act(v + cb, act) * csc + csh; };
                 if (!a.pool) {
                     if (cvalid) {
-                        for (int rr0 = 0; rr0 < nrows; rr0 += 8) {
-                            float res[8];
-                            float kp[8];
+                        for (int rr0 = 0; rr0 < nrows; rr0 += EPB) {
+                            float res[EPB];
+                            float kp[EPB];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
+                            for (int i = 0; i < EPB; ++i) {
                                 const bool ok = rr0 + i < nrows;
                                 res[i] = (ok && a.e.residual) ? __ldg(a.e.residual + (row0 + rr0 + i) * a.e.ldr + col) : 0.f;
                                 kp[i] = (ok && a.e.keep) ? (a.e.keep[(row0 + rr0 + i) * (int64_t)a.e.N + col] ? a.e.keep_scale : 0.f) : 1.f;
                             }
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
+                            for (int i = 0; i < EPB; ++i) {
                                 if (rr0 + i < nrows)
                                     a.e.Y[(row0 + rr0 + i) * a.e.ldy + col] = affine(my_scr[(rr0 + i) * 33 + lane]) * kp[i] + res[i];
                             }

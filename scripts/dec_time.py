@@ -37,3 +37,10 @@ if os.environ.get("TACO_TRACE"):
     print("cycles (inputs+mma | barrier | epilogue | to-next):")
     for i, n_ in enumerate(names):
         print(f"  {n_:4s} {int(np.median(seg[:, i, 0])):6d} {int(np.median(seg[:, i, 1])):6d} {int(np.median(seg[:, i, 2])):6d} {int(np.median(nxt[:-1, i])):6d}")
+
+    if os.environ.get("TACO_AL"):
+        ckr = ws[total + n + 16: total + n + 16 + 4 * n].reshape(n, 4)[2:]
+        ckr = ckr[: (len(ckr) // 13) * 13].reshape(-1, 13, 4)[5:-1]
+        att, al = ckr[:, 11], ckr[:, 12]
+        print("AL breakdown (cycles): yseg", int(np.median(att[:, 1] - al[:, 0])), "ms-wait", int(np.median(att[:, 2] - att[:, 1])),
+              "ctx-loop", int(np.median(att[:, 3] - att[:, 2])), "finalize+rest", int(np.median(al[:, 1] - att[:, 3])))

@@ -612,20 +612,25 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
                     }
                 }
                 // finalise this CTA's slice of the alignments: a_j = p_j * exp(m_q - M) / S
-                if (arow < B && tid < Tq) {
+                // (done by the last two warps, which own the fewest k-tiles of this stage; the four loads are issued together)
+                if (arow < B && tid >= NTHR - 64 && tid - (NTHR - 64) < Tq) {
+                    const int j = tid - (NTHR - 64);
                     const uint64_t* ms = ws + P.ws.att_ms + (int64_t)arow * 8;
+                    ulonglong2 mv[4];
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd) mv[qd] = ll_load2(ms + 2 * qd);
                     float m[4], sq[4], M = -INFINITY;
 #pragma unroll
                     for (int qd = 0; qd < 4; ++qd) {
-                        const float2 x = ll_wait2(ms + 2 * qd, tag_now);
-                        m[qd] = x.x; sq[qd] = x.y; M = fmaxf(M, x.x);
+                        ll_spin(mv[qd], ms + 2 * qd, tag_now);
+                        m[qd] = __uint_as_float((uint32_t)mv[qd].x); sq[qd] = __uint_as_float((uint32_t)mv[qd].y); M = fmaxf(M, m[qd]);
                     }
                     float S = 0.f;
 #pragma unroll
                     for (int qd = 0; qd < 4; ++qd) S += ((m[qd] == -INFINITY) ? 0.f : __expf(m[qd] - M)) * sq[qd];
                     const float sc = ((m[aq] == -INFINITY) ? 0.f : __expf(m[aq] - M)) / S;
                     const float* p_s = small_s + 512 + 64;
-                    A.align[((int64_t)arow * T + t) * Tx + aq * Tq + tid] = p_s[tid] * sc;
+                    A.align[((int64_t)arow * T + t) * Tx + aq * Tq + j] = p_s[j] * sc;
                 }
         }
         if (tracer) ctrace[1] = (uint64_t)clock64();

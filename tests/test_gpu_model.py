@@ -134,3 +134,29 @@ def test_cuda_graph_replay_matches_eager():
     torch.cuda.synchronize()
     assert_close(y3, y_ref, TOL["tf32"], "graph y")
     assert_close(out3, out_ref, TOL["tf32"], "graph out")
+
+
+@pytest.mark.parametrize("B,Tx,T,r", [(1, 140, 100, 5), (4, 128, 72, 5), (1, 4, 1, 2), (33, 8, 3, 2)])
+def test_shape_edge_cases(B, Tx, T, r):
+    """BASELINE config 5 (B=1, prompt padded to 140, 500 frames) and config 1 (B=4, T=72) shapes, the smallest
+    legal shapes, and a batch that needs two decoder launches (B=33 > 32)."""
+    cfg = ocfg(r=r, T=T, vocab=30)
+    p = O.init_params(cfg, seed=2, trained_like=True)
+    inp = O.synthetic_inputs(cfg, B, Tx, T, seed=B, ragged=Tx >= 8, with_targets=False)
+    y_ref, out_ref, a_ref = O.inference(p, inp, cfg, train=False)
+    m = make_model(cfg, p, "fp32")
+    y, out = m.inference(to_cuda(inp), train=False)
+    torch.cuda.synchronize()
+    assert_close(y, y_ref, TOL["fp32"], "y")
+    assert_close(out, out_ref, TOL["fp32"], "out")
+    assert_close(m.alignments, a_ref, TOL["fp32"], "align")
+
+
+def test_bad_inputs_raise():
+    cfg = ocfg(r=2, T=4, vocab=30)
+    m = make_model(cfg, O.init_params(cfg, seed=2), "tf32")
+    bad = {"text": torch.ones(2, 6, dtype=torch.int32, device="cuda"), "text_length": torch.full((2,), 6, dtype=torch.int32, device="cuda")}
+    with pytest.raises(ValueError):
+        m.inference(bad, train=False)                      # width not a multiple of 4
+    with pytest.raises(NotImplementedError):
+        m.add_train_op(None)

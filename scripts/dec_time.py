@@ -22,25 +22,21 @@ print("LL mode", os.environ.get("TACO_DEC_LL", "default"), "decoder ms", statist
 if os.environ.get("TACO_TRACE"):
     import numpy as np
     ws = m.runtime.dec_ws.view(torch.int64).cpu().numpy()
-    n = 2 + 13 * T
-    total = len(ws) - (5 * n + 32)
+    n_alloc = 2 + 13 * T
+    total = len(ws) - (5 * n_alloc + 32)
+    NORD = 12
+    n = 2 + NORD * T
     tr = ws[total: total + n]
-    names = ["IN", "G1", "C1", "G2", "C2", "G3", "C3", "OUT", "P1", "Q", "P2", "ATT", "AL"]
+    names = ["IN", "G1", "C1", "G2", "C2", "G3", "C3", "OUT", "Q", "P1", "ATT", "P2"]
     d = np.diff(tr)[2:]
-    d = d[: (len(d) // 13) * 13].reshape(-1, 13)[5:]
+    d = d[: (len(d) // NORD) * NORD].reshape(-1, NORD)[5:]
     med = np.median(d, axis=0)
     print("per-slot median ns (CTA 0):", {n_: int(v) for n_, v in zip(names, med)}, "sum", int(med.sum()))
     ck = ws[total + n + 16: total + n + 16 + 4 * n].reshape(n, 4)[2:]
-    ck = ck[: (len(ck) // 13) * 13].reshape(-1, 13, 4)[5:-1]
+    ck = ck[: (len(ck) // NORD) * NORD].reshape(-1, NORD, 4)[5:-1]
     seg = np.stack([ck[:, :, 1] - ck[:, :, 0], ck[:, :, 2] - ck[:, :, 1], ck[:, :, 3] - ck[:, :, 2]], -1)   # inputs+mma, barrier, epilogue
-    nxt = np.roll(ck[:, :, 0].reshape(-1), -1).reshape(ck.shape[0], 13) - ck[:, :, 3]                         # epilogue end -> next slot start
+    nxt = np.roll(ck[:, :, 0].reshape(-1), -1).reshape(ck.shape[0], NORD) - ck[:, :, 3]                         # epilogue end -> next slot start
     print("cycles (inputs+mma | barrier | epilogue | to-next):")
     for i, n_ in enumerate(names):
         print(f"  {n_:4s} {int(np.median(seg[:, i, 0])):6d} {int(np.median(seg[:, i, 1])):6d} {int(np.median(seg[:, i, 2])):6d} {int(np.median(nxt[:-1, i])):6d}")
 
-    if os.environ.get("TACO_AL"):
-        ckr = ws[total + n + 16: total + n + 16 + 4 * n].reshape(n, 4)[2:]
-        ckr = ckr[: (len(ckr) // 13) * 13].reshape(-1, 13, 4)[5:-1]
-        att, al = ckr[:, 11], ckr[:, 12]
-        print("AL breakdown (cycles): yseg", int(np.median(att[:, 1] - al[:, 0])), "ms-wait", int(np.median(att[:, 2] - att[:, 1])),
-              "ctx-loop", int(np.median(att[:, 3] - att[:, 2])), "finalize+rest", int(np.median(al[:, 1] - att[:, 3])))

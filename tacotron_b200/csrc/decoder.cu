@@ -63,8 +63,8 @@ constexpr int MAXT = 8;        // max k-tiles per warp per segment (segment widt
 
 enum StageKind { K_P1 = 0, K_P2, K_IN, K_G1, K_C1, K_G2, K_C2, K_G3, K_C3, K_OUT, K_Q, K_ATT, K_AL };
 // execution order inside a step (P1/P2 belong to step t+1); two prologue slots P1(0), P2(0) come first
-__constant__ int c_order[NSTAGE] = {K_IN, K_G1, K_C1, K_G2, K_C2, K_G3, K_C3, K_OUT, K_P1, K_Q, K_P2, K_ATT, K_AL};
-static const int h_order[NSTAGE] = {K_IN, K_G1, K_C1, K_G2, K_C2, K_G3, K_C3, K_OUT, K_P1, K_Q, K_P2, K_ATT, K_AL};
+constexpr int NORD = 12;       // slots per decoder step (K_AL is folded into K_IN, see "fused linear stages" below)
+__constant__ int c_order[NORD] = {K_IN, K_G1, K_C1, K_G2, K_C2, K_G3, K_C3, K_OUT, K_Q, K_P1, K_ATT, K_P2};
 
 struct StageDesc {
     int K0, K1;        // K = K0 + K1 (two concatenated sources), multiples of 8
@@ -84,7 +84,7 @@ struct DecParams {
     StageDesc st[NSTAGE];
     DecLayout ws;
     taco_decoder_args a;
-    const float *pre_b1, *pre_b2, *in_b, *gru_bg[3], *gru_bc[3], *out_b, *att_v;
+    const float *pre_b1, *pre_b2, *in_b, *gru_bg[3], *gru_bc[3], *out_b, *att_v, *q_bias;
     int OUT;           // 80*r
     int Tq;            // Tx/4
     int smem_kv_off, smem_res_off, smem_stream_off, smem_total_floats;
@@ -94,12 +94,12 @@ __host__ __device__ inline void stage_dims(int kind, int OUT, int& K0, int& K1, 
     switch (kind) {
         case K_P1: K0 = MF;  K1 = 0;   N = 256; NCV = 8;  break;
         case K_P2: K0 = 256; K1 = 0;   N = 128; NCV = 4;  break;
-        case K_IN: K0 = 128; K1 = AU;  N = U;   NCV = 8;  break;
+        case K_IN: K0 = OUT + ENC; K1 = 128; N = U; NCV = 8; break;   // fused: [y(t-1) | ctx(t-1) | p2(t)] . W_inF
         case K_G1: case K_G2: case K_G3: K0 = U; K1 = U; N = 2 * U; NCV = 16; break;
         case K_C1: case K_C2: case K_C3: K0 = U; K1 = U; N = U;     NCV = 8;  break;
         case K_OUT: K0 = U;  K1 = 0;   N = OUT; NCV = (OUT + NS - 1) / NS; NCV = (NCV <= 4) ? 4 : (NCV <= 8) ? 8 : 16; break;
-        case K_Q:  K0 = OUT; K1 = 0;   N = AU;  NCV = 8;  break;
-        case K_AL: K0 = OUT; K1 = ENC; N = AU;  NCV = 8;  break;
+        case K_Q:  K0 = U;   K1 = 0;   N = AU;  NCV = 8;  break;        // fused: s . (W_out W_q) + b_out W_q
+        case K_AL: K0 = 0;   K1 = 0;   N = AU;  NCV = 8;  break;        // folded into K_IN (no slot, no weights)
         default:   K0 = K1 = N = 0; NCV = 8; break;      // K_ATT has no weight slice
     }
 }
@@ -311,6 +311,7 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
                 case K_G1: case K_G2: case K_G3: bp = P.gru_bg[(s - K_G1) / 2]; break;
                 case K_C1: case K_C2: case K_C3: bp = P.gru_bc[(s - K_C1) / 2]; break;
                 case K_OUT: bp = P.out_b; break;
+                case K_Q: bp = P.q_bias; break;        // b_out . W_q (fused query stage)
                 default: break;
             }
             if (bp && col >= 0) bv = __ldg(bp + col);
@@ -333,6 +334,7 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
                 const StageDesc& d = P.st[s];
                 if (s == K_ATT || d.res_off < 0) continue;
                 const int fl = (d.K0 + d.K1) * d.NT * 8;
+                if (fl == 0) continue;
                 bulk_load(res_s + d.res_off, A.packed + d.w_off + (int64_t)cs * fl, (uint32_t)fl * 4, &wbar[2]);
             }
         } else {
@@ -357,8 +359,8 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
     __syncthreads();
 
     // slot -> stage kind.  Slots 0,1 = P1(0), P2(0); then 13 per step in c_order.
-    const int total_slots = 2 + T * NSTAGE;
-    auto slot_kind = [&](int sl) { return sl < 2 ? sl : c_order[(sl - 2) % NSTAGE]; };
+    const int total_slots = 2 + T * NORD;
+    auto slot_kind = [&](int sl) { return sl < 2 ? sl : c_order[(sl - 2) % NORD]; };
     // streamed-slice bookkeeping: issue order == consume order; buffer = (index) & 1.  At most two slices
     // are in flight.  A buffer is re-filled only at the top of a slot, when every thread has passed the
     // post-compute __syncthreads of the slot that last read it.
@@ -382,9 +384,34 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
         }
     };
 
+    // alignments of step `step`: a_j = p_j * exp(m_q - M) / S from the four quarter (max, sum) pairs.  Done by
+    // the last two warps (fewest k-tiles) with the four loads issued together; p_s still holds that step's
+    // unnormalised probabilities (the next K_ATT slot has not run yet).
+    auto finalize_align = [&](int step, uint32_t tag) {
+        if (arow < B && tid >= NTHR - 64 && tid - (NTHR - 64) < Tq) {
+            const int j = tid - (NTHR - 64);
+            const uint64_t* ms = ws + P.ws.att_ms + (int64_t)arow * 8;
+            ulonglong2 mv[4];
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) mv[qd] = ll_load2(ms + 2 * qd);
+            float m[4], sq[4], M = -INFINITY;
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) {
+                ll_spin(mv[qd], ms + 2 * qd, tag);
+                m[qd] = __uint_as_float((uint32_t)mv[qd].x); sq[qd] = __uint_as_float((uint32_t)mv[qd].y); M = fmaxf(M, m[qd]);
+            }
+            float S = 0.f;
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) S += ((m[qd] == -INFINITY) ? 0.f : __expf(m[qd] - M)) * sq[qd];
+            const float sc = ((m[aq] == -INFINITY) ? 0.f : __expf(m[aq] - M)) / S;
+            const float* p_s = small_s + 512 + 64;
+            A.align[((int64_t)arow * T + step) * Tx + aq * Tq + j] = p_s[j] * sc;
+        }
+    };
+
     for (int sl = 0; sl < total_slots; ++sl) {
         const int s = slot_kind(sl);
-        const int t = sl < 2 ? -1 : (sl - 2) / NSTAGE;           // decoder step this slot executes in (-1 = prologue)
+        const int t = sl < 2 ? -1 : (sl - 2) / NORD;             // decoder step this slot executes in (-1 = prologue)
         const int tb = (s == K_P1 || s == K_P2) ? t + 1 : t;      // decoder step the OUTPUT of this slot belongs to
         const uint32_t tag_out = (uint32_t)tb + 1;                // tag of everything produced for step tb
         pump();
@@ -505,9 +532,8 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
 
         switch (s) {
             case K_P2: SEG(P.ws.p1, 256, 256, 0, tag_out); break;
-            case K_IN:
-                SEG(P.ws.p2, 128, 128, 0, tag_now);
-                if (t > 0) SEG(P.ws.attn, AU, AU, 16, tag_prev);
+            case K_IN:                                   // y(t-1) here; ctx(t-1) merge and p2(t) follow below
+                if (t > 0) SEG(P.ws.ybuf, YLD, OUT, 0, tag_prev);
                 break;
             case K_G1: case K_G2: case K_G3: {
                 const int gi = (s - K_G1) / 2;
@@ -522,8 +548,7 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
                 SEG(P.ws.rh[gi], U, U, 32, tag_now);
             } break;
             case K_OUT: SEG(P.ws.s, U, U, 0, tag_now); break;
-            case K_Q: SEG(P.ws.ybuf, YLD, OUT, 0, tag_now); break;
-            case K_AL: SEG(P.ws.ybuf, YLD, OUT, 0, tag_now); break;
+            case K_Q: SEG(P.ws.s, U, U, 0, tag_now); break;
             default: break;
         }
 #undef SEG
@@ -556,7 +581,8 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
                     load_w<1>(wf1, Wsl + (size_t)kt * 64 + lane * 2);
                     ktile_mma<1>(acc, xa, xb, wf1);
                 }
-        } else if (s == K_AL) {
+        } else if (s == K_IN) {
+            if (t > 0) {                                 // everything here refers to step t-1: tag_prev
                 // ctx = flash-style merge of the four quarter partials, built directly in fragment form.
                 // (rows >= B have no partials: their lanes feed zeros; the MMAs below are warp-collective,
                 //  so every lane runs the same loop.)
@@ -571,7 +597,7 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
                         for (int qd = 0; qd < 4; ++qd) mv[qd] = ll_load2(ms + 2 * qd);
 #pragma unroll
                         for (int qd = 0; qd < 4; ++qd) {
-                            ll_spin(mv[qd], ms + 2 * qd, tag_now);
+                            ll_spin(mv[qd], ms + 2 * qd, tag_prev);
                             m[qd] = __uint_as_float((uint32_t)mv[qd].x); sq[qd] = __uint_as_float((uint32_t)mv[qd].y); M = fmaxf(M, m[qd]);
                         }
                         float S = 0.f;
@@ -602,7 +628,7 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
                             if (live) {
 #pragma unroll
                                 for (int qd = 0; qd < 4; ++qd) {
-                                    ll_spin(v[u][qd], cp + qd * ENC + (ip + u) * (NWARP * 8), tag_now);
+                                    ll_spin(v[u][qd], cp + qd * ENC + (ip + u) * (NWARP * 8), tag_prev);
                                     xa = fmaf(w[qd], __uint_as_float((uint32_t)v[u][qd].x), xa);
                                     xb = fmaf(w[qd], __uint_as_float((uint32_t)v[u][qd].y), xb);
                                 }
@@ -611,27 +637,10 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
                         }
                     }
                 }
-                // finalise this CTA's slice of the alignments: a_j = p_j * exp(m_q - M) / S
-                // (done by the last two warps, which own the fewest k-tiles of this stage; the four loads are issued together)
-                if (arow < B && tid >= NTHR - 64 && tid - (NTHR - 64) < Tq) {
-                    const int j = tid - (NTHR - 64);
-                    const uint64_t* ms = ws + P.ws.att_ms + (int64_t)arow * 8;
-                    ulonglong2 mv[4];
-#pragma unroll
-                    for (int qd = 0; qd < 4; ++qd) mv[qd] = ll_load2(ms + 2 * qd);
-                    float m[4], sq[4], M = -INFINITY;
-#pragma unroll
-                    for (int qd = 0; qd < 4; ++qd) {
-                        ll_spin(mv[qd], ms + 2 * qd, tag_now);
-                        m[qd] = __uint_as_float((uint32_t)mv[qd].x); sq[qd] = __uint_as_float((uint32_t)mv[qd].y); M = fmaxf(M, m[qd]);
-                    }
-                    float S = 0.f;
-#pragma unroll
-                    for (int qd = 0; qd < 4; ++qd) S += ((m[qd] == -INFINITY) ? 0.f : __expf(m[qd] - M)) * sq[qd];
-                    const float sc = ((m[aq] == -INFINITY) ? 0.f : __expf(m[aq] - M)) / S;
-                    const float* p_s = small_s + 512 + 64;
-                    A.align[((int64_t)arow * T + t) * Tx + aq * Tq + j] = p_s[j] * sc;
-                }
+                finalize_align(t - 1, tag_prev);
+            }
+            // p2(t) last: it was produced one slot ago; its words arrive while the two segments above run
+            seg_ll<1>(acc, ws + P.ws.p2 + rowoff * 128, 16, (OUT + ENC) / 8, tag_now, Wsl, warp, lane);
         }
         if (tracer) ctrace[1] = (uint64_t)clock64();
         // ---- per-warp partial tiles -> shared memory (rows 0..7 of the 16x8 accumulator are the real rows) ----
@@ -697,6 +706,7 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
         if (tracer) ctrace[3] = (uint64_t)clock64();
         // hazards: part_s alternates by slot parity; loc arrays are ordered by the next slot's __syncthreads
     }
+    finalize_align(T - 1, (uint32_t)T);                 // the last step has no following K_IN slot
 }
 
 // ---- packing: TF [K][N] -> per-slice MMA B fragments [cs][k-tile][nt][lane][2], optional gate permutation ----
@@ -715,6 +725,38 @@ __global__ void pack_stage_kernel(const float* __restrict__ W, int K, int N, int
         const int col = stage_col(kind, cs, nt * 8 + g, NCV, N);
         dst[idx] = (col >= 0) ? W[(int64_t)k * N + col] : 0.0f;
     }
+}
+
+// ---- fused linear stages (weight-only precompute, once per weight update) ----------------------------------
+//   K_IN :  z(t) = p2(t).W_in[0:128] + attn(t-1).W_in[128:384] + b_in, attn(t-1) = [y(t-1), ctx(t-1)].W_a  (no bias,
+//           no non-linearity in between)  =>  z(t) = [y(t-1) | ctx(t-1) | p2(t)] . W_inF + b_in with
+//           W_inF = [ W_a . W_in[128:384] ; W_in[0:128] ]                 ((80r+256+128) x 256)
+//   K_Q  :  q(t) = y(t).W_q, y(t) = s(t).W_out + b_out  =>  q(t) = s(t).(W_out.W_q) + b_out.W_q      (256 x 256)
+// The attention state itself (attn) is consumed by nothing else (tacotron.py:64-71), so it is never formed.
+// This removes the K_AL slot and two dependent L2 hops from every decoder step; sums are re-associated
+// (differences ~1e-6 relative, inside the stated fp32 tolerance).
+__global__ void matmul_naive_kernel(const float* __restrict__ Amat, int lda, const float* __restrict__ Bmat, int ldb,
+                                    float* __restrict__ Cmat, int ldc, int M, int N, int K) {
+    const int64_t total = (int64_t)M * N;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int m = (int)(i / N), n = (int)(i % N);
+        double acc = 0.0;                                   // weight-only precompute: accumulate in double
+        for (int k = 0; k < K; ++k) acc += (double)Amat[(int64_t)m * lda + k] * (double)Bmat[(int64_t)k * ldb + n];
+        Cmat[(int64_t)m * ldc + n] = (float)acc;
+    }
+}
+__global__ void copy_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+struct FusedTail { int64_t w_inF, w_qF, b_qF, total; };    // float offsets inside the packed buffer
+FusedTail fused_tail(int r, int64_t slices_total) {
+    const int OUT = MF * r;
+    FusedTail f;
+    f.w_inF = (slices_total + 63) / 64 * 64;
+    f.w_qF = f.w_inF + (int64_t)(OUT + ENC + 128) * U;
+    f.b_qF = f.w_qF + (int64_t)U * AU;
+    f.total = f.b_qF + AU;
+    return f;
 }
 
 void build_stage_table(int r, StageDesc* st, int64_t* total_floats) {
@@ -746,7 +788,7 @@ void build_ws_layout(DecLayout* L) {
 extern "C" size_t taco_decoder_packed_bytes(int r) {
     StageDesc st[NSTAGE]; int64_t tot;
     build_stage_table(r, st, &tot);
-    return (size_t)tot * 4;
+    return (size_t)fused_tail(r, tot).total * 4;
 }
 
 extern "C" size_t taco_decoder_workspace_bytes(int B, int Tx, int T, int r) {
@@ -760,15 +802,32 @@ extern "C" int taco_decoder_pack(const taco_decoder_weights* w, int r, float* pa
     TACO_CHECK(r >= 1 && MF * r <= 512, "taco_decoder_pack: r=%d out of range (80r <= 512)", r);
     StageDesc st[NSTAGE]; int64_t tot;
     build_stage_table(r, st, &tot);
-    const float* src[NSTAGE] = {w->pre_W1, w->pre_W2, w->in_W, w->gru_Wg[0], w->gru_Wc[0], w->gru_Wg[1], w->gru_Wc[1],
-                                w->gru_Wg[2], w->gru_Wc[2], w->out_W, w->att_Wq, nullptr, w->att_Wa};
+    cudaStream_t stm = (cudaStream_t)stream;
+    const int OUT = MF * r;
+    const FusedTail ft = fused_tail(r, tot);
+    float* w_inF = packed + ft.w_inF;
+    float* w_qF = packed + ft.w_qF;
+    float* b_qF = packed + ft.b_qF;
+    TACO_CHECK(w->att_Wa && w->in_W && w->out_W && w->att_Wq && w->out_b, "taco_decoder_pack: NULL weight");
+    // W_inF rows [0, OUT+256) = W_a . W_in[128:384]; rows [OUT+256, OUT+384) = W_in[0:128]
+    matmul_naive_kernel<<<592, 256, 0, stm>>>(w->att_Wa, AU, w->in_W + (int64_t)128 * U, U, w_inF, U, OUT + ENC, U, AU);
+    TACO_LAUNCH_CHECK();
+    copy_rows_kernel<<<64, 256, 0, stm>>>(w->in_W, w_inF + (int64_t)(OUT + ENC) * U, (int64_t)128 * U);
+    TACO_LAUNCH_CHECK();
+    // W_qF = W_out . W_q ; b_qF = b_out . W_q
+    matmul_naive_kernel<<<256, 256, 0, stm>>>(w->out_W, OUT, w->att_Wq, AU, w_qF, AU, U, AU, OUT);
+    TACO_LAUNCH_CHECK();
+    matmul_naive_kernel<<<1, 256, 0, stm>>>(w->out_b, OUT, w->att_Wq, AU, b_qF, AU, 1, AU, OUT);
+    TACO_LAUNCH_CHECK();
+    const float* src[NSTAGE] = {w->pre_W1, w->pre_W2, w_inF, w->gru_Wg[0], w->gru_Wc[0], w->gru_Wg[1], w->gru_Wc[1],
+                                w->gru_Wg[2], w->gru_Wc[2], w->out_W, w_qF, nullptr, nullptr};
     for (int s = 0; s < NSTAGE; ++s) {
-        if (s == K_ATT) continue;
+        if (s == K_ATT || s == K_AL) continue;
         TACO_CHECK(src[s] != nullptr, "taco_decoder_pack: weight %d is NULL", s);
         const int K = st[s].K0 + st[s].K1;
         const int64_t total = (int64_t)NS * K * st[s].NT * 8;
         const int blocks = (int)((total + 255) / 256);
-        pack_stage_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src[s], K, st[s].N, st[s].NCV, st[s].NT, s, packed + st[s].w_off);
+        pack_stage_kernel<<<blocks, 256, 0, stm>>>(src[s], K, st[s].N, st[s].NCV, st[s].NT, s, packed + st[s].w_off);
         TACO_LAUNCH_CHECK();
     }
     return 0;
@@ -801,6 +860,7 @@ extern "C" int taco_decoder_fwd(const taco_decoder_args* a, void* stream) {
     TACO_CHECK(P.OUT / 8 <= MAXT * NWARP, "taco_decoder_fwd: 80r too wide for the fragment pipeline");
     P.pre_b1 = g_dec_w.pre_b1; P.pre_b2 = g_dec_w.pre_b2; P.in_b = g_dec_w.in_b; P.out_b = g_dec_w.out_b; P.att_v = g_dec_w.att_v;
     for (int i = 0; i < 3; ++i) { P.gru_bg[i] = g_dec_w.gru_bg[i]; P.gru_bc[i] = g_dec_w.gru_bc[i]; }
+    P.q_bias = a->packed + fused_tail(a->r, tot).b_qF;
 
     // shared-memory plan
     int off = 64 + 2 * NWARP * 128 + 512 + 256 + 1024;
@@ -814,16 +874,15 @@ extern "C" int taco_decoder_fwd(const taco_decoder_args* a, void* stream) {
     const int max_floats = (227 * 1024) / 4;
     const int budget = max_floats - off;
     // greedy residency: biggest per-step traffic first (GRU gates, candidates, attention layer, ...)
-    const int order[] = {K_G1, K_G2, K_G3, K_C1, K_C2, K_C3, K_AL, K_IN, K_OUT, K_Q, K_P2, K_P1};
+    const int order[] = {K_G1, K_G2, K_G3, K_C1, K_C2, K_C3, K_IN, K_OUT, K_Q, K_P2, K_P1};
     int res = 0;
-    for (int i = 0; i < 12; ++i) {
+    for (int i = 0; i < 11; ++i) {
         StageDesc& d = P.st[order[i]];
         const int fl = (d.K0 + d.K1) * d.NT * 8;
         if (fl <= budget - res) { d.res_off = res; res += fl; }
     }
     P.smem_total_floats = off + res;
     const size_t smem_bytes = (size_t)P.smem_total_floats * 4;
-    (void)h_order;
 
     static bool configured = false;
     if (!configured) {

@@ -60,10 +60,14 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
 def test_decoder_sizes_host_only():
     from tacotron_b200 import _lib
     lib = _lib.lib()
-    # packed floats = 32 slices x sum_s K_s * 8*NT_s  (MMA B fragments, columns padded to multiples of 8)
-    r5 = lib.taco_decoder_packed_bytes(5) // 4
-    r2 = lib.taco_decoder_packed_bytes(2) // 4
-    per_slice5 = 80*8 + 256*8 + 384*8 + 3*(512*16 + 512*8) + 256*16 + 400*8 + 656*8
-    per_slice2 = 80*8 + 256*8 + 384*8 + 3*(512*16 + 512*8) + 256*8 + 160*8 + 416*8
-    assert r5 == 32 * per_slice5 and r2 == 32 * per_slice2
+    # packed floats = 32 slices x sum_s K_s * 8*NT_s (MMA B fragments, columns padded to multiples of 8), rounded to 64,
+    # + the fused weight-only products W_inF ((80r+384) x 256), W_qF (256 x 256), b_qF (256)
+    def expect(r):
+        out = 80 * r
+        nt_out = 2 if (out + 31) // 32 > 8 else 1
+        per_slice = 80*8 + 256*8 + (out + 256 + 128)*8 + 3*(512*16 + 512*8) + 256*8*nt_out + 256*8
+        sl = (32 * per_slice + 63) // 64 * 64
+        return sl + (out + 384) * 256 + 256 * 256 + 256
+    assert lib.taco_decoder_packed_bytes(5) // 4 == expect(5)
+    assert lib.taco_decoder_packed_bytes(2) // 4 == expect(2)
     assert lib.taco_decoder_workspace_bytes(32, 128, 200, 5) > 0

@@ -22,6 +22,15 @@ namespace {
 
 constexpr int H = 128;
 
+// d += a * b on two packed fp32 lanes (Blackwell FFMA2: one issue slot for two FMAs)
+__device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b) {
+    unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d);
+    const unsigned long long aa = *reinterpret_cast<const unsigned long long*>(&a);
+    const unsigned long long bb = *reinterpret_cast<const unsigned long long*>(&b);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(aa), "l"(bb));
+    d = *reinterpret_cast<float2*>(&dd);
+}
+
 // Reduce N per-lane partial sums (N = 16 or 8) across the 32 lanes.  Each round halves the number of
 // live values: a lane keeps the half selected by its lane bit and receives the partner's
 // contribution for that half.  On return p[0] holds the full sum of column
@@ -100,15 +109,21 @@ bigru_kernel(const float* __restrict__ xp, const float* __restrict__ Wg_fw, cons
         // ---- gates: h . Wg_h ----
         {
             const float4 hv = *reinterpret_cast<const float4*>(h_s + 4 * lane);
+            float2 p2[8];
+            const float2 hx = make_float2(hv.x, hv.x), hy = make_float2(hv.y, hv.y), hz = make_float2(hv.z, hv.z), hw = make_float2(hv.w, hv.w);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) p2[c] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) ffma2(p2[c], hx, make_float2(wg[0][2 * c], wg[0][2 * c + 1]));
+#pragma unroll
+            for (int c = 0; c < 8; ++c) ffma2(p2[c], hy, make_float2(wg[1][2 * c], wg[1][2 * c + 1]));
+#pragma unroll
+            for (int c = 0; c < 8; ++c) ffma2(p2[c], hz, make_float2(wg[2][2 * c], wg[2][2 * c + 1]));
+#pragma unroll
+            for (int c = 0; c < 8; ++c) ffma2(p2[c], hw, make_float2(wg[3][2 * c], wg[3][2 * c + 1]));
             float p[16];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) p[c] = hv.x * wg[0][c];
-#pragma unroll
-            for (int c = 0; c < 16; ++c) p[c] = fmaf(hv.y, wg[1][c], p[c]);
-#pragma unroll
-            for (int c = 0; c < 16; ++c) p[c] = fmaf(hv.z, wg[2][c], p[c]);
-#pragma unroll
-            for (int c = 0; c < 16; ++c) p[c] = fmaf(hv.w, wg[3][c], p[c]);
+            for (int c = 0; c < 8; ++c) { p[2 * c] = p2[c].x; p[2 * c + 1] = p2[c].y; }
             const float acc = butterfly<16>(p, lane);
             if (g_owner) {
                 const float g = sigmoidf_acc(acc + xg);
@@ -120,15 +135,21 @@ bigru_kernel(const float* __restrict__ xp, const float* __restrict__ Wg_fw, cons
         // ---- candidate: (r*h) . Wc_h ----
         {
             const float4 rv = *reinterpret_cast<const float4*>(rh_s + 4 * lane);
+            float2 p2[4];
+            const float2 rx = make_float2(rv.x, rv.x), ry = make_float2(rv.y, rv.y), rz = make_float2(rv.z, rv.z), rw = make_float2(rv.w, rv.w);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) p2[c] = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) ffma2(p2[c], rx, make_float2(wc[0][2 * c], wc[0][2 * c + 1]));
+#pragma unroll
+            for (int c = 0; c < 4; ++c) ffma2(p2[c], ry, make_float2(wc[1][2 * c], wc[1][2 * c + 1]));
+#pragma unroll
+            for (int c = 0; c < 4; ++c) ffma2(p2[c], rz, make_float2(wc[2][2 * c], wc[2][2 * c + 1]));
+#pragma unroll
+            for (int c = 0; c < 4; ++c) ffma2(p2[c], rw, make_float2(wc[3][2 * c], wc[3][2 * c + 1]));
             float p[8];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) p[c] = rv.x * wc[0][c];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) p[c] = fmaf(rv.y, wc[1][c], p[c]);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) p[c] = fmaf(rv.z, wc[2][c], p[c]);
-#pragma unroll
-            for (int c = 0; c < 8; ++c) p[c] = fmaf(rv.w, wc[3][c], p[c]);
+            for (int c = 0; c < 4; ++c) { p[2 * c] = p2[c].x; p[2 * c + 1] = p2[c].y; }
             const float cacc = butterfly<8>(p, lane);
             if (c_owner) {
                 const float c = tanhf_acc(cacc + xc);

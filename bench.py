@@ -248,6 +248,10 @@ def run_ours(args):
         pk = peaks()
         dms = statistics.mean(dec_ms)
         ach = DECODER_GFLOP / dms                      # GFLOP / ms = TFLOP/s
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r01_decoder_traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes")
         cpu = None
         if not args.no_cpu_baseline:
             ts, threads = time_cpu_oracle(3)
@@ -269,7 +273,7 @@ def run_ours(args):
                     "ms_per_step": float(e2e_t.item()) * 1e3},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "decoder_kernel (persistent, 200 steps)", "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"],
-                         "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": None, "peak_source": pk["source"],
+                         "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write.sum)", "peak_source": pk["source"],
                          "algorithmic_gflop_per_launch": DECODER_GFLOP,
                          "whole_step": {"achieved": FWD_GFLOP / ms_per_step, "frac": FWD_GFLOP / ms_per_step / pk["bf16_tflops"]}},
             "cpu_baseline": cpu,

@@ -385,5 +385,8 @@ int taco_linear_tc(const taco_linear_desc* d, cudaStream_t st) {
     }
     dim3 grid((d->N + BN - 1) / BN, (unsigned)(a.tiles_per_seq * d->B));
     if (highway) return launch_tc<256, 2, 1>(tmA, tmB, a, grid, st);
+    // short K loops (<= 8 k-iterations: dense 128/256-wide inputs) are epilogue/latency bound: a 2-stage ring (64 KB)
+    // lets three CTAs share an SM instead of two
+    if (!a.bank && a.taps * a.cchunks <= 8) return launch_tc<128, 2, 0>(tmA, tmB, a, grid, st);
     return launch_tc<128, 3, 0>(tmA, tmB, a, grid, st);
 }

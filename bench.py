@@ -175,12 +175,18 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # clocks are sampled from the first warm-up step to the end of the timed region (the GPU is under the
+    # same load throughout; the timed region alone is too short for nvidia-smi's ~100 ms sampling period)
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    t_warm = time.perf_counter()
+    while sampler is not None and time.perf_counter() - t_warm < 0.35:      # keep the load on until a few samples exist
         step()
     barrier()
 
     # ---------------- device-resident timing: K steps, per-step events, L2 flushed between steps ----------------
-    sampler = ClockSampler(local) if rank == 0 else None
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     dec_ms, enc_ms, post_ms, step_lat = [], [], [], []

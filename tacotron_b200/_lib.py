@@ -16,8 +16,6 @@ IMPL_TC, IMPL_SIMT = 0, 1
 EPI_NORMAL, EPI_HIGHWAY = 0, 1
 DEC_INFER, DEC_TEACHER, DEC_SCHED = 0, 1, 2
 
-c_float_p = C.c_void_p   # device pointers travel as integers
-
 
 class LinearDesc(C.Structure):
     _fields_ = [
@@ -102,10 +100,8 @@ def lib():
     L.taco_l1_loss_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.taco_l1_partial_count.restype = C.c_int
     L.taco_launch_count.restype = C.c_ulonglong
-    for name in EXPORTS:
-        fn = getattr(L, name)
-        if fn.restype is C.c_int and name not in ("taco_version", "taco_l1_partial_count"):
-            pass
+    for name in EXPORTS:                      # every declared symbol must resolve (AttributeError otherwise)
+        getattr(L, name)
     _lib = L
     return L
 

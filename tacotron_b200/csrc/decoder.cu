@@ -32,8 +32,9 @@
 //     fragments (weights) come from shared memory pre-packed in fragment order (one LDS.64 per MMA).
 //   * GRU gate columns are permuted so that CTA cs owns r and u of the SAME 8 hidden units: u, the
 //     previous state and z never leave the CTA.
-//   * pre-net of step t+1 is scheduled between OUT/Q and Q/ATT of step t, off the critical chain:
-//     11 dependent hops per step instead of 13.
+//   * fused linear stages (weight-only precompute at pack time): the attention layer is folded into the
+//     input projection and the query is taken from the residual sum, so K_AL has no slot (12 per step);
+//     pre-net of step t+1 is scheduled after Q and after ATT of step t, off the critical chain.
 //   * weight slices are RESIDENT in shared memory or streamed from L2 by cp.async.bulk + mbarrier
 //     (double buffered, issued ahead).
 //   * attention: CTA (utterance, quarter of Tx) keeps its keys/values slice in shared memory for all
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
     mbar_wait(&wbar[2], 0);
     __syncthreads();
 
-    // slot -> stage kind.  Slots 0,1 = P1(0), P2(0); then 13 per step in c_order.
+    // slot -> stage kind.  Slots 0,1 = P1(0), P2(0); then NORD (12) per step in c_order.
     const int total_slots = 2 + T * NORD;
     auto slot_kind = [&](int sl) { return sl < 2 ? sl : c_order[(sl - 2) % NORD]; };
     // streamed-slice bookkeeping: issue order == consume order; buffer = (index) & 1.  At most two slices
@@ -699,7 +700,6 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
                         if (row < B) A.y[((int64_t)row * T + t) * OUT + col] = v;
                     } break;
                     case K_Q: ll_store(ws + P.ws.q + ro * AU + perm8(col), v, tag_out); break;
-                    case K_AL: ll_store(ws + P.ws.attn + ro * AU + perm8(col), v, tag_out); break;
                 }
             }
         }

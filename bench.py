@@ -147,13 +147,11 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from tacotron_b200 import Config, Tacotron, _lib
+    from tacotron_b200.utils import dist as D
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world, rank, local = D.world()
     torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    D.init("nccl")
     lib = _lib.lib()
 
     cfg = Config(r=R, vocab_size=64, max_decode_iter=T, precision=args.precision, cuda_graph=not args.no_graph)
@@ -170,10 +168,7 @@ def run_ours(args):
     def step():
         return model.inference(inp, train=False)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    barrier = D.barrier
 
     # clocks are sampled from the first warm-up step to the end of the timed region (the GPU is under the
     # same load throughout; the timed region alone is too short for nvidia-smi's ~100 ms sampling period)
@@ -211,12 +206,9 @@ def run_ours(args):
     launches = lib.taco_launch_count() - launches0 + args.steps * int(model.last_graph_kernels)
     clocks = sampler.stop() if sampler else None
     total_ms = sum(s.elapsed_time(e) for s, e in zip(starts, ends))
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
+    total_ms = D.max_over_ranks(total_ms)                 # the job advances at the slowest rank
     ms_per_step = total_ms / args.steps
-    value = world * FRAMES / (ms_per_step / 1e3)
+    value = D.aggregate_throughput(FRAMES, world, ms_per_step)
 
     # ---------------- end to end through the public API with host buffers ----------------
     # Every step: H2D of the step's inputs from pinned memory, Tacotron.inference, D2H of output + alignments
@@ -243,10 +235,8 @@ def run_ours(args):
     torch.cuda.synchronize()
     t1 = time.perf_counter()
     model.section_wait = None
-    e2e_t = torch.tensor([(t1 - t0) / e2e_steps], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_val = world * FRAMES / float(e2e_t.item())
+    e2e_s = D.max_over_ranks((t1 - t0) / e2e_steps)
+    e2e_val = D.aggregate_throughput(FRAMES, world, e2e_s * 1e3)
     h2d = text_h.numel() * 4 + len_h.numel() * 4
     d2h = out_h.numel() * 4 + align_h.numel() * 4
 
@@ -276,7 +266,7 @@ def run_ours(args):
             "sections_ms": {"encoder": statistics.mean(enc_ms), "decoder": dms, "postnet": statistics.mean(post_ms)},
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": "mel frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": float(e2e_t.item()) * 1e3},
+                    "ms_per_step": e2e_s * 1e3},
             "gpu_launches": int(launches),
             "roofline": {"kernel": "decoder_kernel (persistent, 200 steps)", "bound": "tensor", "achieved": ach, "peak": pk["bf16_tflops"],
                          "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write.sum)", "peak_source": pk["source"],

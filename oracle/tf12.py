@@ -11,6 +11,14 @@ attention_wrapper.py / helper.py / basic_decoder.py) as restated in SURVEY.md
 Appendix A, and are anchored on the reference's own call sites (cited per
 function).
 
+What IS pinned (tests/golden/make_golden.py, tests/test_oracle.py):
+  * audio.reshape_frames against outputs of the reference's own function;
+  * the model graph WIRING (call order, slices, wrapper nesting, helper semantics, loss) against outputs
+    obtained by executing the reference's own models/tacotron.py + models/ops.py, unmodified, over
+    oracle/tf12_shim.py (a stand-in for the TF-1.2 API whose primitives delegate to the functions below).
+What is NOT pinned: the numerics/semantics of the TF-1.2 primitives themselves (this file) -- no
+TensorFlow 1.2 run, checkpoint or golden vector is reachable from this container.
+
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 reference legs may import this package.  The product path (tacotron_b200/) never
 does: it fails loudly when the CUDA library is missing.

@@ -74,6 +74,64 @@ def oracle_small():
         print(f"oracle_small_r{r}.npz written")
 
 
+def reference_wiring():
+    """Execute the reference's OWN models/tacotron.py + models/ops.py (unmodified, imported from /root/reference)
+    over oracle/tf12_shim.py and save its outputs: pins the oracle's graph wiring against the reference source."""
+    from oracle import tacotron_oracle as O
+    from oracle import tf12_shim as shim
+    from tacotron_b200.tf_names import tf_name_to_param as tf_name_to_oracle
+    for name in ("librosa", "tqdm"):
+        m = types.ModuleType(name)
+        if name == "tqdm":
+            m.tqdm = lambda x, **k: x
+        sys.modules[name] = m
+    shim.install()
+    for k in [k for k in sys.modules if k == "audio" or k == "models" or k.startswith("models.")]:
+        del sys.modules[k]
+    if "/root/reference" not in sys.path:
+        sys.path.insert(0, "/root/reference")
+    import models.tacotron as ref_tacotron            # the reference module, unmodified
+
+    for r in (2, 5):
+        B, Tx, T = 2, 12, 6
+        cfg_o = O.OracleConfig(r=r, max_decode_iter=T, vocab_size=20)
+        params = O.init_params(cfg_o, seed=1, trained_like=True)
+        inp = O.synthetic_inputs(cfg_o, B, Tx, T, seed=0, ragged=True)
+        enc_m, dec_m = O.dropout_masks(cfg_o, B, Tx, T, seed=2)
+        sm = O.sched_mask(cfg_o, B, T, seed=3)
+        used = set()
+
+        def lookup(name, shape):
+            on = tf_name_to_oracle(name)
+            used.add(on)
+            return params[on]
+
+        out = {}
+        for mode in ("infer", "teacher", "sched"):
+            config = ref_tacotron.Config()
+            config.r, config.vocab_size, config.max_decode_iter = r, 20, T
+            config.scheduled_sample = 0.5 if mode == "sched" else 0
+            train = mode != "infer"
+            drops = []
+            if train:                                  # call order: encoder pre-net (2), then 2 per decoder step
+                drops = [enc_m[0], enc_m[1]]
+                for t in range(T):
+                    drops += [dec_m[0][t], dec_m[1][t]]
+            shim.S.reset(lookup, dropout_masks=drops, sample_masks=[sm[t] for t in range(T)] if mode == "sched" else None)
+            model = ref_tacotron.Tacotron(config, inp, train=train)
+            out[f"y_{mode}"] = model.seq2seq_output.numpy()
+            out[f"out_{mode}"] = model.output.numpy()
+            out[f"align_{mode}"] = model.alignments.numpy()
+            if train:
+                out[f"loss_{mode}"] = np.array(float(model.loss))
+            assert not shim.S.dropout_masks, "dropout masks left over: the reference made fewer dropout calls than assumed"
+        assert used == set(params), sorted(set(params) - used)
+        out["tf_variable_names"] = np.array(shim.S.created)
+        np.savez_compressed(os.path.join(HERE, f"reference_wiring_r{r}.npz"), **out)
+        print(f"reference_wiring_r{r}.npz written ({len(shim.S.created)} variables)")
+
+
 if __name__ == "__main__":
     reference_reshape_frames()
     oracle_small()
+    reference_wiring()

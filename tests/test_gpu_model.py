@@ -160,3 +160,29 @@ def test_bad_inputs_raise():
         m.inference(bad, train=False)                      # width not a multiple of 4
     with pytest.raises(NotImplementedError):
         m.add_train_op(None)
+
+
+@pytest.mark.parametrize("r", [2, 5])
+def test_against_reference_code_fixture(r):
+    """CUDA path vs outputs of the reference's own model code executed over the TF shim (tests/golden/make_golden.py)."""
+    g = np.load(os.path.join(GOLD, f"reference_wiring_r{r}.npz"))
+    cfg = O.OracleConfig(r=r, max_decode_iter=6, vocab_size=20)
+    p = O.init_params(cfg, seed=1, trained_like=True)
+    inp = O.synthetic_inputs(cfg, 2, 12, 6, seed=0, ragged=True)
+    enc_m, dec_m = O.dropout_masks(cfg, 2, 12, 6, seed=2)
+    sm = O.sched_mask(cfg, 2, 6, seed=3)
+    m = make_model(cfg, p, "fp32")
+    ci = to_cuda(inp)
+    cm = lambda t: tuple(x.cuda() for x in t)
+    y, out = m.inference(ci, train=False)
+    torch.cuda.synchronize()
+    assert_close(y, torch.from_numpy(g["y_infer"]), TOL["fp32"], "y infer")
+    assert_close(out, torch.from_numpy(g["out_infer"]), TOL["fp32"], "out infer")
+    assert_close(m.alignments, torch.from_numpy(g["align_infer"]), TOL["fp32"], "align infer")
+    m.train = True
+    m.config.scheduled_sample = 0.5
+    y, out = m(ci, enc_drop_masks=cm(enc_m), dec_drop_masks=cm(dec_m), sample_mask=sm.cuda())
+    torch.cuda.synchronize()
+    assert_close(y, torch.from_numpy(g["y_sched"]), TOL["fp32"], "y sched")
+    assert_close(out, torch.from_numpy(g["out_sched"]), TOL["fp32"], "out sched")
+    assert abs(float(m.loss) - float(g["loss_sched"])) / float(g["loss_sched"]) < TOL["fp32"]

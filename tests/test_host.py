@@ -63,3 +63,17 @@ def test_model_requires_cuda():
     from tacotron_b200 import Tacotron
     with pytest.raises(RuntimeError):
         Tacotron(Config(), None, train=False)
+
+
+def test_tf_name_map_covers_every_parameter():
+    """Every TF variable the reference's graph code creates (recorded while executing it, tests/golden) maps to
+    exactly one parameter of the store, and every parameter is hit."""
+    import os
+    from tacotron_b200.tf_names import tf_name_to_param
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_wiring_r5.npz"))
+    names = [str(x) for x in g["tf_variable_names"]]
+    mapped = [tf_name_to_param(n) for n in names]
+    store_names = {n for n, _, _ in model_shapes(Config(r=5, vocab_size=20))}
+    assert len(set(mapped)) == len(mapped) == len(store_names) and set(mapped) == store_names
+    with pytest.raises(KeyError):
+        tf_name_to_param("global_step")

@@ -164,3 +164,28 @@ def test_decoder_teacher_forcing_has_no_go_frame():
     inp2 = dict(inp); inp2["mel"] = inp["mel"].clone(); inp2["mel"][:, 2, -1] += 1.0   # last frame of group 2
     y1, _, _ = O.inference(p, inp2, cfg, train=True)
     assert torch.equal(y0[:, :2], y1[:, :2]) and not torch.equal(y0[:, 2], y1[:, 2])
+
+
+@pytest.mark.parametrize("r", [2, 5])
+def test_oracle_matches_reference_code_wiring(r):
+    """tests/golden/reference_wiring_r*.npz was produced by EXECUTING the reference's own models/tacotron.py +
+    models/ops.py (imported from /root/reference, unmodified) over oracle/tf12_shim.py with these weights, inputs,
+    dropout masks and sampling draws.  The oracle's independent restatement of the graph must agree: this pins the
+    wiring (call order, slices, wrapper nesting, helper semantics, loss) against the reference source."""
+    g = np.load(os.path.join(GOLD, f"reference_wiring_r{r}.npz"))
+    cfg = O.OracleConfig(r=r, max_decode_iter=6, vocab_size=20)
+    p = O.init_params(cfg, seed=1, trained_like=True)
+    inp = O.synthetic_inputs(cfg, 2, 12, 6, seed=0, ragged=True)
+    enc_m, dec_m = O.dropout_masks(cfg, 2, 12, 6, seed=2)
+    sm = O.sched_mask(cfg, 2, 6, seed=3)
+    y, o, a = O.inference(p, inp, cfg, train=False)
+    for got, key in ((y, "y_infer"), (o, "out_infer"), (a, "align_infer")):
+        np.testing.assert_allclose(got.numpy(), g[key], rtol=2e-5, atol=2e-6)
+    y, o, a = O.inference(p, inp, cfg, train=True, enc_drop_masks=enc_m, dec_drop_masks=dec_m)
+    for got, key in ((y, "y_teacher"), (o, "out_teacher"), (a, "align_teacher")):
+        np.testing.assert_allclose(got.numpy(), g[key], rtol=2e-5, atol=2e-6)
+    assert abs(float(O.loss(y, o, inp["mel"], inp["stft"])[0]) - float(g["loss_teacher"])) / float(g["loss_teacher"]) < 1e-6
+    y, o, a = O.inference(p, inp, cfg, train=True, enc_drop_masks=enc_m, dec_drop_masks=dec_m, sample_mask=sm)
+    for got, key in ((y, "y_sched"), (o, "out_sched"), (a, "align_sched")):
+        np.testing.assert_allclose(got.numpy(), g[key], rtol=2e-5, atol=2e-6)
+    assert len(g["tf_variable_names"]) == len(p)

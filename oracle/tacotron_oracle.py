@@ -339,3 +339,29 @@ def dropout_masks(cfg: OracleConfig, B, Tx, T, seed=2):
 def sched_mask(cfg: OracleConfig, B, T, seed=3):
     g = torch.Generator().manual_seed(seed)
     return (torch.rand(T, B, generator=g) < cfg.scheduled_sample).to(torch.uint8)
+
+
+# ----------------------------------------------------------------------------
+# models/tacotron.py:167-185  add_train_op -- gradients / clip / Adam, as the target the CUDA backward
+# (not built yet) will be checked against.  torch.autograd over the forward above; TF semantics A.12.
+# ----------------------------------------------------------------------------
+def loss_and_grads(p, inputs, cfg: OracleConfig, enc_drop_masks=None, dec_drop_masks=None, sample_mask=None):
+    """Returns (loss, {name: grad}) for the trainable variables.  Scheduled sampling back-propagates through the
+    sampled outputs (no stop_gradient, A.9); BN moving statistics get no gradient (A.4)."""
+    q = {k: v.detach().clone().requires_grad_(not k.endswith(NON_TRAINABLE_SUFFIXES)) for k, v in p.items()}
+    y, out, _ = inference(q, inputs, cfg, train=True, enc_drop_masks=enc_drop_masks, dec_drop_masks=dec_drop_masks,
+                          sample_mask=sample_mask)
+    total, _, _ = loss(y, out, inputs["mel"].to(y.dtype), inputs["stft"].to(y.dtype))
+    names = [k for k, v in q.items() if v.requires_grad]
+    grads = torch.autograd.grad(total, [q[k] for k in names])
+    return total.detach(), dict(zip(names, grads))
+
+
+def train_step(p, m, v, inputs, cfg: OracleConfig, lr, step, **kw):
+    """One reference training step: grads -> clip_by_global_norm(cap_grads) -> TF Adam.  p/m/v: dicts; step is 1-based."""
+    total, g = loss_and_grads(p, inputs, cfg, **kw)
+    names = list(g)
+    clipped, gnorm = tf12.clip_by_global_norm([g[n] for n in names], float(cfg.cap_grads))
+    for n, gc in zip(names, clipped):
+        p[n], m[n], v[n] = tf12.adam_tf(p[n], gc, m[n], v[n], lr, step)
+    return total, gnorm

@@ -189,3 +189,38 @@ def test_oracle_matches_reference_code_wiring(r):
     for got, key in ((y, "y_sched"), (o, "out_sched"), (a, "align_sched")):
         np.testing.assert_allclose(got.numpy(), g[key], rtol=2e-5, atol=2e-6)
     assert len(g["tf_variable_names"]) == len(p)
+
+
+def test_oracle_gradients_match_finite_differences():
+    """Target for the (future) CUDA backward: autograd over the oracle, checked against central differences in fp64."""
+    cfg = O.OracleConfig(r=2, max_decode_iter=3, vocab_size=12)
+    p = {k: v.double() for k, v in O.init_params(cfg, 1, True).items()}
+    inp = O.synthetic_inputs(cfg, 2, 8, 3, seed=0, ragged=True)
+    inp = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in inp.items()}
+    enc_m, dec_m = O.dropout_masks(cfg, 2, 8, 3, seed=2)
+    sm = O.sched_mask(cfg, 2, 3, seed=3)
+    kw = dict(enc_drop_masks=enc_m, dec_drop_masks=dec_m, sample_mask=sm)
+    total, g = O.loss_and_grads(p, inp, cfg, **kw)
+    assert set(g) == {k for k in p if not k.endswith(("bn_mean", "bn_var"))}
+    gen = torch.Generator().manual_seed(0)
+    for name in ("dec/gru2/Wc", "enc/cbhg/bank/W3", "dec/attn/W_q", "post/cbhg/gru_bw/Wg", "dec/prenet/W1", "embedding"):
+        idx = tuple(int(torch.randint(0, s, (1,), generator=gen)) for s in p[name].shape)
+        eps = 1e-6
+        def f(delta):
+            q = dict(p); t = p[name].clone(); t[idx] += delta; q[name] = t
+            y, o, _ = O.inference(q, inp, cfg, train=True, **kw)
+            return float(O.loss(y, o, inp["mel"], inp["stft"])[0])
+        fd = (f(eps) - f(-eps)) / (2 * eps)
+        an = float(g[name][idx])
+        assert abs(fd - an) <= 1e-4 * max(1.0, abs(fd)), (name, idx, fd, an)   # L1 loss: piecewise linear, kinks are measure-zero
+
+
+def test_oracle_train_step_reduces_nothing_but_runs():
+    cfg = O.OracleConfig(r=2, max_decode_iter=3, vocab_size=12)
+    p = O.init_params(cfg, 1, True)
+    m = {k: torch.zeros_like(v) for k, v in p.items()}
+    v = {k: torch.zeros_like(t) for k, t in p.items()}
+    inp = O.synthetic_inputs(cfg, 2, 8, 3, seed=0)
+    l0, gn = O.train_step(p, m, v, inp, cfg, lr=cfg.init_lr, step=1)
+    l1, _ = O.train_step(p, m, v, inp, cfg, lr=cfg.init_lr, step=2)
+    assert float(gn) > 0 and float(l1) < float(l0)          # same batch twice: Adam must make progress

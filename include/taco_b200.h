@@ -157,6 +157,8 @@ typedef struct taco_decoder_args {
     float*         align;        /* [B][T][Tx]    alignment history                           */
     void*          workspace;    /* taco_decoder_workspace_bytes                              */
     uint64_t*      step_ns;      /* [T] device buffer: %globaltimer at the start of each step, or NULL */
+    float*         h_save;       /* [3][T][B][256] the three GRU state sequences (training: input of
+                                    taco_decoder_bwd's batched recomputation), or NULL          */
 } taco_decoder_args;
 
 int taco_decoder_fwd(const taco_decoder_args* a, void* stream);
@@ -167,6 +169,104 @@ int taco_l1_partial_count(void);   /* floats partial_ws must hold */
 
 /* number of kernels this library has launched so far in this process (for bench.py's gpu_launches) */
 unsigned long long taco_launch_count(void);
+
+/* ==========================================================================================
+ * Training path.  Replaces what `tf.gradients` + `tf.clip_by_global_norm` + `tf.train.AdamOptimizer`
+ * build for Tacotron.add_train_op (models/tacotron.py:167-185) over the forward graph
+ * (models/tacotron.py:107-165, models/ops.py:27-132).  The host side (tacotron_b200/models/grad.py)
+ * is the hand-written reverse of the forward; the entry points below are its arithmetic.
+ * The semantics of each are pinned by the function of the same name in tests/mirror_kernels.py.
+ * ========================================================================================== */
+
+/* C_z[M][N] = beta*C_z + opA_z[M][K] . opB_z[K][N]  for z < batch  (fp32 FFMA; beta in {0,1}).
+ *   ta=0: A stored [M][K]: opA[m][k] = A[m + sh(k)][k mod kper],  sh(k) = shift + z*bshift + (k / kper)*dshift
+ *   ta=1: A stored [K][M]: opA[m][k] = A[k + sh][m],              sh    = shift + z*bshift
+ *         a shifted stored row that leaves its block of `period` rows (0: one block) reads as zero.
+ *   tb=0: B stored [K][N];  tb=1: B stored [N][kper] per K-segment j at offset j*b_tap_stride.
+ * This one contraction covers every dense / conv1d('same') data gradient (row shift = tap offset, zero fill =
+ * the 'same' padding per utterance), every weight gradient (ta=1, batch = taps, split-K with atomics), the
+ * h(t-1) products of the recurrent layers (shift = one step) and the per-utterance attention context GEMMs.  */
+typedef struct taco_gemm_desc {
+    const float* A; int64_t lda;
+    const float* B; int64_t ldb;
+    float*       C; int64_t ldc;
+    int32_t M, N, K;
+    int32_t ta, tb;
+    float   beta;
+    int32_t shift, period;
+    int32_t taps, dshift, kper;
+    int64_t b_tap_stride;
+    int32_t batch;
+    int64_t a_bstride, b_bstride, c_bstride;   /* in elements */
+    int32_t bshift;
+} taco_gemm_desc;
+int taco_gemm(const taco_gemm_desc* d, void* stream);
+
+/* out[n] += sum_m A[m][n] * (Bm ? Bm[m][n] - (R ? R[m][n] : 0) : 1)     (bias / batch-norm gradients) */
+int taco_colsum(float* out, const float* A, int64_t lda, const float* Bm, int64_t ldb, const float* R, int64_t ldr,
+                int M, int N, void* stream);
+/* in place C = act(C + bias) (bias may be NULL); out = X * H[row+shift] (zero outside the period block) */
+int taco_bias_act(float* C, int64_t ldc, int M, int N, const float* bias, int act, void* stream);
+int taco_mul_shift(float* out, int64_t ldo, const float* X, int64_t ldx, const float* H, int64_t ldh, int M, int N,
+                   int shift, int period, void* stream);
+/* backward of taco_linear_fwd's epilogue: dZ = dY*gain*scale[n]*mask; relu mask = Y > 0 (no scale) or
+ * (Y - R - shift[n])*scale[n] > 0.  dZ may alias dY.                                                       */
+int taco_epi_bwd(float* dZ, int64_t lddz, const float* dY, int64_t lddy, const float* Y, int64_t ldy, const float* R,
+                 int64_t ldr, int M, int N, int relu, const float* scale, const float* shift, float gain, void* stream);
+/* in place dropout with an explicit keep mask [M][N]: X = keep ? X*gain : 0   (tacotron.py:41,43) */
+int taco_epi_fwd_keep(float* X, int64_t ldx, const uint8_t* keep, int M, int N, float gain, void* stream);
+/* dbeta += S1; dgamma += (S2 - beta*S1)/gamma   (tf.layers.batch_normalization, inference form, ops.py:64,87) */
+int taco_bn_param_grad(float* dgamma, float* dbeta, const float* S1, const float* S2, const float* gamma,
+                       const float* beta, int N, void* stream);
+/* tf.layers.max_pooling1d(2,1,'same') backward (ops.py:66-71); ties go to the first element */
+int taco_maxpool_bwd(float* dX, const float* dP, const float* X, int B, int T, int C, void* stream);
+/* highway gate (ops.py:32-45) from saved pre-activations P = [h_pre | t_pre] ([M][2U]) and its backward */
+int taco_highway_fwd(float* Y, int64_t ldy, const float* P, int64_t ldp, const float* X, int64_t ldx, int M, int U,
+                     void* stream);
+int taco_highway_bwd(float* dP, int64_t lddp, float* dXd, int64_t lddx, const float* dY, int64_t lddy, const float* P,
+                     int64_t ldp, const float* X, int64_t ldx, int M, int U, void* stream);
+/* dA = beta*dA + sign(A - B)    (tacotron.py:158-160) */
+int taco_l1_bwd(float* dA, const float* A, const float* B, int64_t n, float beta, void* stream);
+/* dTable[ids[m]][:] += dRows[m][:]   (embedding_lookup backward, tacotron.py:111-114) */
+int taco_scatter_add_rows(float* dTable, const int32_t* ids, const float* dRows, int rows, int width, int vocab,
+                          void* stream);
+/* serial part of the bidirectional-GRU backward (ops.py:118-128): see csrc/gru_bwd.cu */
+int taco_bigru_bwd(float* dxp, const float* dOut, const float* out, const float* ACT, const float* Wg_h_fw,
+                   const float* Wc_h_fw, const float* Wg_h_bw, const float* Wc_h_bw, int B, int T, void* stream);
+/* decoder step inputs of the Training / ScheduledOutputTraining helpers, time-major: Xin [T][B][80], sel [T][B] */
+int taco_dec_inputs(float* Xin, uint8_t* sel, const float* mel, const float* y, const uint8_t* sample_mask, int B, int T,
+                    int r, int sched, void* stream);
+
+/* serial part of the attention-decoder backward (tacotron.py:46-105,136-138): see csrc/decoder_bwd.cu.
+ * All tensors time-major ([T][B][n]) unless noted; B <= 32.                                               */
+typedef struct taco_decoder_bwd_args {
+    int32_t B, T, Tx, r;
+    float   keep_scale;
+    const float *W_a, *W_q, *W_out, *W_in, *W1, *W2, *v;      /* TF layouts (see taco_decoder_weights) */
+    const float *Wg[3], *Wc[3];
+    const float *dy_ext;                  /* [T][B][80r] gradient arriving at seq2seq_output            */
+    const float *RU[3], *C[3], *H[3];     /* [T][B][512] gates, [T][B][256] candidates, states          */
+    const float *align;                   /* [B][T][Tx]                                                 */
+    const float *values, *keys;           /* [B][Tx][256]                                               */
+    const float *PQ, *PN1, *PN2;          /* [T][B][256] y.W_q ; pre-net activations [T][B][256|128]    */
+    const uint8_t* sel;                   /* [T][B] 1 = step input was the model's own previous output  */
+    float *DATT, *DY, *DPQ;               /* out: pre-activation gradients per step                     */
+    float *DSCORE;                        /* out: [B][T][Tx]                                            */
+    float *DCTX, *DG[3], *DC[3], *DZ, *DPN2, *DPN1, *DX;
+    float *workspace;                     /* taco_decoder_bwd_workspace_bytes                           */
+} taco_decoder_bwd_args;
+size_t taco_decoder_bwd_workspace_bytes(void);
+int    taco_decoder_bwd(const taco_decoder_bwd_args* a, void* stream);
+/* dkeys[b][j][d] = sum_t DSCORE[b][t][j] v[d] (1-e^2); dv[d] += sum DSCORE e; e = tanh(keys + PQ[t][b]) */
+int taco_attn_bwd_post(float* dkeys, float* dv, const float* DSCORE, const float* keys, const float* PQ, const float* v,
+                       int B, int T, int Tx, void* stream);
+
+/* tf.clip_by_global_norm(cap_grads) + tf.train.AdamOptimizer (tacotron.py:170-184) on the flat
+ * parameter / gradient buffers: out = sum x^2 (deterministic); g *= clip/max(sqrt(sumsq), clip);
+ * m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr_t m/(sqrt(v)+eps), lr_t = lr sqrt(1-b2^t)/(1-b1^t).   */
+int taco_sumsq(const float* x, int64_t n, float* partial_ws, float* out, void* stream);
+int taco_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float b1, float b2, float eps,
+                   float clip, const float* sumsq, void* stream);
 
 #ifdef __cplusplus
 }

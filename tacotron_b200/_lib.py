@@ -53,6 +53,33 @@ class DecoderArgs(C.Structure):
         ("keep_scale", C.c_float), ("mode", C.c_int32),
         ("B", C.c_int32), ("Tx", C.c_int32), ("T", C.c_int32), ("r", C.c_int32),
         ("y", C.c_void_p), ("align", C.c_void_p), ("workspace", C.c_void_p), ("step_ns", C.c_void_p),
+        ("h_save", C.c_void_p),
+    ]
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("lda", C.c_int64), ("B", C.c_void_p), ("ldb", C.c_int64), ("C", C.c_void_p), ("ldc", C.c_int64),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("ta", C.c_int32), ("tb", C.c_int32), ("beta", C.c_float),
+        ("shift", C.c_int32), ("period", C.c_int32), ("taps", C.c_int32), ("dshift", C.c_int32), ("kper", C.c_int32),
+        ("b_tap_stride", C.c_int64), ("batch", C.c_int32),
+        ("a_bstride", C.c_int64), ("b_bstride", C.c_int64), ("c_bstride", C.c_int64), ("bshift", C.c_int32),
+    ]
+
+
+class DecoderBwdArgs(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("T", C.c_int32), ("Tx", C.c_int32), ("r", C.c_int32), ("keep_scale", C.c_float),
+        ("W_a", C.c_void_p), ("W_q", C.c_void_p), ("W_out", C.c_void_p), ("W_in", C.c_void_p), ("W1", C.c_void_p),
+        ("W2", C.c_void_p), ("v", C.c_void_p),
+        ("Wg", C.c_void_p * 3), ("Wc", C.c_void_p * 3),
+        ("dy_ext", C.c_void_p),
+        ("RU", C.c_void_p * 3), ("C", C.c_void_p * 3), ("H", C.c_void_p * 3),
+        ("align", C.c_void_p), ("values", C.c_void_p), ("keys", C.c_void_p),
+        ("PQ", C.c_void_p), ("PN1", C.c_void_p), ("PN2", C.c_void_p), ("sel", C.c_void_p),
+        ("DATT", C.c_void_p), ("DY", C.c_void_p), ("DPQ", C.c_void_p), ("DSCORE", C.c_void_p),
+        ("DCTX", C.c_void_p), ("DG", C.c_void_p * 3), ("DC", C.c_void_p * 3), ("DZ", C.c_void_p), ("DPN2", C.c_void_p),
+        ("DPN1", C.c_void_p), ("DX", C.c_void_p), ("workspace", C.c_void_p),
     ]
 
 
@@ -68,6 +95,11 @@ EXPORTS = [
     "taco_maxpool_fwd", "taco_gather_rows", "taco_mask_rows", "taco_bigru_fwd",
     "taco_decoder_packed_bytes", "taco_decoder_workspace_bytes", "taco_decoder_pack", "taco_decoder_fwd",
     "taco_l1_loss_fwd", "taco_l1_partial_count", "taco_launch_count",
+    # training path
+    "taco_gemm", "taco_colsum", "taco_bias_act", "taco_mul_shift", "taco_epi_bwd", "taco_epi_fwd_keep", "taco_bn_param_grad",
+    "taco_maxpool_bwd", "taco_highway_fwd", "taco_highway_bwd", "taco_l1_bwd", "taco_scatter_add_rows", "taco_bigru_bwd",
+    "taco_dec_inputs", "taco_decoder_bwd_workspace_bytes", "taco_decoder_bwd", "taco_attn_bwd_post", "taco_sumsq",
+    "taco_adam_step",
 ]
 
 
@@ -100,6 +132,26 @@ def lib():
     L.taco_l1_loss_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     L.taco_l1_partial_count.restype = C.c_int
     L.taco_launch_count.restype = C.c_ulonglong
+    vp, i64, i32, f32 = C.c_void_p, C.c_int64, C.c_int, C.c_float
+    L.taco_gemm.argtypes = [C.POINTER(GemmDesc), vp]
+    L.taco_colsum.argtypes = [vp, vp, i64, vp, i64, vp, i64, i32, i32, vp]
+    L.taco_bias_act.argtypes = [vp, i64, i32, i32, vp, i32, vp]
+    L.taco_mul_shift.argtypes = [vp, i64, vp, i64, vp, i64, i32, i32, i32, i32, vp]
+    L.taco_epi_bwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, i32, vp, vp, f32, vp]
+    L.taco_epi_fwd_keep.argtypes = [vp, i64, vp, i32, i32, f32, vp]
+    L.taco_bn_param_grad.argtypes = [vp, vp, vp, vp, vp, vp, i32, vp]
+    L.taco_maxpool_bwd.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+    L.taco_highway_fwd.argtypes = [vp, i64, vp, i64, vp, i64, i32, i32, vp]
+    L.taco_highway_bwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, vp]
+    L.taco_l1_bwd.argtypes = [vp, vp, vp, i64, f32, vp]
+    L.taco_scatter_add_rows.argtypes = [vp, vp, vp, i32, i32, i32, vp]
+    L.taco_bigru_bwd.argtypes = [vp] * 8 + [i32, i32, vp]
+    L.taco_dec_inputs.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    L.taco_decoder_bwd_workspace_bytes.restype = C.c_size_t
+    L.taco_decoder_bwd.argtypes = [C.POINTER(DecoderBwdArgs), vp]
+    L.taco_attn_bwd_post.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
+    L.taco_sumsq.argtypes = [vp, i64, vp, vp, vp]
+    L.taco_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, vp, vp]
     for name in EXPORTS:                      # every declared symbol must resolve (AttributeError otherwise)
         getattr(L, name)
     _lib = L

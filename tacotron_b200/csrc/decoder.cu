@@ -693,6 +693,7 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
                         const float hn = uu * h_loc[gi * 64 + rr * 8 + j] + (1.0f - uu) * cnd;
                         h_loc[gi * 64 + rr * 8 + j] = hn;
                         ll_store(ws + P.ws.h[gi] + ro * U + perm8(col), hn, tag_out);
+                        if (A.h_save && row < B) A.h_save[(((int64_t)gi * T + t) * B + row) * U + col] = hn;   // training: BPTT input
                         if (gi == 2) ll_store(ws + P.ws.s + ro * U + perm8(col), z_loc[rr * 8 + j] + hn, tag_out);
                     } break;
                     case K_OUT: {

@@ -1,0 +1,312 @@
+// decoder_bwd.cu -- serial part of the attention-decoder backward: back-propagation through the T steps of
+// BasicDecoder(OutputProjectionWrapper(InputProjectionWrapper(ResidualWrapper(MultiRNNCell(3 x GRUCell(256))))),
+// AttentionWrapper(BahdanauAttention), Training/ScheduledOutputTrainingHelper)   models/tacotron.py:46-105, :136-138.
+//
+// The caller (tacotron_b200/models/grad.py::decoder_bwd) has already recomputed, in batch, every activation of
+// every step from what the forward kernel saved (y, alignments, the three GRU state sequences), and will turn the
+// PRE-ACTIVATION gradients this kernel stores per step into all weight gradients with batched GEMMs.  What is left
+// here is the data-gradient chain, which really is serial in t (11 dependent stages per step):
+//
+//   1  [dy_att | dctx] = dattn(t) . W_a^T                         (+ pre-net L2 backward of step t+1)
+//   2  attention: dalign = dctx.values, softmax backward -> dscore, dpq = sum_j dscore_j v (1-e_j^2)
+//                                                                  (+ pre-net L1 backward of step t+1 -> dx(t+1))
+//   3  dy(t) = dy_ext + dy_att + dpq.W_q^T + [sampled] dx(t+1)
+//   4  dres = dy.W_out^T ; GRU3 element-wise part                  (ResidualWrapper: dz += dres, dh3 += dres)
+//   5,6 x3  GRU_i:  [dIN_c | drh] = dc_pre.Wc_i^T ;  [dIN_g | dh_g] = [dr_pre,du_pre].Wg_i^T ; carries
+//   7  [dpn2 | dattn(t-1)] = dz.W_in^T
+//
+// One cooperative kernel runs all T steps; stages are separated by grid.sync().  Every stage is a skinny GEMM
+// out[32 x N] = in[32 x K] . W^T with W rows contiguous (TF [in,out] layouts make every data-gradient a "NT"
+// product): one warp per output column, lane = batch row, the 32 x K input staged once per CTA in shared memory.
+// Inter-stage data lives in L2 (ld.global.cg; never the non-coherent path).  This is a first, simple schedule --
+// the same dataflow treatment as the forward kernel (decoder.cu) is the planned optimisation.
+// Semantics pinned by tests/mirror_kernels.py::decoder_bwd.
+#include <cooperative_groups.h>
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int U = 256;        // decoder / attention units
+constexpr int RB = 32;        // rows (utterances) per launch
+constexpr int NW = 8;         // warps per CTA
+constexpr int MAXK = 512;
+
+struct DecBwdP {
+    int B, T, Tx, OUT, MF;
+    float ks;
+    const float *W_a, *W_q, *W_out, *W_in, *W1, *W2, *v, *Wg[3], *Wc[3];
+    const float *dy_ext, *RU[3], *C[3], *Hs[3], *align, *values, *keys, *PQ, *PN1, *PN2;
+    const uint8_t* sel;
+    float *DATT, *DY, *DPQ, *DSCORE, *DCTX, *DG[3], *DC[3], *DZ, *DPN2, *DPN1, *DX;
+    float* ws;
+};
+
+// scratch layout (floats): every buffer is [32][ld]
+constexpr int WS_DYATT = 0;                       // [32][512]
+constexpr int WS_DRES = WS_DYATT + RB * 512;      // [32][256]
+constexpr int WS_DINC = WS_DRES + RB * U;         // [32][256]
+constexpr int WS_DHR = WS_DINC + RB * U;          // [32][256]
+constexpr int WS_DHU = WS_DHR + RB * U;           // [3][32][256]
+constexpr int WS_DHC = WS_DHU + 3 * RB * U;       // [3][32][256]   carries, zeroed by the host
+constexpr int WS_TOTAL = WS_DHC + 3 * RB * U;
+
+// out[row][n] = sum_k in[row][k] * W[n][k]   (row = lane).  Columns are dealt to the warps of the whole grid; with
+// `reverse` they are dealt from the last warp backwards so that two GEMMs of one stage land on different CTAs.
+template <class Epi>
+__device__ __forceinline__ void skinny_gemm(float* in_s, const float* in, int ldi, int rows, int K, const float* __restrict__ W, int ldw,
+                                            int N, bool reverse, Epi epi) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int TW = gridDim.x * NW;
+    const int first = reverse ? (TW - 1 - (int)(blockIdx.x * NW + NW - 1)) : (int)(blockIdx.x * NW);   // smallest column index of this CTA
+    if (first >= N) return;                              // CTA-uniform: no column for any warp of this CTA
+    const int lds = K + 1;
+    const int K4 = K >> 2;
+    for (int idx = tid; idx < RB * K4; idx += blockDim.x) {
+        const int row = idx / K4, k4 = idx - row * K4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < rows) v = __ldcg(reinterpret_cast<const float4*>(in + (int64_t)row * ldi) + k4);
+        float* d = in_s + row * lds + 4 * k4;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+    __syncthreads();
+    const int gw = blockIdx.x * NW + warp;
+    for (int n = reverse ? (TW - 1 - gw) : gw; n < N; n += TW) {
+        const float4* wrow = reinterpret_cast<const float4*>(W + (int64_t)n * ldw);
+        const float* a = in_s + lane * lds;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+        for (int k4 = 0; k4 < K4; ++k4) {
+            const float4 w = __ldg(wrow + k4);
+            a0 = fmaf(a[4 * k4 + 0], w.x, a0);
+            a1 = fmaf(a[4 * k4 + 1], w.y, a1);
+            a2 = fmaf(a[4 * k4 + 2], w.z, a2);
+            a3 = fmaf(a[4 * k4 + 3], w.w, a3);
+        }
+        epi(lane, n, (a0 + a1) + (a2 + a3));
+    }
+    __syncthreads();                                     // in_s is reused by the next GEMM
+}
+
+__global__ void __launch_bounds__(256, 1) decoder_bwd_kernel(const DecBwdP p) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) float in_s[];        // [32][MAXK+1]
+    __shared__ float dctx_s[U], dal_s[256], ds_s[256], red_s[NW];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int B = p.B, T = p.T, Tx = p.Tx, OUT = p.OUT, MF = p.MF;
+    const int lo = OUT - MF;
+    float* dyatt = p.ws + WS_DYATT;
+    float* dres = p.ws + WS_DRES;
+    float* dINc = p.ws + WS_DINC;
+    float* dhr = p.ws + WS_DHR;
+    float* dhu = p.ws + WS_DHU;
+    float* dhc = p.ws + WS_DHC;
+
+    // element-wise head of GRU layer i at step t for (row, unit n): consumes the gradient arriving at h_i(t)
+    auto gru_head = [&](int i, int t, int row, int n, float dh_in) {
+        const int64_t o = (int64_t)t * B + row;
+        const float dh = dh_in + __ldcg(dhc + (i * RB + row) * U + n);
+        const float hprev = (t > 0) ? __ldg(p.Hs[i] + (o - B) * U + n) : 0.f;
+        const float u = __ldg(p.RU[i] + o * 2 * U + U + n);
+        const float c = __ldg(p.C[i] + o * U + n);
+        p.DG[i][o * 2 * U + U + n] = dh * (hprev - c) * u * (1.0f - u);     // du_pre
+        p.DC[i][o * U + n] = dh * (1.0f - u) * (1.0f - c * c);               // dc_pre
+        dhu[(i * RB + row) * U + n] = dh * u;
+    };
+
+    for (int t = T - 1; t >= -1; --t) {
+        const int tt = t + 1;
+        // ================= stage 1: attention layer backward  |  pre-net layer 2 backward of step t+1 =================
+        if (t >= 0) {
+            const float* in = p.DATT + (int64_t)t * B * U;
+            skinny_gemm(in_s, in, U, B, U, p.W_a, U, OUT + U, false, [&](int row, int n, float v) {
+                if (row >= B) return;
+                if (n < OUT) dyatt[row * 512 + n] = v;
+                else p.DCTX[((int64_t)t * B + row) * U + (n - OUT)] = v;
+            });
+        }
+        if (tt < T) {
+            const float* in = p.DPN2 + (int64_t)tt * B * 128;
+            skinny_gemm(in_s, in, 128, B, 128, p.W2, 128, 256, true, [&](int row, int n, float v) {
+                if (row >= B) return;
+                const int64_t o = ((int64_t)tt * B + row) * 256 + n;
+                p.DPN1[o] = (__ldg(p.PN1 + o) > 0.f) ? v * p.ks : 0.f;
+            });
+        }
+        grid.sync();
+        // ================= stage 2: attention scores backward  |  pre-net layer 1 backward of step t+1 ================
+        if (t >= 0) {
+            for (int b = (int)gridDim.x - 1 - (int)blockIdx.x; b < B; b += gridDim.x) {
+                dctx_s[tid] = __ldcg(p.DCTX + ((int64_t)t * B + b) * U + tid);
+                __syncthreads();
+                for (int j = warp; j < Tx; j += NW) {                       // dalign_j = dctx . values_j
+                    const float* vj = p.values + ((int64_t)b * Tx + j) * U;
+                    float s = 0.f;
+#pragma unroll
+                    for (int i = 0; i < U / 32; ++i) s = fmaf(dctx_s[lane + 32 * i], __ldg(vj + lane + 32 * i), s);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                    if (lane == 0) dal_s[j] = s;
+                }
+                __syncthreads();
+                const float aj = (tid < Tx) ? __ldg(p.align + ((int64_t)b * T + t) * Tx + tid) : 0.f;
+                float part = (tid < Tx) ? aj * dal_s[tid] : 0.f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                if (lane == 0) red_s[warp] = part;
+                __syncthreads();
+                float tot = 0.f;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) tot += red_s[w];
+                if (tid < Tx) {                                              // softmax backward
+                    const float ds = aj * (dal_s[tid] - tot);
+                    ds_s[tid] = ds;
+                    p.DSCORE[((int64_t)b * T + t) * Tx + tid] = ds;
+                }
+                __syncthreads();
+                {                                                            // dpq_d = v_d sum_j dscore_j (1 - e_jd^2)
+                    const int d = tid;
+                    const float pq = __ldg(p.PQ + ((int64_t)t * B + b) * U + d);
+                    const float* kb = p.keys + (int64_t)b * Tx * U + d;
+                    float acc = 0.f;
+                    for (int j = 0; j < Tx; ++j) {
+                        const float ds = ds_s[j];
+                        if (ds != 0.f) {
+                            const float e = tanhf_acc(__ldg(kb + (int64_t)j * U) + pq);
+                            acc = fmaf(ds, 1.0f - e * e, acc);
+                        }
+                    }
+                    p.DPQ[((int64_t)t * B + b) * U + d] = acc * __ldg(p.v + d);
+                }
+                __syncthreads();
+            }
+        }
+        if (tt < T) {
+            const float* in = p.DPN1 + (int64_t)tt * B * 256;
+            skinny_gemm(in_s, in, 256, B, 256, p.W1, 256, MF, false, [&](int row, int n, float v) {
+                if (row >= B) return;
+                p.DX[((int64_t)tt * B + row) * MF + n] = v;
+            });
+        }
+        grid.sync();
+        if (t < 0) break;
+        // ================= stage 3: query layer backward, total gradient at y(t) ======================================
+        {
+            const float* in = p.DPQ + (int64_t)t * B * U;
+            skinny_gemm(in_s, in, U, B, U, p.W_q, U, OUT, false, [&](int row, int n, float v) {
+                if (row >= B) return;
+                const int64_t o = ((int64_t)t * B + row) * OUT + n;
+                float dy = __ldg(p.dy_ext + o) + __ldcg(dyatt + row * 512 + n) + v;
+                if (n >= lo && tt < T && p.sel[(int64_t)tt * B + row]) dy += __ldcg(p.DX + ((int64_t)tt * B + row) * MF + (n - lo));
+                p.DY[o] = dy;
+            });
+        }
+        grid.sync();
+        // ================= stage 4: output projection backward + GRU3 head ============================================
+        {
+            const float* in = p.DY + (int64_t)t * B * OUT;
+            skinny_gemm(in_s, in, OUT, B, OUT, p.W_out, OUT, U, false, [&](int row, int n, float v) {
+                if (row >= B) return;
+                dres[row * U + n] = v;
+                gru_head(2, t, row, n, v);
+            });
+        }
+        grid.sync();
+        // ================= stages 5/6 x 3: the GRU stack, top to bottom ===============================================
+        for (int i = 2; i >= 0; --i) {
+            {   // [dIN_c | drh] = dc_pre . Wc_i^T
+                const float* in = p.DC[i] + (int64_t)t * B * U;
+                skinny_gemm(in_s, in, U, B, U, p.Wc[i], U, 2 * U, false, [&](int row, int n, float v) {
+                    if (row >= B) return;
+                    if (n < U) { dINc[row * U + n] = v; return; }
+                    const int k = n - U;
+                    const int64_t o = (int64_t)t * B + row;
+                    const float hprev = (t > 0) ? __ldg(p.Hs[i] + (o - B) * U + k) : 0.f;
+                    const float r = __ldg(p.RU[i] + o * 2 * U + k);
+                    p.DG[i][o * 2 * U + k] = v * hprev * r * (1.0f - r);     // dr_pre
+                    dhr[row * U + k] = v * r;
+                });
+            }
+            grid.sync();
+            {   // [dIN_g | dh_g] = [dr_pre, du_pre] . Wg_i^T
+                const float* in = p.DG[i] + (int64_t)t * B * 2 * U;
+                skinny_gemm(in_s, in, 2 * U, B, 2 * U, p.Wg[i], 2 * U, 2 * U, false, [&](int row, int n, float v) {
+                    if (row >= B) return;
+                    if (n < U) {
+                        const float dIN = __ldcg(dINc + row * U + n) + v;   // gradient at the layer input
+                        if (i > 0) gru_head(i - 1, t, row, n, dIN);
+                        else p.DZ[((int64_t)t * B + row) * U + n] = __ldcg(dres + row * U + n) + dIN;
+                    } else {
+                        const int k = n - U;
+                        dhc[(i * RB + row) * U + k] = __ldcg(dhu + (i * RB + row) * U + k) + __ldcg(dhr + row * U + k) + v;
+                    }
+                });
+            }
+            grid.sync();
+        }
+        // ================= stage 7: input projection backward =========================================================
+        {
+            const float* in = p.DZ + (int64_t)t * B * U;
+            skinny_gemm(in_s, in, U, B, U, p.W_in, U, 128 + U, false, [&](int row, int n, float v) {
+                if (row >= B) return;
+                if (n < 128) {
+                    const int64_t o = ((int64_t)t * B + row) * 128 + n;
+                    p.DPN2[o] = (__ldg(p.PN2 + o) > 0.f) ? v * p.ks : 0.f;
+                } else if (t > 0) {
+                    p.DATT[((int64_t)(t - 1) * B + row) * U + (n - 128)] = v;
+                }
+            });
+        }
+        grid.sync();
+    }
+}
+
+}  // namespace
+
+extern "C" size_t taco_decoder_bwd_workspace_bytes(void) { return (size_t)WS_TOTAL * 4; }
+
+extern "C" int taco_decoder_bwd(const taco_decoder_bwd_args* a, void* stream) {
+    TACO_CHECK(a, "taco_decoder_bwd: NULL args");
+    TACO_CHECK(a->B >= 1 && a->B <= RB, "taco_decoder_bwd: B=%d must be in [1,%d] per launch", a->B, RB);
+    TACO_CHECK(a->T >= 1 && a->Tx >= 1 && a->Tx <= 256, "taco_decoder_bwd: T=%d Tx=%d (Tx <= 256)", a->T, a->Tx);
+    TACO_CHECK(a->r >= 1 && 80 * a->r <= MAXK && ((80 * a->r) % 4) == 0, "taco_decoder_bwd: r=%d unsupported", a->r);
+    TACO_CHECK(a->W_a && a->W_q && a->W_out && a->W_in && a->W1 && a->W2 && a->v, "taco_decoder_bwd: NULL weight");
+    TACO_CHECK(a->dy_ext && a->align && a->values && a->keys && a->PQ && a->PN1 && a->PN2 && a->sel, "taco_decoder_bwd: NULL saved tensor");
+    TACO_CHECK(a->DATT && a->DY && a->DPQ && a->DSCORE && a->DCTX && a->DZ && a->DPN2 && a->DPN1 && a->DX && a->workspace,
+               "taco_decoder_bwd: NULL output");
+    DecBwdP p;
+    memset(&p, 0, sizeof(p));
+    p.B = a->B; p.T = a->T; p.Tx = a->Tx; p.OUT = 80 * a->r; p.MF = 80; p.ks = a->keep_scale;
+    p.W_a = a->W_a; p.W_q = a->W_q; p.W_out = a->W_out; p.W_in = a->W_in; p.W1 = a->W1; p.W2 = a->W2; p.v = a->v;
+    for (int i = 0; i < 3; ++i) {
+        TACO_CHECK(a->Wg[i] && a->Wc[i] && a->RU[i] && a->C[i] && a->H[i] && a->DG[i] && a->DC[i], "taco_decoder_bwd: NULL GRU tensor %d", i);
+        p.Wg[i] = a->Wg[i]; p.Wc[i] = a->Wc[i]; p.RU[i] = a->RU[i]; p.C[i] = a->C[i]; p.Hs[i] = a->H[i];
+        p.DG[i] = a->DG[i]; p.DC[i] = a->DC[i];
+    }
+    p.dy_ext = a->dy_ext; p.align = a->align; p.values = a->values; p.keys = a->keys; p.PQ = a->PQ; p.PN1 = a->PN1; p.PN2 = a->PN2;
+    p.sel = a->sel;
+    p.DATT = a->DATT; p.DY = a->DY; p.DPQ = a->DPQ; p.DSCORE = a->DSCORE; p.DCTX = a->DCTX; p.DZ = a->DZ; p.DPN2 = a->DPN2;
+    p.DPN1 = a->DPN1; p.DX = a->DX;
+    p.ws = a->workspace;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = (size_t)RB * (MAXK + 1) * 4;
+    static int max_ctas = 0;
+    if (max_ctas == 0) {
+        TACO_CUDA(cudaFuncSetAttribute(decoder_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int dev = 0, sms = 0, per_sm = 0;
+        TACO_CUDA(cudaGetDevice(&dev));
+        TACO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        TACO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decoder_bwd_kernel, 256, smem));
+        TACO_CHECK(per_sm >= 1, "taco_decoder_bwd: kernel does not fit on an SM");
+        max_ctas = sms * per_sm;
+    }
+    const int G = max_ctas < 128 ? max_ctas : 128;
+    // carries start at zero; dattn(T-1) = 0 (the last attention state feeds nothing)
+    TACO_CUDA(cudaMemsetAsync(a->workspace, 0, (size_t)WS_TOTAL * 4, st));
+    TACO_CUDA(cudaMemsetAsync(a->DATT + (int64_t)(a->T - 1) * a->B * U, 0, (size_t)a->B * U * 4, st));
+    void* args[] = {(void*)&p};
+    TACO_CUDA(cudaLaunchCooperativeKernel((void*)decoder_bwd_kernel, dim3(G), dim3(256), args, smem, st));
+    ++g_taco_launches;
+    return 0;
+}

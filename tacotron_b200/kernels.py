@@ -1,0 +1,201 @@
+"""Tensor-level namespace over the training entry points of libtaco_b200.so (include/taco_b200.h, "Training path").
+
+This is the `K` that tacotron_b200/models/grad.py is written against: every function takes CUDA fp32 tensors
+(2-D views may be strided in their leading dimension), extracts pointers / leading strides and calls the C-ABI on
+the current stream.  There is NO fallback: a missing library or a non-CUDA tensor raises.
+Semantics = the docstrings of the same names in tests/mirror_kernels.py (the kernels are tested against them).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3
+
+
+def _chk2(t, name):
+    if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and (t.shape[1] == 1 or t.stride(1) == 1)):
+        raise L.TacoError(f"{name}: expected a CUDA fp32 [M,N] view with unit inner stride, got {tuple(t.shape)} "
+                          f"{t.dtype} {t.device} strides {t.stride()}")
+    return t
+
+
+def _ld(t):
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], t.stride(0))
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _st():
+    return L.current_stream()
+
+
+def empty(shape, like, dtype=None):
+    return torch.empty(shape, dtype=dtype or like.dtype, device=like.device)
+
+
+def zeros(shape, like, dtype=None):
+    return torch.zeros(shape, dtype=dtype or like.dtype, device=like.device)
+
+
+def gemm(Cm, A, B, *, ta=False, tb=False, beta=0.0, shift=0, period=0, taps=1, dshift=0, kper=0, b_tap_stride=0,
+         batch=1, a_bstride=0, b_bstride=0, c_bstride=0, bshift=0):
+    _chk2(Cm, "gemm C"); _chk2(A, "gemm A"); _chk2(B, "gemm B")
+    M, N = Cm.shape
+    if ta:
+        K, Ma = A.shape
+        assert Ma == M, (A.shape, Cm.shape)
+    else:
+        Ma, Kseg = A.shape
+        assert Ma == M, (A.shape, Cm.shape)
+        K = Kseg * taps
+        if taps > 1:
+            assert kper == Kseg
+    if tb:
+        assert B.shape[0] == N and B.shape[1] * taps == K, (B.shape, N, K)
+    else:
+        assert B.shape == (K, N), (B.shape, K, N)
+    d = L.GemmDesc()
+    d.A = A.data_ptr(); d.lda = _ld(A); d.B = B.data_ptr(); d.ldb = _ld(B); d.C = Cm.data_ptr(); d.ldc = _ld(Cm)
+    d.M = M; d.N = N; d.K = K; d.ta = int(ta); d.tb = int(tb); d.beta = float(beta)
+    d.shift = shift; d.period = period; d.taps = taps; d.dshift = dshift; d.kper = kper; d.b_tap_stride = b_tap_stride
+    d.batch = batch; d.a_bstride = a_bstride; d.b_bstride = b_bstride; d.c_bstride = c_bstride; d.bshift = bshift
+    L.check(L.lib().taco_gemm(C.byref(d), _st()), "taco_gemm")
+
+
+def colsum(out, A, Bm=None, R=None, beta=1.0):
+    _chk2(A, "colsum A")
+    M, N = A.shape
+    assert out.is_contiguous() and out.numel() == N
+    if beta == 0.0:
+        out.zero_()
+    else:
+        assert beta == 1.0
+    L.check(L.lib().taco_colsum(_p(out), _p(A), _ld(A), _p(Bm), _ld(Bm) if Bm is not None else 0, _p(R),
+                                _ld(R) if R is not None else 0, M, N, _st()), "taco_colsum")
+
+
+def bias_act_(Cm, bias, act):
+    _chk2(Cm, "bias_act C")
+    L.check(L.lib().taco_bias_act(_p(Cm), _ld(Cm), Cm.shape[0], Cm.shape[1], _p(bias), act, _st()), "taco_bias_act")
+
+
+def mul_shift(out, X, Hm, shift, period):
+    _chk2(out, "mul_shift out"); _chk2(X, "mul_shift X"); _chk2(Hm, "mul_shift H")
+    M, N = out.shape
+    L.check(L.lib().taco_mul_shift(_p(out), _ld(out), _p(X), _ld(X), _p(Hm), _ld(Hm), M, N, shift, period, _st()), "taco_mul_shift")
+
+
+def epi_bwd(dZ, dY, Y, relu, scale=None, shift=None, gain=1.0, R=None):
+    _chk2(dZ, "epi_bwd dZ"); _chk2(dY, "epi_bwd dY")
+    M, N = dY.shape
+    L.check(L.lib().taco_epi_bwd(_p(dZ), _ld(dZ), _p(dY), _ld(dY), _p(Y), _ld(Y) if Y is not None else 0, _p(R),
+                                 _ld(R) if R is not None else 0, M, N, int(bool(relu)), _p(scale), _p(shift), float(gain), _st()),
+            "taco_epi_bwd")
+
+
+def epi_fwd_keep_(X, keep, gain):
+    _chk2(X, "epi_fwd_keep X")
+    assert keep.dtype == torch.uint8 and keep.is_contiguous() and keep.numel() == X.numel()
+    L.check(L.lib().taco_epi_fwd_keep(_p(X), _ld(X), _p(keep), X.shape[0], X.shape[1], float(gain), _st()), "taco_epi_fwd_keep")
+
+
+def bn_param_grad(dgamma, dbeta, S1, S2, gamma, beta):
+    L.check(L.lib().taco_bn_param_grad(_p(dgamma), _p(dbeta), _p(S1), _p(S2), _p(gamma), _p(beta), gamma.numel(), _st()),
+            "taco_bn_param_grad")
+
+
+def maxpool_bwd(dX, dP, X):
+    B, T, Cc = X.shape
+    assert dX.is_contiguous() and dP.is_contiguous() and X.is_contiguous()
+    L.check(L.lib().taco_maxpool_bwd(_p(dX), _p(dP), _p(X), B, T, Cc, _st()), "taco_maxpool_bwd")
+
+
+def highway_fwd(Y, Pm, X):
+    _chk2(Y, "highway_fwd Y"); _chk2(Pm, "highway_fwd P"); _chk2(X, "highway_fwd X")
+    M, U = X.shape
+    L.check(L.lib().taco_highway_fwd(_p(Y), _ld(Y), _p(Pm), _ld(Pm), _p(X), _ld(X), M, U, _st()), "taco_highway_fwd")
+
+
+def highway_bwd(dP, dXd, dY, Pm, X):
+    M, U = X.shape
+    L.check(L.lib().taco_highway_bwd(_p(dP), _ld(dP), _p(dXd), _ld(dXd), _p(dY), _ld(dY), _p(Pm), _ld(Pm), _p(X), _ld(X), M, U,
+                                     _st()), "taco_highway_bwd")
+
+
+def l1_bwd(dA, A, Bt, beta=0.0):
+    assert dA.is_contiguous() and A.is_contiguous() and Bt.is_contiguous() and A.numel() == Bt.numel() == dA.numel()
+    L.check(L.lib().taco_l1_bwd(_p(dA), _p(A), _p(Bt), A.numel(), float(beta), _st()), "taco_l1_bwd")
+
+
+def scatter_add_rows(dTable, ids, dRows):
+    assert ids.dtype == torch.int32 and ids.is_contiguous() and dRows.is_contiguous() and dTable.is_contiguous()
+    V, W = dTable.shape
+    L.check(L.lib().taco_scatter_add_rows(_p(dTable), _p(ids), _p(dRows), ids.numel(), W, V, _st()), "taco_scatter_add_rows")
+
+
+def bigru_bwd(dxp, dOut, out, ACT, Wg_h_fw, Wc_h_fw, Wg_h_bw, Wc_h_bw):
+    B, T, _ = out.shape
+    for t in (dxp, dOut, out, ACT, Wg_h_fw, Wc_h_fw, Wg_h_bw, Wc_h_bw):
+        assert t.is_contiguous() and t.is_cuda
+    L.check(L.lib().taco_bigru_bwd(_p(dxp), _p(dOut), _p(out), _p(ACT), _p(Wg_h_fw), _p(Wc_h_fw), _p(Wg_h_bw), _p(Wc_h_bw), B, T,
+                                   _st()), "taco_bigru_bwd")
+
+
+def dec_inputs(Xin, sel, mel, y, sample_mask, r, sched):
+    T, B, mf = Xin.shape
+    assert mf == 80 and sel.dtype == torch.uint8 and mel.is_contiguous() and y.is_contiguous()
+    L.check(L.lib().taco_dec_inputs(_p(Xin), _p(sel), _p(mel), _p(y), _p(sample_mask), B, T, r, int(bool(sched)), _st()),
+            "taco_dec_inputs")
+
+
+def decoder_bwd(a):
+    T, B, OUT = a["dy_ext"].shape
+    Tx = a["align"].shape[2]
+    d = L.DecoderBwdArgs()
+    d.B, d.T, d.Tx, d.r, d.keep_scale = B, T, Tx, OUT // 80, float(a["keep_scale"])
+    for k in ("W_a", "W_q", "W_out", "W_in", "W1", "W2", "v", "dy_ext", "align", "values", "keys", "PQ", "PN1", "PN2", "sel",
+              "DATT", "DY", "DPQ", "DSCORE", "DCTX", "DZ", "DPN2", "DPN1", "DX"):
+        assert a[k].is_contiguous() and a[k].is_cuda, k
+        setattr(d, k, a[k].data_ptr())
+    for k in ("Wg", "Wc", "RU", "C", "H", "DG", "DC"):
+        for i in range(3):
+            assert a[k][i].is_contiguous(), k
+            getattr(d, k)[i] = a[k][i].data_ptr()
+    ws = torch.empty(L.lib().taco_decoder_bwd_workspace_bytes() // 4, dtype=torch.float32, device=a["dy_ext"].device)
+    d.workspace = ws.data_ptr()
+    L.check(L.lib().taco_decoder_bwd(C.byref(d), _st()), "taco_decoder_bwd")
+    a["_ws"] = ws                                            # keep the scratch alive until the stream has consumed it
+
+
+def attn_bwd_post(dkeys, dv, DSCORE, keys, PQ, v):
+    B, T, Tx = DSCORE.shape
+    assert keys.shape[2] == 256
+    L.check(L.lib().taco_attn_bwd_post(_p(dkeys), _p(dv), _p(DSCORE), _p(keys), _p(PQ), _p(v), B, T, Tx, _st()), "taco_attn_bwd_post")
+
+
+def mask_rows(dst, src, length):
+    B, T, Cc = src.shape
+    L.check(L.lib().taco_mask_rows(_p(src), _p(length), _p(dst), B, T, Cc, _st()), "taco_mask_rows")
+
+
+_ss_ws = {}
+
+
+def sumsq(out, x):
+    ws = _ss_ws.get(x.device)
+    if ws is None:
+        ws = _ss_ws[x.device] = torch.empty(2048, dtype=torch.float32, device=x.device)
+    L.check(L.lib().taco_sumsq(_p(x), x.numel(), _p(ws), _p(out), _st()), "taco_sumsq")
+
+
+def adam_step(p, g, m, v, lr_t, b1, b2, eps, clip, sumsq_t):
+    for t in (p, g, m, v):
+        assert t.is_contiguous() and t.is_cuda and t.dtype == torch.float32
+    L.check(L.lib().taco_adam_step(_p(p), _p(g), _p(m), _p(v), p.numel(), float(lr_t), float(b1), float(b2), float(eps),
+                                   float(clip), _p(sumsq_t), _st()), "taco_adam_step")

@@ -138,6 +138,8 @@ def bigru_bwd(K, P, G, S, p, dOut):
     dxp = K.empty((M, 768), out)
     K.bigru_bwd(dxp.view(B, T, 768), dOut, out, ACT.view(B, T, 768), P[f"{names[0]}/Wg"][128:], P[f"{names[0]}/Wc"][128:],
                 P[f"{names[1]}/Wg"][128:], P[f"{names[1]}/Wc"][128:])
+    if "_capture" in S:
+        S["_capture"][f"{p}/bigru_bwd"] = {"dxp": dxp.view(B, T, 768), "dOut": dOut, "out": out, "ACT": ACT.view(B, T, 768)}
     dHin = K.empty((M, 128), out)
     for d, dn in enumerate(names):
         Wg, Wc = P[f"{dn}/Wg"], P[f"{dn}/Wc"]
@@ -311,7 +313,9 @@ def decoder_bwd(K, P, G, S, cfg, dY_ext):
         "DX": tm(mf),
     }
     K.decoder_bwd(a)
-    DATT, DY, DPQ, DZ = _v2(a["DATT"]), _v2(a["DY"]), _v2(a["DPQ"]), _v2(a["DZ"])
+    if "_capture" in S:                                   # tests: expose the serial kernel's arguments and outputs
+        S["_capture"]["decoder_bwd"] = a
+    DATT, DY, DPQ, DZ =_v2(a["DATT"]), _v2(a["DY"]), _v2(a["DPQ"]), _v2(a["DZ"])
     Ytm2, CTX2 = _v2(R["Ytm"]), _v2(R["CTX"])
     # attention layer / query layer / output projection
     K.gemm(G["dec/attn/W_a"][:OUT], Ytm2, DATT, ta=True, beta=1.0)

@@ -67,6 +67,24 @@ def current_scope():
     return _scope_stack[-1]
 
 
+# ----------------------------------------------------------------------------------------------
+# train-mode activation saving: inside `with saving(S):` every op records the tensors the hand-written
+# backward (models/grad.py) needs, under the names grad.py reads, and uses the un-fused variants whose
+# intermediates must exist in memory (bank max-pool input, highway pre-activations).
+# ----------------------------------------------------------------------------------------------
+_save = None
+
+
+@contextlib.contextmanager
+def saving(S):
+    global _save
+    prev, _save = _save, S
+    try:
+        yield S
+    finally:
+        _save = prev
+
+
 class Runtime:
     """Per-store kernel-side state: precision mode, derived operand buffers, scratch buffers."""
 
@@ -213,6 +231,8 @@ def pre_net(inputs, units=(256, 128), dropout=0.5, train=True, masks=None, scope
                     act=L.ACT_RELU, keep=m1, keep_scale=ks, tag=sc.name("l1"))
     l2 = linear(rt, l1, W2, packed_weight(rt, sc.name("W2"), W2, 1, units[0], units[1]), units[1], bias=b2,
                 act=L.ACT_RELU, keep=m2, keep_scale=ks, tag=sc.name("l2"))
+    if _save is not None and ids is not None:
+        _save[sc.name("t1")] = t1.view(V, units[0]); _save[sc.name("l1")] = l1; _save[sc.name("l2")] = l2
     return l2
 
 
@@ -235,12 +255,15 @@ def conv1d_banks(inputs, K=16, cout=128, scope=None):
                 _pack(rt, None, sc.p(f"W{k}"), k, Cin, cout, ld=ld, row0=(k - 1) * cout, dst=dst)
             return dst
         Wp = rt.get(("pack", sc.name("bank")), build)
-        return linear(rt, inputs, Wall, Wp, K * cout, bank_K=K, bank_cout=cout, bias=ball, act=L.ACT_RELU, scale=scale,
-                      shift=shift, pool=True, tag=sc.name("pool"))
-    bank = linear(rt, inputs, Wall, None, K * cout, bank_K=K, bank_cout=cout, bias=ball, act=L.ACT_RELU, scale=scale,
+        if _save is None:
+            return linear(rt, inputs, Wall, Wp, K * cout, bank_K=K, bank_cout=cout, bias=ball, act=L.ACT_RELU, scale=scale,
+                          shift=shift, pool=True, tag=sc.name("pool"))
+    bank = linear(rt, inputs, Wall, Wp, K * cout, bank_K=K, bank_cout=cout, bias=ball, act=L.ACT_RELU, scale=scale,
                   shift=shift, tag=sc.name("bn"))
     pooled = rt.buf(sc.name("pool"), (B, T, K * cout))
     L.check(L.lib().taco_maxpool_fwd(L.ptr(bank), L.ptr(pooled), B, T, K * cout, L.current_stream()), "taco_maxpool_fwd")
+    if _save is not None:
+        _save[sc.name("bn")] = bank; _save[sc.name("pool")] = pooled; _save[sc.name("bn_affine")] = (scale, shift)
     return pooled
 
 
@@ -270,6 +293,13 @@ def highway(inputs, units=128, scope=None):
     Whw = rt.get(("hw_w", sc.prefix), build_w)
     bhw = rt.get(("hw_b", sc.prefix), build_b)
     Wp = packed_weight(rt, sc.name("hw"), Whw, 1, units, 2 * units)
+    if _save is not None:                                       # train: keep [h_pre | t_pre] for the backward
+        from .. import kernels as K
+        Pm = linear(rt, inputs, Whw, Wp, 2 * units, bias=bhw, tag=sc.name("P"))
+        out = rt.buf(sc.name("out"), (B, T, units))
+        K.highway_fwd(out.view(-1, units), Pm.view(-1, 2 * units), inputs.view(-1, units))
+        _save[sc.name("in")] = inputs; _save[sc.name("P")] = Pm
+        return out
     return linear(rt, inputs, Whw, Wp, 2 * units, bias=bhw, highway_x=inputs, tag=sc.name("out"))
 
 
@@ -303,6 +333,8 @@ def bidirectional_gru(inputs, gru_units=128, scope=None):
     out = rt.buf(sc.name("gru_out"), (B, T, 2 * gru_units))
     L.check(L.lib().taco_bigru_fwd(L.ptr(xp), L.ptr(fw.p("Wg")[Cin:]), L.ptr(fw.p("Wc")[Cin:]), L.ptr(bw.p("Wg")[Cin:]),
                                    L.ptr(bw.p("Wc")[Cin:]), L.ptr(out), B, T, L.current_stream()), "taco_bigru_fwd")
+    if _save is not None:
+        _save[sc.name("hw_out")] = inputs; _save[sc.name("xp")] = xp; _save[sc.name("gru_out")] = out
     return out
 
 
@@ -329,12 +361,22 @@ def CBHG(inputs, speaker_embed=None, K=16, c=[128, 128, 128], gru_units=128, num
                                taps=3, bias=b, act=L.ACT_NONE if last else L.ACT_RELU, scale=scale, shift=shift,
                                residual=inputs if last else None, tag=psc.name("out"))   # +inputs: ops.py:92
             cin = c[layer + 1]
+            if _save is not None:
+                _save[psc.name("bn_affine")] = (scale, shift)
+                _save[sc.name("res" if last else f"proj{layer + 1}")] = conv_proj
         h = conv_proj
         if trace is not None:
             trace[sc.name("bank_pool")] = conv_bank
             trace[sc.name("res")] = conv_proj
+        if _save is not None:
+            _save[sc.name("x_in")] = inputs
+            _save[sc.name("bank_bn")] = _save[sc.name("bank/bn")]
+            _save[sc.name("bank_pool")] = conv_bank
         for layer in range(num_highway_layers):
             h = highway(h, scope=sc.sub(f"highway{layer}"))
+            if _save is not None:
+                _save[sc.name(f"hw{layer}_in")] = _save[sc.name(f"highway{layer}/in")]
+                _save[sc.name(f"hw{layer}_P")] = _save[sc.name(f"highway{layer}/P")]
         if trace is not None:
             trace[sc.name("highway_out")] = h
         out = bidirectional_gru(h, gru_units, scope=sc)
@@ -416,6 +458,16 @@ def attention_decoder(encoded, text_length, r, T, mode=L.DEC_INFER, mel=None, sa
     ws = rt.buf(sc.name("dec_ws"), (lib.taco_decoder_workspace_bytes(32, Tx, T, r) // 4,))
     rt.dec_ws = ws                                               # (per-slot time stamps live in its tail; see decoder.cu)
     ks = 1.0 / (1.0 - dropout)
+    hs = None
+    if _save is not None:                                        # train: the three GRU state sequences feed the backward
+        assert B <= 32, "training decodes at most 32 utterances per rank (one launch)"
+        hs = rt.buf(sc.name("H"), (3, T, B, 256))
+        _save[sc.name("H")] = hs; _save[sc.name("values")] = values; _save[sc.name("keys")] = keys
+        _save[sc.name("y")] = y; _save[sc.name("align")] = align
+        if drop_masks is not None:
+            _save[sc.name("keep1")], _save[sc.name("keep2")] = drop_masks
+        if mode == L.DEC_SCHED:
+            _save[sc.name("sample_mask")] = sample_mask
     for b0 in range(0, B, 32):                                   # the kernel handles <= 32 utterances per launch
         nb = min(32, B - b0)
         a = L.DecoderArgs()
@@ -439,5 +491,6 @@ def attention_decoder(encoded, text_length, r, T, mode=L.DEC_INFER, mel=None, sa
         a.B = nb; a.Tx = Tx; a.T = T; a.r = r
         a.y = y[b0:].data_ptr(); a.align = align[b0:].data_ptr(); a.workspace = ws.data_ptr()
         a.step_ns = step_ns.data_ptr() if step_ns is not None else None
+        a.h_save = hs.data_ptr() if hs is not None else None
         L.check(lib.taco_decoder_fwd(C.byref(a), L.current_stream()), "taco_decoder_fwd")
     return y, align

@@ -248,8 +248,44 @@ class Tacotron(object):
         self.output_loss = res[1]
         return res[0] + res[1]
 
-    def add_train_op(self, loss):
-        raise NotImplementedError("backward / Adam (tacotron.py:167-185) is not part of this round's path")
+    # -- add_train_op (tacotron.py:167-185) -------------------------------------------------------
+    def add_train_op(self, loss=None):
+        """Creates the optimizer state (Adam moments + flat gradient bucket) and returns the callable that plays the
+        role of `train_op`: ``train_op(inputs, lr)`` = one ``sess.run([train_op, loss, global_step], {lr})``."""
+        from ..optim import FlatAdam
+        if getattr(self, "_opt", None) is None:
+            self._opt = FlatAdam(self.store.flat)
+            self._gviews = self._opt.views(self.store)
+        return self.train_step
+
+    def backward(self, S):
+        """d(loss)/d(parameters) into the flat gradient bucket (zeroed first): the hand-written reverse of
+        inference + add_loss_op (models/grad.py) over the saved activations S of a train-mode forward."""
+        from .. import kernels as K
+        from . import grad
+        self.add_train_op()
+        self._opt.zero_grad()
+        grad.model_bwd(K, self.store, self._gviews, S, self.config)
+        return self._gviews
+
+    def train_step(self, inputs, lr=None, **kw):
+        """forward (train mode, activations saved) -> loss -> backward -> [all-reduce] -> clip -> Adam.
+        Returns the loss tensor (device scalar); `self.global_step`, `self.grad_sumsq` are updated."""
+        from .. import kernels as K
+        self.add_train_op()
+        lr = self.lr if lr is None else lr
+        S = {}
+        with ops.saving(S):
+            self.seq2seq_output, self.output = self.inference(inputs, True, **kw)
+        self.loss = self.add_loss_op(self.seq2seq_output, self.output, inputs["mel"], inputs["stft"])
+        S.update(text=inputs["text"], text_length=inputs["text_length"], mel=inputs["mel"], stft=inputs["stft"])
+        S["post/out"] = self.output
+        self.saved = S
+        self.backward(S)
+        self.grad_sumsq = self._opt.apply(K, self.store.flat, lr, self.config.cap_grads)
+        self.store.version += 1                    # derived kernel-layout buffers are refreshed on the next forward
+        self.global_step += 1
+        return self.loss
 
     # -- the eager stand-in for sess.run([...]) ---------------------------------------------------
     def __call__(self, inputs, **kw):

@@ -16,7 +16,16 @@ from tests import train_checks as TC  # noqa: E402
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
 os.makedirs(OUT, exist_ok=True)
-log = open(os.path.join(OUT, "train_diag.txt"), "w")
+# optional argument: a group letter (A..F) so that each group runs in its own process -- a device fault in one
+# group then cannot poison the CUDA context of the others.  No argument = everything in this process.
+GROUP = sys.argv[1] if len(sys.argv) > 1 else ""
+log = open(os.path.join(OUT, "train_diag.txt"), "a" if GROUP else "w")
+GROUPS = {"A": ("smoke", "gemm", "elementwise"), "B": ("bigru",), "C": ("train_forward",), "D": ("decoder_bwd",),
+          "E": ("model_bwd", "train_step"), "F": ("timing",)}
+
+
+def wanted(name):
+    return not GROUP or any(name.startswith(p) for p in GROUPS[GROUP])
 
 
 def say(*a):
@@ -67,8 +76,19 @@ def timing():
 
 
 if __name__ == "__main__":
-    say("device:", torch.cuda.get_device_name(0))
+    say(f"---- group {GROUP or 'all'}  device:", torch.cuda.get_device_name(0))
+    if wanted("smoke"):
+        try:                                               # the inference path must be untouched by the rebuilt library
+            import __graft_entry__ as ge
+            t0 = time.time()
+            ge.smoke()
+            say(f"== smoke() (inference path vs oracle): OK ({time.time() - t0:.1f}s)")
+        except Exception:
+            say("== smoke(): EXCEPTION")
+            say(traceback.format_exc())
     for name, fn in CHECKS:
+        if not wanted(name):
+            continue
         t0 = time.time()
         try:
             res = fn()
@@ -77,9 +97,10 @@ if __name__ == "__main__":
         except Exception:
             say(f"== {name}: EXCEPTION")
             say(traceback.format_exc())
-    try:
-        timing()
-    except Exception:
-        say("== timing: EXCEPTION")
-        say(traceback.format_exc())
+    if wanted("timing"):
+        try:
+            timing()
+        except Exception:
+            say("== timing: EXCEPTION")
+            say(traceback.format_exc())
     log.close()

@@ -36,16 +36,19 @@ def test_struct_sizes_match_header_layout():
     probe = r'''
 #include <stdio.h>
 #include "taco_b200.h"
-int main(void){ printf("%zu %zu %zu\n", sizeof(taco_linear_desc), sizeof(taco_decoder_weights), sizeof(taco_decoder_args)); return 0; }
+int main(void){ printf("%zu %zu %zu %zu %zu\n", sizeof(taco_linear_desc), sizeof(taco_decoder_weights), sizeof(taco_decoder_args),
+                       sizeof(taco_gemm_desc), sizeof(taco_decoder_bwd_args)); return 0; }
 '''
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "p.c"); exe = os.path.join(d, "p")
         open(c, "w").write(probe)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
-        a, b, cc = map(int, subprocess.check_output([exe]).split())
+        a, b, cc, g, db = map(int, subprocess.check_output([exe]).split())
     assert ctypes.sizeof(_lib.LinearDesc) == a
     assert ctypes.sizeof(_lib.DecoderWeights) == b
     assert ctypes.sizeof(_lib.DecoderArgs) == cc
+    assert ctypes.sizeof(_lib.GemmDesc) == g
+    assert ctypes.sizeof(_lib.DecoderBwdArgs) == db
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

@@ -335,6 +335,11 @@ def check_model_bwd(r=2, sched=True, precision="fp32", B=2, Tx=8, T=5):
     res = {}
     for k, gr in g_ref.items():
         _cmp(res, k, G[k], gr)
+    # whole-gradient agreement (what the optimizer sees): relative L2 error and cosine over all parameters
+    a = torch.cat([G[k].detach().float().cpu().reshape(-1) for k in g_ref])
+    b = torch.cat([g_ref[k].float().reshape(-1) for k in g_ref])
+    res["_rel_l2"] = (((a - b).norm() / b.norm()).item(), 1.0)
+    res["_cosine"] = (torch.nn.functional.cosine_similarity(a, b, dim=0).item(), 1.0)
     return res
 
 

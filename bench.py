@@ -17,6 +17,7 @@ N > 1: inference shards by utterance with no exchange -> N independent replicas 
 """
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -148,6 +149,65 @@ def _log(msg):
     sys.stderr.flush()
 
 
+def measure_train(args, world, rank):
+    """Side measurement: the TRAINING step on the same C2 batch per rank -- train-mode
+    forward (dropout, scheduled sampling 0.5), L1 losses, hand-written backward, one SUM all-reduce of the flat
+    28.4 MB gradient bucket over NCCL when N > 1 (config C4 = N x C2), global-norm clip, Adam.  Never allowed to break
+    the headline line: every rank first proves its own step works WITHOUT the collective, the ranks agree on that
+    (MIN all-reduce of a flag), and only then are the data-parallel steps run and timed."""
+    import torch
+    import torch.distributed as dist
+    from tacotron_b200 import Config, Tacotron
+    from tacotron_b200.utils import dist as D
+    ok, err, m, gi = 1, None, None, None
+    try:
+        cfg = Config(r=R, vocab_size=64, precision=args.precision)
+        m = Tacotron(cfg, None, train=True, seed=1)
+        g = torch.Generator().manual_seed(100 + rank)
+        gi = {"text": torch.randint(1, 64, (B, TX), generator=g, dtype=torch.int32).cuda(),
+              "text_length": torch.full((B,), TX, dtype=torch.int32).cuda(),
+              "mel": torch.randn(B, T, 80 * R, generator=g).half().float().cuda(),
+              "stft": torch.randn(B, T, 1025 * R, generator=g).half().float().cuda()}
+        m.dp = False
+        m.train_step(gi, lr=1e-4)                          # local step: no collective
+        torch.cuda.synchronize()
+        if not math.isfinite(float(m.loss)):
+            raise RuntimeError("non-finite training loss")
+    except Exception as ex:
+        ok, err = 0, f"{type(ex).__name__}: {str(ex)[:160]}"
+    if world > 1:
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        all_ok = int(flag.item())
+    else:
+        all_ok = ok
+    if not all_ok:
+        return {"error": err or "another rank failed its local training step"}
+    try:
+        m.dp = True
+        for _ in range(2):
+            m.train_step(gi, lr=1e-4)
+        D.barrier()
+        n = 5
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+        ev[0].record()
+        for i in range(n):
+            m.train_step(gi, lr=1e-4)
+            ev[i + 1].record()
+        torch.cuda.synchronize()
+        D.barrier()
+        ms = D.max_over_ranks(ev[0].elapsed_time(ev[n]) / n)
+        loss = float(m.loss)
+        return {"value": D.aggregate_throughput(FRAMES, world, ms), "unit": "mel frames/s", "ms_per_step": ms, "steps": n, "warmup": 3,
+                "n_gpus": world, "scaling": "weak",
+                "config": f"training step on C2 per rank (B=32, char 128, T=200, r=5; global batch {32 * world}): dropout 0.5, scheduled "
+                          "sampling 0.5, L1 losses, backward, clip 5, Adam; targets (2 x 141 MB) + activations exceed L2",
+                "allreduce": ({"op": "SUM", "bytes_per_step": int(m.store.flat.numel() * 4), "backend": "nccl"} if world > 1 else None),
+                "precision": f"{args.precision} forward, fp32 backward (exact-product FFMA GEMMs)", "loss_last_step": loss}
+    except Exception as ex:
+        return {"error": f"{type(ex).__name__}: {str(ex)[:160]}"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -249,6 +309,11 @@ def run_ours(args):
     h2d = text_h.numel() * 4 + len_h.numel() * 4
     d2h = out_h.numel() * 4 + align_h.numel() * 4
 
+    train = None
+    if not args.no_train:
+        train = measure_train(args, world, rank)
+        _log(f"training side measurement done: {train.get('ms_per_step', train.get('error'))}")
+
     if rank == 0:
         pk = peaks()
         dms = statistics.mean(dec_ms)
@@ -308,6 +373,7 @@ def run_ours(args):
                          "algorithmic_gflop_per_launch": DECODER_GFLOP,
                          "whole_step": {"achieved": FWD_GFLOP / ms_per_step, "frac": FWD_GFLOP / ms_per_step / pk["bf16_tflops"]}},
             "exact_fp32_mode": exact,
+            "train": train,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
@@ -325,6 +391,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fp32-mode", action="store_true", help="skip the side measurement of the exact-fp32 precision mode")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--no-train", action="store_true", help="skip the side measurement of the training step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -282,7 +282,9 @@ class Tacotron(object):
         S["post/out"] = self.output
         self.saved = S
         self.backward(S)
-        self.grad_sumsq = self._opt.apply(K, self.store.flat, lr, self.config.cap_grads)
+        # data parallel: one SUM all-reduce of the flat gradient bucket when a process group exists (self.dp = False
+        # keeps the step local, e.g. for a per-rank health check before the first collective)
+        self.grad_sumsq = self._opt.apply(K, self.store.flat, lr, self.config.cap_grads, allreduce=getattr(self, "dp", True))
         self.store.version += 1                    # derived kernel-layout buffers are refreshed on the next forward
         self.global_step += 1
         return self.loss

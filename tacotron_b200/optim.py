@@ -44,9 +44,9 @@ class FlatAdam:
     def zero_grad(self):
         self.g.zero_()
 
-    def apply(self, K, flat, lr, clip):
+    def apply(self, K, flat, lr, clip, allreduce=True):
         """flat <- Adam(flat, clip(all_reduce(g)));  returns the device scalar holding sum(g^2) (pre-clip)."""
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        if allreduce and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.g, op=dist.ReduceOp.SUM)
         K.sumsq(self.sumsq, self.g)
         self.step += 1

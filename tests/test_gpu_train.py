@@ -65,4 +65,11 @@ def test_model_backward_tf32_forward():
 
 
 def test_train_step_matches_oracle():
-    _assert(TC.check_train_step(2, True, "fp32", steps=2), 2e-3, floor=1e-3)
+    res = TC.check_train_step(2, True, "fp32", steps=2)
+    params = {k: v for k, v in res.items() if k.startswith("param_worst")}
+    _assert({k: v for k, v in res.items() if k not in params}, 1e-4, floor=1e-3)      # losses and global gradient norms
+    # parameters after 2 Adam steps of lr 1e-3 (each moves a parameter by ~1e-3): 5e-4 catches a missing or
+    # wrong-signed update, and tolerates the sign noise of parameters whose true gradient is at rounding level
+    # (measured on B200: 2.4e-5)
+    for k, (e, r) in params.items():
+        assert e <= 5e-4, (k, e, r)

@@ -264,6 +264,23 @@ int taco_attn_bwd_post(float* dkeys, float* dv, const float* DSCORE, const float
 /* tf.clip_by_global_norm(cap_grads) + tf.train.AdamOptimizer (tacotron.py:170-184) on the flat
  * parameter / gradient buffers: out = sum x^2 (deterministic); g *= clip/max(sqrt(sumsq), clip);
  * m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; p -= lr_t m/(sqrt(v)+eps), lr_t = lr sqrt(1-b2^t)/(1-b1^t).   */
+/* ==========================================================================================
+ * Spectrogram inversion: the fused steps of audio.griffinlim between the two
+ * library FFTs of an iteration (reference audio.py:67-97; reshape_frames inverse audio.py:30-35; librosa
+ * stft/istft conventions).  n = frames = 4r*(T/4), F = n_fft/2+1 bins, L = hop*(n-1) samples; complex tensors
+ * are interleaved (re, im) fp32.  Semantics: tests/mirror_kernels.py gl_*.
+ * ========================================================================================== */
+/* mag[b,f,k] = exp(spec[b, t(f), c(f)*F+k]*scale + shift) (scale/shift may be NULL), full = mag*exp(2 pi i u):
+ * reshape_frames(forward=False) + the driver's de-normalisation (test.py:64) + np.exp + the random phase (:81) */
+int taco_gl_init(float* full_c64, float* mag, const float* spec, const float* phase_u, int B, int T, int n, int r, int F,
+                 const float* scale, const float* shift, void* stream);
+/* tail of librosa.istft: window, overlap-add, window-sum-square normalisation, centre trim: fr [B][n][n_fft] -> y [B][L] */
+int taco_gl_ola(float* y, const float* fr, int B, int n, int hop, int n_fft, int win_length, void* stream);
+/* head of librosa.stft: reflect padding, framing, hann window: y [B][L] -> frw [B][n][n_fft] */
+int taco_gl_frame(float* frw, const float* y, int B, int n, int hop, int n_fft, int win_length, void* stream);
+/* full = mag * rebuilt/|rebuilt|  (audio.py:84,87) over `count` complex elements */
+int taco_gl_phase(float* full_c64, const float* mag, const float* rebuilt_c64, int64_t count, void* stream);
+
 int taco_sumsq(const float* x, int64_t n, float* partial_ws, float* out, void* stream);
 int taco_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float b1, float b2, float eps,
                    float clip, const float* sumsq, void* stream);

@@ -100,6 +100,8 @@ EXPORTS = [
     "taco_maxpool_bwd", "taco_highway_fwd", "taco_highway_bwd", "taco_l1_bwd", "taco_scatter_add_rows", "taco_bigru_bwd",
     "taco_dec_inputs", "taco_decoder_bwd_workspace_bytes", "taco_decoder_bwd", "taco_attn_bwd_post", "taco_sumsq",
     "taco_adam_step",
+    # spectrogram inversion (Griffin-Lim glue kernels)
+    "taco_gl_init", "taco_gl_ola", "taco_gl_frame", "taco_gl_phase",
 ]
 
 
@@ -152,6 +154,10 @@ def lib():
     L.taco_attn_bwd_post.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, vp]
     L.taco_sumsq.argtypes = [vp, i64, vp, vp, vp]
     L.taco_adam_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, vp, vp]
+    L.taco_gl_init.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, i32, vp, vp, vp]
+    L.taco_gl_ola.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
+    L.taco_gl_frame.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
+    L.taco_gl_phase.argtypes = [vp, vp, vp, i64, vp]
     for name in EXPORTS:                      # every declared symbol must resolve (AttributeError otherwise)
         getattr(L, name)
     _lib = L

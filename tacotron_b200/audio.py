@@ -1,0 +1,99 @@
+"""Spectrogram inversion on the GPU -- host-side mirror of the reference's ``audio.py`` inversion surface
+(``reshape_frames`` :23-35, ``invert_spectrogram`` :67-75, ``griffinlim`` :77-97), SURVEY.md section 8(f) rank 1:
+it sits inside BASELINE config 5's end-to-end latency (test.py:64) and would dominate it on the CPU.
+
+Design: a batch of utterances stays on the device for all iterations.  The two FFTs per iteration are library calls
+(cuFFT through ``torch.fft`` -- "plain library FFTs", like cuBLAS for a plain GEMM); everything between them is four
+fused kernels of libtaco_b200.so (csrc/audio.cu):
+
+    gl_init   reshape_frames(forward=False) + de-normalisation + exp + initial phase  ->  magnitude, first spectrum
+    gl_ola    window, overlap-add, window-sum-square normalisation, centre trim        (the tail of librosa.istft)
+    gl_frame  reflect padding, framing, window                                         (the head of librosa.stft)
+    gl_phase  mag * rebuilt/|rebuilt|                                                  (audio.py:84,87)
+
+so one iteration is irfft -> gl_ola -> gl_frame -> rfft -> gl_phase: 5 launches, ~20 MB of HBM traffic per utterance of
+500 frames.  All arithmetic goes through the kernel namespace K (tacotron_b200/kernels.py); tests run the same
+orchestration over tests/mirror_kernels.py on CPU tensors against the numpy oracle (oracle/audio_oracle.py).
+"""
+from __future__ import annotations
+
+import torch
+
+n_fft = 2048            # audio.py:10
+win_length = 1200       # audio.py:11
+hop_length = 300        # audio.py:12
+F_BINS = 1 + n_fft // 2
+
+
+def _K():
+    from . import kernels
+    return kernels
+
+
+def reshape_frames(signal, r, forward=False):
+    """audio.reshape_frames (audio.py:23-35) as a pure index permutation on a torch tensor (any device).
+    forward=False: [T, F*r] -> [4r*(T//4), F]; forward=True: [F, n] -> [4*(n//4r), F*r]."""
+    if forward:
+        Fd, n = signal.shape
+        nb = n // (4 * r)
+        s = signal[:, :nb * 4 * r].reshape(Fd, nb, r, 4)                     # frame = 4r*b + 4c + tl
+        return s.permute(1, 3, 2, 0).reshape(nb * 4, r * Fd)                 # row = 4b + tl, col = c*F + k
+    T, W = signal.shape
+    Fd = W // r
+    nb = T // 4
+    s = signal[:nb * 4].reshape(nb, 4, r, Fd)                                # [b, tl, c, k]
+    return s.permute(0, 2, 1, 3).reshape(nb * 4 * r, Fd)                     # frame = 4r*b + 4c + tl
+
+
+def griffinlim_batch(spec, r, n_iter=50, scale=None, shift=None, phase_u=None, K=None, generator=None):
+    """spec [B, T, 1025*r] (log magnitudes in the decoder's r-frames-per-step layout, optionally normalised:
+    magnitude = exp(spec*scale + shift), the driver's ``out*stft_std + stft_mean`` of test.py:64) -> waveforms [B, L],
+    L = hop*(4r*(T//4) - 1).  phase_u: uniform [0,1) initial phases [B, n, 1025] (audio.py:81), drawn if None."""
+    K = K or _K()
+    B, T, W = spec.shape
+    assert W == F_BINS * r, (W, r)
+    n = 4 * r * (T // 4)
+    assert n >= 2, "need at least one block of 4 decoder steps"
+    L = hop_length * (n - 1)
+    assert L > n_fft // 2, f"{n} frames are fewer than the reflect padding of the STFT needs (>= 5)"
+    rdt = spec.dtype
+    cdt = torch.complex64 if rdt == torch.float32 else torch.complex128
+    if phase_u is None:
+        phase_u = torch.rand((B, n, F_BINS), dtype=rdt, device=spec.device, generator=generator)
+    mag = torch.empty((B, n, F_BINS), dtype=rdt, device=spec.device)
+    full = torch.empty((B, n, F_BINS), dtype=cdt, device=spec.device)
+    y = torch.empty((B, L), dtype=rdt, device=spec.device)
+    frw = torch.empty((B, n, n_fft), dtype=rdt, device=spec.device)
+    K.gl_init(full, mag, spec, phase_u, r, scale, shift)
+    for it in range(n_iter + 1):
+        fr = torch.fft.irfft(full, n=n_fft, dim=-1)                          # cuFFT C2R, batch B*n
+        K.gl_ola(y, fr, hop_length, win_length)
+        if it == n_iter:
+            break
+        K.gl_frame(frw, y, hop_length, win_length)
+        rebuilt = torch.fft.rfft(frw, dim=-1)                                # cuFFT R2C
+        K.gl_phase(full, mag, rebuilt)
+    return y
+
+
+def griffinlim(spectrogram, n_iter=50, phase_u=None, K=None):
+    """audio.griffinlim for ONE magnitude spectrogram [1025, frames] (audio.py:77) -> waveform [hop*(frames-1)]."""
+    Fd, n = spectrogram.shape
+    assert Fd == F_BINS
+    spec = torch.log(spectrogram.t().contiguous().clamp_min(1e-30))[None]    # reuse the batch path with r = 1 layout
+    # r=1: reshape_frames(forward=False) is the identity on whole blocks of 4 frames
+    assert n % 4 == 0, "frame count must be a multiple of 4 (the reference always produces 4r-frame blocks)"
+    pu = None if phase_u is None else phase_u[None]
+    return griffinlim_batch(spec, 1, n_iter=n_iter, phase_u=pu, K=K)[0]
+
+
+def invert_spectrogram(spec, r, n_iter=50, stft_mean=None, stft_std=None, phase_u=None, K=None):
+    """audio.invert_spectrogram (audio.py:67-75) with the driver's de-normalisation folded in.
+    spec [T, 1025*r] or [B, T, 1025*r] on the device -> waveform(s)."""
+    single = spec.dim() == 2
+    s = spec[None] if single else spec
+    scale, shift = (stft_std, stft_mean) if stft_std is not None else (None, None)
+    if phase_u is not None and single:
+        phase_u = phase_u[None]
+    y = griffinlim_batch(s.contiguous(), r, n_iter=n_iter, scale=scale, shift=shift, phase_u=phase_u, K=K)
+    return y[0] if single else y

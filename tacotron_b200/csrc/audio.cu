@@ -1,0 +1,150 @@
+// audio.cu -- the fused steps of Griffin-Lim spectrogram inversion between the two library FFTs of an iteration
+// (reference: audio.py:67-97 invert_spectrogram / griffinlim, audio.py:30-35 reshape_frames(forward=False);
+// librosa.stft / librosa.istft conventions as restated in oracle/audio_oracle.py).  SURVEY.md section 8(f) rank 1.
+//
+// All four kernels are bandwidth-bound gathers with one thread per output element; consecutive threads touch
+// consecutive addresses of every operand.  Semantics pinned by tests/mirror_kernels.py (gl_init, gl_ola, gl_frame,
+// gl_phase).  n = frames, NB = n_fft/2 + 1 bins, L = hop*(n-1) samples; the hann window (periodic, win_length
+// samples, centred in n_fft) is evaluated on the fly.
+#include <float.h>
+#include "common.cuh"
+
+namespace {
+
+inline int grid_for(int64_t total, int block) {
+    int64_t g = (total + block - 1) / block;
+    if (g > 148 * 32) g = 148 * 32;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+__device__ __forceinline__ float hann_at(int j, int lpad, int win_length) {   // j in [0, n_fft); 0 outside the support
+    const int i = j - lpad;
+    if (i < 0 || i >= win_length) return 0.f;
+    return 0.5f - 0.5f * cospif(2.0f * (float)i / (float)win_length);
+}
+
+// mag[b,f,k] = exp(spec[b, t(f), c(f)*F + k] * scale + shift);  full = mag * exp(2 pi i u)
+__global__ void gl_init_kernel(float2* __restrict__ full, float* __restrict__ mag, const float* __restrict__ spec,
+                               const float* __restrict__ phase_u, int T, int n, int r, int F, const float* __restrict__ scale,
+                               const float* __restrict__ shift, int64_t total) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(i % F);
+        const int f = (int)((i / F) % n);
+        const int b = (int)(i / ((int64_t)F * n));
+        const int b4 = f / (4 * r), rem = f % (4 * r);
+        const int c = rem >> 2, tl = rem & 3;
+        const int t = 4 * b4 + tl;
+        const int col = c * F + k;
+        float v = spec[((int64_t)b * T + t) * ((int64_t)F * r) + col];
+        if (scale) v = fmaf(v, scale[col], shift[col]);
+        const float m = expf(v);
+        float s, co;
+        sincospif(2.0f * phase_u[i], &s, &co);
+        mag[i] = m;
+        full[i] = make_float2(m * co, m * s);
+    }
+}
+
+// y[b,s] = sum_t w[j] fr[b,t,j] / sum_t w[j]^2,  j = s + n_fft/2 - t*hop inside the window support
+__global__ void gl_ola_kernel(float* __restrict__ y, const float* __restrict__ fr, int n, int L, int hop, int n_fft, int win_length,
+                              int64_t total) {
+    const int lpad = (n_fft - win_length) / 2;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int s = (int)(i % L);
+        const int b = (int)(i / L);
+        const int p = s + n_fft / 2;
+        // frames whose window support [t*hop + lpad, t*hop + lpad + win_length) contains p
+        int tmax = (p - lpad) / hop;
+        if (tmax > n - 1) tmax = n - 1;
+        int tmin = (p - lpad - win_length + hop) / hop;             // ceil((p - lpad - win_length + 1) / hop)
+        if (p - lpad - win_length + 1 <= 0) tmin = 0;
+        float acc = 0.f, ss = 0.f;
+        for (int t = tmin; t <= tmax; ++t) {
+            const int j = p - t * hop;
+            const float w = hann_at(j, lpad, win_length);
+            acc = fmaf(w, fr[((int64_t)b * n + t) * n_fft + j], acc);
+            ss = fmaf(w, w, ss);
+        }
+        y[i] = (ss > FLT_MIN) ? acc / ss : acc;
+    }
+}
+
+// frw[b,t,j] = w[j] * ypad[t*hop + j],  ypad = y reflect-padded by n_fft/2 on both sides
+__global__ void gl_frame_kernel(float* __restrict__ frw, const float* __restrict__ y, int n, int L, int hop, int n_fft, int win_length,
+                                int64_t total) {
+    const int lpad = (n_fft - win_length) / 2;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int j = (int)(i % n_fft);
+        const int t = (int)((i / n_fft) % n);
+        const int b = (int)(i / ((int64_t)n_fft * n));
+        const float w = hann_at(j, lpad, win_length);
+        float v = 0.f;
+        if (w != 0.f) {
+            int q = t * hop + j - n_fft / 2;
+            if (q < 0) q = -q;
+            if (q >= L) q = 2 * (L - 1) - q;
+            v = w * y[(int64_t)b * L + q];
+        }
+        frw[i] = v;
+    }
+}
+
+// full = mag * rebuilt / |rebuilt|   (angle(0) = 0 -> unit phasor 1)
+__global__ void gl_phase_kernel(float2* __restrict__ full, const float* __restrict__ mag, const float2* __restrict__ rebuilt, int64_t total) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const float2 z = rebuilt[i];
+        const float a = hypotf(z.x, z.y);
+        const float m = mag[i];
+        full[i] = (a > 0.f) ? make_float2(m * (z.x / a), m * (z.y / a)) : make_float2(m, 0.f);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int taco_gl_init(float* full_c64, float* mag, const float* spec, const float* phase_u, int B, int T, int n, int r, int F,
+                 const float* scale, const float* shift, void* stream) {
+    TACO_CHECK(full_c64 && mag && spec && phase_u, "taco_gl_init: NULL");
+    TACO_CHECK(r >= 1 && n == 4 * r * (T / 4) && F >= 1, "taco_gl_init: n=%d must be 4*r*(T/4) (r=%d, T=%d)", n, r, T);
+    TACO_CHECK((scale == nullptr) == (shift == nullptr), "taco_gl_init: scale and shift go together");
+    const int64_t total = (int64_t)B * n * F;
+    if (total == 0) return 0;
+    gl_init_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float2*>(full_c64), mag, spec, phase_u, T, n, r, F,
+                                                                           scale, shift, total);
+    TACO_LAUNCH_CHECK();
+    return 0;
+}
+
+int taco_gl_ola(float* y, const float* fr, int B, int n, int hop, int n_fft, int win_length, void* stream) {
+    TACO_CHECK(y && fr, "taco_gl_ola: NULL");
+    TACO_CHECK(n >= 2 && hop >= 1 && win_length >= 1 && win_length <= n_fft, "taco_gl_ola: bad sizes");
+    const int L = hop * (n - 1);
+    const int64_t total = (int64_t)B * L;
+    if (total == 0) return 0;
+    gl_ola_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(y, fr, n, L, hop, n_fft, win_length, total);
+    TACO_LAUNCH_CHECK();
+    return 0;
+}
+
+int taco_gl_frame(float* frw, const float* y, int B, int n, int hop, int n_fft, int win_length, void* stream) {
+    TACO_CHECK(frw && y, "taco_gl_frame: NULL");
+    const int L = hop * (n - 1);
+    TACO_CHECK(n >= 2 && L > n_fft / 2, "taco_gl_frame: signal (%d samples) shorter than the reflect padding (%d)", L, n_fft / 2);
+    const int64_t total = (int64_t)B * n * n_fft;
+    gl_frame_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(frw, y, n, L, hop, n_fft, win_length, total);
+    TACO_LAUNCH_CHECK();
+    return 0;
+}
+
+int taco_gl_phase(float* full_c64, const float* mag, const float* rebuilt_c64, int64_t count, void* stream) {
+    TACO_CHECK(full_c64 && mag && rebuilt_c64 && count >= 0, "taco_gl_phase: bad arguments");
+    if (count == 0) return 0;
+    gl_phase_kernel<<<grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float2*>(full_c64), mag,
+                                                                            reinterpret_cast<const float2*>(rebuilt_c64), count);
+    TACO_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

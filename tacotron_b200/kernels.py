@@ -184,6 +184,42 @@ def mask_rows(dst, src, length):
     L.check(L.lib().taco_mask_rows(_p(src), _p(length), _p(dst), B, T, Cc, _st()), "taco_mask_rows")
 
 
+# ---- Griffin-Lim glue (tacotron_b200/audio.py) ----
+def _f32c(t, name):
+    if not (t.is_cuda and t.is_contiguous() and t.dtype in (torch.float32, torch.complex64)):
+        raise L.TacoError(f"{name}: expected a contiguous CUDA fp32/complex64 tensor, got {t.dtype} {t.device}")
+    return t
+
+
+def gl_init(full, mag, spec, phase_u, r, scale=None, shift=None):
+    B, n, F = mag.shape
+    T = spec.shape[1]
+    for t, nm in ((full, "full"), (mag, "mag"), (spec, "spec"), (phase_u, "phase_u")):
+        _f32c(t, f"gl_init {nm}")
+    assert full.dtype == torch.complex64 and spec.shape == (B, T, F * r) and phase_u.shape == mag.shape
+    L.check(L.lib().taco_gl_init(_p(full), _p(mag), _p(spec), _p(phase_u), B, T, n, r, F, _p(scale), _p(shift), _st()), "taco_gl_init")
+
+
+def gl_ola(y, fr, hop, win_length):
+    B, n, n_fft = fr.shape
+    _f32c(y, "gl_ola y"); _f32c(fr, "gl_ola fr")
+    assert y.shape == (B, hop * (n - 1)) and fr.dtype == torch.float32
+    L.check(L.lib().taco_gl_ola(_p(y), _p(fr), B, n, hop, n_fft, win_length, _st()), "taco_gl_ola")
+
+
+def gl_frame(frw, y, hop, win_length):
+    B, n, n_fft = frw.shape
+    _f32c(y, "gl_frame y"); _f32c(frw, "gl_frame frw")
+    assert y.shape == (B, hop * (n - 1))
+    L.check(L.lib().taco_gl_frame(_p(frw), _p(y), B, n, hop, n_fft, win_length, _st()), "taco_gl_frame")
+
+
+def gl_phase(full, mag, rebuilt):
+    _f32c(full, "gl_phase full"); _f32c(mag, "gl_phase mag"); _f32c(rebuilt, "gl_phase rebuilt")
+    assert full.dtype == torch.complex64 and rebuilt.dtype == torch.complex64 and full.shape == rebuilt.shape == mag.shape
+    L.check(L.lib().taco_gl_phase(_p(full), _p(mag), _p(rebuilt), mag.numel(), _st()), "taco_gl_phase")
+
+
 _ss_ws = {}
 
 

@@ -13,6 +13,8 @@ Semantics are stated in the docstrings; they ARE the specification of the CUDA k
 """
 from __future__ import annotations
 
+import math
+
 import torch
 
 ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3
@@ -324,3 +326,66 @@ def mask_rows(dst, src, length):
     B, T, _ = src.shape
     m = (torch.arange(T)[None, :] < length[:, None].to(torch.int64)).to(src.dtype)
     dst.copy_(src * m[:, :, None])
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Griffin-Lim glue kernels (audio.py:67-97).  FFTs are library calls (torch.fft); these are the
+# fused steps between them.  n = frames, NB = 1 + n_fft/2 bins, L = hop*(n-1) samples.
+# ------------------------------------------------------------------------------------------------------------
+def _hann_padded(win_length, n_fft, dtype):
+    n = torch.arange(win_length, dtype=torch.float64)
+    w = 0.5 - 0.5 * torch.cos(2.0 * math.pi * n / win_length)
+    out = torch.zeros(n_fft, dtype=torch.float64)
+    lp = (n_fft - win_length) // 2
+    out[lp:lp + win_length] = w
+    return out.to(dtype)
+
+
+def gl_init(full, mag, spec, phase_u, r, scale=None, shift=None):
+    """reshape_frames(forward=False) (audio.py:30-35) + de-normalisation + exp + initial phase:
+    frame f of block b4 = f // 4r holds spec[t = 4*b4 + (f % 4r) % 4,  c*F : (c+1)*F],  c = (f % 4r) // 4;
+    mag = exp(v*scale + shift); full = mag * exp(2 pi i phase_u).   spec [B,T,F*r]; mag/phase_u [B,n,F]; full complex."""
+    B, n, F = mag.shape
+    f = torch.arange(n)
+    b4, rem = f // (4 * r), f % (4 * r)
+    c, tl = rem // 4, rem % 4
+    t = 4 * b4 + tl
+    cols = c[:, None] * F + torch.arange(F)[None, :]                         # [n, F]
+    v = spec[:, t[:, None], cols]                                             # [B, n, F]
+    if scale is not None:
+        v = v * scale[cols] + shift[cols]
+    m = torch.exp(v)
+    mag.copy_(m)
+    ang = 2.0 * math.pi * phase_u
+    full.copy_(torch.complex(m * torch.cos(ang), m * torch.sin(ang)))
+
+
+def gl_ola(y, fr, hop, win_length):
+    """librosa.istft after the inverse FFT: y[s] = sum_t w[p - t*hop] fr[t, p - t*hop] / sum_t w^2[p - t*hop],
+    p = s + n_fft/2 (centre trim), division only where the window sum exceeds tiny.  fr [B,n,n_fft] real, y [B,L]."""
+    B, n, n_fft = fr.shape
+    w = _hann_padded(win_length, n_fft, fr.dtype)
+    tot = torch.zeros(B, n_fft + hop * (n - 1), dtype=fr.dtype)
+    ss = torch.zeros(n_fft + hop * (n - 1), dtype=fr.dtype)
+    for t in range(n):
+        tot[:, t * hop:t * hop + n_fft] += fr[:, t] * w
+        ss[t * hop:t * hop + n_fft] += w * w
+    nz = ss > torch.finfo(fr.dtype).tiny
+    tot[:, nz] = tot[:, nz] / ss[nz]
+    y.copy_(tot[:, n_fft // 2:n_fft // 2 + y.shape[1]])
+
+
+def gl_frame(frw, y, hop, win_length):
+    """librosa.stft before the FFT: frw[t, j] = w[j] * ypad[t*hop + j], ypad = reflect-padded y by n_fft/2."""
+    B, n, n_fft = frw.shape
+    w = _hann_padded(win_length, n_fft, y.dtype)
+    yp = torch.nn.functional.pad(y[:, None, :], (n_fft // 2, n_fft // 2), mode="reflect")[:, 0]
+    for t in range(n):
+        frw[:, t] = yp[:, t * hop:t * hop + n_fft] * w
+
+
+def gl_phase(full, mag, rebuilt):
+    """full = mag * exp(i angle(rebuilt))   (audio.py:84,87; angle(0) = 0)"""
+    a = rebuilt.abs()
+    unit = torch.where(a > 0, rebuilt / torch.where(a > 0, a, torch.ones_like(a)), torch.ones_like(rebuilt))
+    full.copy_(unit * mag)

@@ -208,6 +208,61 @@ def measure_train(args, world, rank):
         return {"error": f"{type(ex).__name__}: {str(ex)[:160]}"}
 
 
+def measure_c5(args):
+    """Side measurement, rank 0 only, no collective: BASELINE config 5 -- one utterance (B=1, prompt padded to 140
+    chars, 500 mel frames = 100 decoder steps at r=5), inference through the public API with host text in and host
+    waveform out, INCLUDING spectrogram inversion (Griffin-Lim, 50 iterations; audio.py:67-97, called at test.py:64).
+    p50 over 20 runs.  The spectral-convergence self check guards against timing a broken inversion."""
+    import torch
+    from tacotron_b200 import Config, Tacotron, audio
+    try:
+        Bc, TXc, Tc = 1, 140, 100
+        m = Tacotron(Config(r=R, vocab_size=64, max_decode_iter=Tc, precision=args.precision, cuda_graph=not args.no_graph), None,
+                     train=False, seed=1)
+        g = torch.Generator().manual_seed(0)
+        text_h = torch.randint(1, 64, (Bc, TXc), generator=g, dtype=torch.int32).pin_memory()
+        len_h = torch.full((Bc,), 97, dtype=torch.int32).pin_memory()
+        n = 4 * R * (Tc // 4)
+        wav_h = torch.empty((Bc, audio.hop_length * (n - 1)), dtype=torch.float32).pin_memory()
+        mean = torch.full((1025 * R,), -4.0, device="cuda")          # stands in for the data set's stft_mean / stft_std
+        std = torch.full((1025 * R,), 1.5, device="cuda")
+        t_model, t_gl, t_all = [], [], []
+
+        def once(record):
+            t0 = time.perf_counter()
+            ci = {"text": text_h.cuda(non_blocking=True), "text_length": len_h.cuda(non_blocking=True)}
+            _, out = m.inference(ci, train=False)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            wav = audio.invert_spectrogram(out, R, n_iter=50, stft_mean=mean, stft_std=std)
+            wav_h.copy_(wav, non_blocking=True)
+            torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            if record:
+                t_model.append((t1 - t0) * 1e3); t_gl.append((t2 - t1) * 1e3); t_all.append((t2 - t0) * 1e3)
+            return out, wav
+        for _ in range(3):
+            out, wav = once(False)
+        for _ in range(20):
+            out, wav = once(True)
+        # self check: 50 iterations must have reduced || |STFT(y)| - mag ||_F / ||mag||_F well below the random-phase start
+        mag = torch.exp(audio.reshape_frames(out[0], R, forward=False) * 1.5 - 4.0).t()          # [1025, n]
+        win = torch.hann_window(audio.win_length, periodic=True, device="cuda")
+
+        def conv(w):
+            S = torch.stft(w, audio.n_fft, audio.hop_length, audio.win_length, window=win, center=True, pad_mode="reflect",
+                           return_complex=True).abs()
+            return float((S - mag).norm() / mag.norm())
+        c50 = conv(wav[0])
+        c0 = conv(audio.invert_spectrogram(out, R, n_iter=0, stft_mean=mean, stft_std=std)[0])
+        return {"config": "C5: B=1, char 140, 500 mel frames (T=100, r=5), inference + Griffin-Lim x50 (n_fft 2048, win 1200, hop 300), "
+                          "host text in, host waveform out", "p50_ms": statistics.median(t_all), "model_p50_ms": statistics.median(t_model),
+                "griffinlim_p50_ms": statistics.median(t_gl), "runs": 20, "spectral_convergence": {"after_50": c50, "after_0": c0},
+                "inversion_ok": bool(math.isfinite(c50) and c50 < c0)}
+    except Exception as ex:
+        return {"error": f"{type(ex).__name__}: {str(ex)[:160]}"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -345,6 +400,8 @@ def run_ours(args):
             except Exception as ex:           # never let the side measurement break the headline line
                 exact = {"error": str(ex)[:200]}
         _log("fp32-mode side measurement done")
+        c5 = None if args.no_c5 else measure_c5(args)
+        _log("C5 (single utterance + Griffin-Lim) side measurement done")
         cpu = None
         if not args.no_cpu_baseline:
             ts, threads = time_cpu_oracle(3)
@@ -374,6 +431,7 @@ def run_ours(args):
                          "whole_step": {"achieved": FWD_GFLOP / ms_per_step, "frac": FWD_GFLOP / ms_per_step / pk["bf16_tflops"]}},
             "exact_fp32_mode": exact,
             "train": train,
+            "c5_latency": c5,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
@@ -392,6 +450,7 @@ def main():
     ap.add_argument("--no-fp32-mode", action="store_true", help="skip the side measurement of the exact-fp32 precision mode")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying CUDA graphs")
     ap.add_argument("--no-train", action="store_true", help="skip the side measurement of the training step")
+    ap.add_argument("--no-c5", action="store_true", help="skip the single-utterance + Griffin-Lim latency side measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -119,6 +119,26 @@ def time_cpu_oracle(iters):
     return ts, threads
 
 
+def time_cpu_oracle_train():
+    """The reference CPU training step stand-in: oracle forward (train mode) + torch.autograd backward at C2 on the
+    host cores (clip + Adam omitted: <1 % of the step).  One warm-up + one timed step (~5-15 s each)."""
+    import torch
+    from oracle import tacotron_oracle as O
+    threads = max(1, min(CPU_THREADS_CAP, os.cpu_count() or 1))
+    torch.set_num_threads(threads)
+    cfg = O.OracleConfig(r=R)
+    params = O.init_params(cfg, seed=1)
+    inp = O.synthetic_inputs(cfg, B, TX, T, seed=0)
+    enc_m, dec_m = O.dropout_masks(cfg, B, TX, T, seed=2)
+    sm = O.sched_mask(cfg, B, T, seed=3)
+    ts = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        O.loss_and_grads(params, inp, cfg, enc_drop_masks=enc_m, dec_drop_masks=dec_m, sample_mask=sm)
+        ts.append(time.perf_counter() - t0)
+    return ts[-1], threads
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -408,6 +428,13 @@ def run_ours(args):
             sec = statistics.median(ts)
             cpu = {"value": FRAMES / sec, "unit": "mel frames/s", "cores": threads, "kind": "port",
                    "sample": "3 full C2 forward passes of the PyTorch-CPU oracle (32000 frames each), median"}
+            if train is not None and "error" not in train:
+                try:
+                    sec_t, thr_t = time_cpu_oracle_train()
+                    train["cpu_baseline"] = {"value": FRAMES / sec_t, "unit": "mel frames/s", "cores": thr_t, "kind": "port",
+                                             "sample": "1 C2 training step (forward + autograd backward) of the PyTorch-CPU oracle after 1 warm-up"}
+                except Exception as ex:
+                    train["cpu_baseline"] = {"error": str(ex)[:160]}
         _log("cpu baseline done")
         line = {
             "metric": METRIC, "value": value, "unit": "mel frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

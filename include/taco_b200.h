@@ -281,6 +281,12 @@ int taco_gl_frame(float* frw, const float* y, int B, int n, int hop, int n_fft, 
 /* full = mag * rebuilt/|rebuilt|  (audio.py:84,87) over `count` complex elements */
 int taco_gl_phase(float* full_c64, const float* mag, const float* rebuilt_c64, int64_t count, void* stream);
 
+/* Input data format: spectrograms are stored float16 (preprocess.py:179-180) and normalised in
+ * that dtype (data_input.py:56-64) before the float32 cast (:38-39).  Bit-exact device version of those statements:
+ * out[i][c] = f32( f16( f32( f16( f32(x) - f32(mean[c]) ) ) / std[c] ) ),  x [rows][W] float16, mean float16, std float32. */
+int taco_normalize_f16(float* out, const void* x_f16, const void* mean_f16, const float* std_f32, int64_t rows, int W,
+                       void* stream);
+
 int taco_sumsq(const float* x, int64_t n, float* partial_ws, float* out, void* stream);
 int taco_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr_t, float b1, float b2, float eps,
                    float clip, const float* sumsq, void* stream);

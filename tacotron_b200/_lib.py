@@ -102,6 +102,8 @@ EXPORTS = [
     "taco_adam_step",
     # spectrogram inversion (Griffin-Lim glue kernels)
     "taco_gl_init", "taco_gl_ola", "taco_gl_frame", "taco_gl_phase",
+    # input data format
+    "taco_normalize_f16",
 ]
 
 
@@ -158,6 +160,7 @@ def lib():
     L.taco_gl_ola.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
     L.taco_gl_frame.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
     L.taco_gl_phase.argtypes = [vp, vp, vp, i64, vp]
+    L.taco_normalize_f16.argtypes = [vp, vp, vp, vp, i64, i32, vp]
     for name in EXPORTS:                      # every declared symbol must resolve (AttributeError otherwise)
         getattr(L, name)
     _lib = L

@@ -22,6 +22,7 @@ import torch
 n_fft = 2048            # audio.py:10
 win_length = 1200       # audio.py:11
 hop_length = 300        # audio.py:12
+maximum_audio_length = 108000   # audio.py:13
 F_BINS = 1 + n_fft // 2
 
 

@@ -11,7 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtaco_b200.so")
-SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "gru.cu", "decoder.cu", "train.cu", "gru_bwd.cu", "decoder_bwd.cu", "audio.cu"]
+SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "gru.cu", "decoder.cu", "train.cu", "gru_bwd.cu", "decoder_bwd.cu", "audio.cu", "data.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

@@ -1,0 +1,58 @@
+// data.cu -- input-side data format of the path.
+//
+// The reference stores spectrograms as float16 (preprocess.py:179-180), normalises them in place in that dtype with
+// the statistics of a 100-utterance sample (data_input.py:56-64) and casts to float32 when batching (:38-39).  Here the
+// float16 arrays stay as stored in pinned host memory; a batch is copied H2D as float16 (half the PCIe bytes of the
+// reference's float32 feed) and normalised + widened on the device by this one bandwidth-bound kernel, bit-exactly:
+//     out = float32( float16( float32( float16( float32(x) - float32(mean) ) ) / std ) )
+// (numpy evaluates float16 arithmetic in float32 and rounds each statement's result to float16, round-to-nearest-even.)
+// Semantics pinned by oracle/data_oracle.py::normalize_explicit and tests/mirror_kernels.py::normalize_f16.
+#include <cuda_fp16.h>
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ float norm_one(__half x, __half m, float s) {
+    const __half d = __float2half_rn(__half2float(x) - __half2float(m));
+    const __half q = __float2half_rn(__fdiv_rn(__half2float(d), s));
+    return __half2float(q);
+}
+
+// two elements per thread: one 4-byte load, one 8-byte store; pairs may straddle a row end (W odd)
+__global__ void normalize_f16_kernel(float* __restrict__ out, const __half* __restrict__ x, const __half* __restrict__ mean,
+                                     const float* __restrict__ stdv, int64_t total, int W) {
+    const int64_t pairs = total >> 1;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < pairs; p += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = 2 * p;
+        const __half2 v = reinterpret_cast<const __half2*>(x)[p];
+        const int c0 = (int)(i % W);
+        const int c1 = (c0 + 1 == W) ? 0 : c0 + 1;
+        float2 o;
+        o.x = norm_one(__low2half(v), mean[c0], stdv[c0]);
+        o.y = norm_one(__high2half(v), mean[c1], stdv[c1]);
+        reinterpret_cast<float2*>(out)[p] = o;
+    }
+    if ((total & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        const int64_t i = total - 1;
+        const int c = (int)(i % W);
+        out[i] = norm_one(x[i], mean[c], stdv[c]);
+    }
+}
+
+}  // namespace
+
+extern "C" int taco_normalize_f16(float* out, const void* x_f16, const void* mean_f16, const float* std_f32, int64_t rows, int W,
+                                  void* stream) {
+    TACO_CHECK(out && x_f16 && mean_f16 && std_f32 && rows >= 0 && W >= 1, "taco_normalize_f16: bad arguments");
+    TACO_CHECK((reinterpret_cast<uintptr_t>(x_f16) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0,
+               "taco_normalize_f16: x must be 4-byte and out 8-byte aligned");
+    const int64_t total = rows * W;
+    if (total == 0) return 0;
+    int64_t g = ((total >> 1) + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    if (g < 1) g = 1;
+    normalize_f16_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(out, reinterpret_cast<const __half*>(x_f16),
+                                                                  reinterpret_cast<const __half*>(mean_f16), std_f32, total, W);
+    TACO_LAUNCH_CHECK();
+    return 0;
+}

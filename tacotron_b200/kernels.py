@@ -220,6 +220,14 @@ def gl_phase(full, mag, rebuilt):
     L.check(L.lib().taco_gl_phase(_p(full), _p(mag), _p(rebuilt), mag.numel(), _st()), "taco_gl_phase")
 
 
+def normalize_f16(out, x, mean, std):
+    """out fp32 [..., W] = the reference's in-place float16 normalisation of x (float16) followed by the float32 cast"""
+    W = x.shape[-1]
+    assert x.is_cuda and x.dtype == torch.float16 and x.is_contiguous() and out.dtype == torch.float32 and out.is_contiguous()
+    assert mean.dtype == torch.float16 and std.dtype == torch.float32 and mean.numel() == W == std.numel() and out.shape == x.shape
+    L.check(L.lib().taco_normalize_f16(_p(out), _p(x), _p(mean), _p(std), x.numel() // W, W, _st()), "taco_normalize_f16")
+
+
 _ss_ws = {}
 
 

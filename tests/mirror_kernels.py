@@ -384,6 +384,12 @@ def gl_frame(frw, y, hop, win_length):
         frw[:, t] = yp[:, t * hop:t * hop + n_fft] * w
 
 
+def normalize_f16(out, x, mean, std):
+    """out = f32( f16( f32( f16( f32(x) - f32(mean) ) ) / std ) )   (data_input.py:61-64 then :38-39)"""
+    d = (x.float() - mean.float()).half()
+    out.copy_((d.float() / std).half().float())
+
+
 def gl_phase(full, mag, rebuilt):
     """full = mag * exp(i angle(rebuilt))   (audio.py:84,87; angle(0) = 0)"""
     a = rebuilt.abs()

@@ -76,7 +76,10 @@ __device__ __forceinline__ void skinny_gemm(float* in_s, const float* in, int ld
         const float4* wrow = reinterpret_cast<const float4*>(W + (int64_t)n * ldw);
         const float* a = in_s + lane * lds;
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
+        // weight rows come from L2 (~300+ cycles per dependent load): keep 16 independent 16-byte loads in flight per
+        // warp.  (First hardware run had unroll 4: 12.5 us per stage, latency-bound on exactly these loads.)  The four
+        // accumulators see the same addends in the same order whatever the unroll factor, so results are bit-identical.
+#pragma unroll 16
         for (int k4 = 0; k4 < K4; ++k4) {
             const float4 w = __ldg(wrow + k4);
             a0 = fmaf(a[4 * k4 + 0], w.x, a0);

@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 nvidia-smi > gpurun_out/nvsmi.txt 2>&1
 python -c "import torch; print(torch.cuda.get_device_name(0), torch.cuda.get_device_capability(0))" > gpurun_out/dev.txt 2>&1
-for f in ${TEST_FILES:-test_gpu_linear test_gpu_recurrent test_gpu_model}; do
+for f in ${TEST_FILES:-test_gpu_linear test_gpu_recurrent test_gpu_model test_gpu_train test_gpu_z_audio test_gpu_z_data}; do
   echo "=== $f ===" 
   timeout 900 python -m pytest tests/$f.py -q -m gpu --tb=short -p no:cacheprovider ${PYTEST_ARGS} > gpurun_out/$f.log 2>&1
   echo "rc=$?" >> gpurun_out/$f.log

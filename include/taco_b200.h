@@ -201,6 +201,9 @@ typedef struct taco_gemm_desc {
     int32_t bshift;
 } taco_gemm_desc;
 int taco_gemm(const taco_gemm_desc* d, void* stream);
+/* which kernel taco_gemm launches: 0 = exact-product FFMA (default), 1 = 3xTF32 mma.sync tensor cores (fp32-grade,
+ * ~1e-6 relative; opt-in until it has had a hardware run).  Returns the previous setting. */
+int taco_set_gemm_impl(int impl);
 
 /* out[n] += sum_m A[m][n] * (Bm ? Bm[m][n] - (R ? R[m][n] : 0) : 1)     (bias / batch-norm gradients) */
 int taco_colsum(float* out, const float* A, int64_t lda, const float* Bm, int64_t ldb, const float* R, int64_t ldr,

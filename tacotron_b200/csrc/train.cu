@@ -134,6 +134,127 @@ __global__ void __launch_bounds__(256) gemm_kernel(const GemmP p) {
 }
 
 // =============================================================================================================
+// The same contraction on the tensor cores: mma.sync m16n8k8 TF32 with the 3xTF32 split (hi*hi + hi*lo + lo*hi,
+// fp32 accumulate) -- fp32-grade results (~1e-6 relative, like the forward decoder kernel) at a multiple of the FFMA
+// rate.  Tile loaders (transposes, row shifts, K segments, batches, split-K) are the SIMT kernel's, verbatim; only
+// the inner product differs.  Shared tiles use a 72-float row so that the fragment reads (bank = 8*tg + g) are
+// conflict-free.  8 warps: warp w owns rows [16*(w&3), +16) x columns [32*(w>>2), +32) of the 64x64 tile.
+// Opt-in (taco_set_gemm_impl(1)); the FFMA kernel stays the default until this one has had a hardware run.
+// Fragment coordinates (PTX m16n8k8 .tf32, g = lane>>2, tg = lane&3):
+//   A: a0 (g, tg) a1 (g+8, tg) a2 (g, tg+4) a3 (g+8, tg+4)    B: b0 (k=tg, n=g) b1 (k=tg+4, n=g)
+//   C: c0 (g, 2tg) c1 (g, 2tg+1) c2 (g+8, 2tg) c3 (g+8, 2tg+1)
+// =============================================================================================================
+constexpr int MLD = 72;
+
+__device__ __forceinline__ void split3(float x, uint32_t& hi, uint32_t& lo) {
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma16n8k8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256) gemm_mma_kernel(const GemmP p) {
+    __shared__ __align__(16) float As[GBK][MLD];
+    __shared__ __align__(16) float Bs[GBK][MLD];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tg = lane & 3;
+    const int z = blockIdx.z / p.splits, split = blockIdx.z % p.splits;
+    const int m0 = blockIdx.y * GBM, n0 = blockIdx.x * GBN;
+    const float* A = p.A + (int64_t)z * p.a_bstride;
+    const float* B = p.B + (int64_t)z * p.b_bstride;
+    float* C = p.C + (int64_t)z * p.c_bstride;
+    const int sh0 = p.shift + z * p.bshift;
+    const int kbeg = split * p.kchunk;
+    const int kend = min(p.K, kbeg + p.kchunk);
+    const int wm = (warp & 3) * 16, wn = (warp >> 2) * 32;
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int k0 = kbeg; k0 < kend; k0 += GBK) {
+        // ---- tile loaders: identical to gemm_kernel ----
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = tid + i * 256;
+            int kk, mm;
+            if (p.ta) { mm = idx & 63; kk = idx >> 6; } else { kk = idx & 15; mm = idx >> 4; }
+            const int k = k0 + kk, m = m0 + mm;
+            float v = 0.f;
+            if (k < kend && m < p.M) {
+                if (p.ta) {
+                    int src;
+                    if (shifted_row(k, sh0, p.period, p.a_rows, src)) v = A[(int64_t)src * p.lda + m];
+                } else {
+                    int sh = sh0, kc = k;
+                    if (p.taps > 1) { const int j = k / p.kper; sh += j * p.dshift; kc = k - j * p.kper; }
+                    int src;
+                    if (shifted_row(m, sh, p.period, p.a_rows, src)) v = A[(int64_t)src * p.lda + kc];
+                }
+            }
+            As[kk][mm] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int idx = tid + i * 256;
+            int kk, nn;
+            if (p.tb) { kk = idx & 15; nn = idx >> 4; } else { nn = idx & 63; kk = idx >> 6; }
+            const int k = k0 + kk, n = n0 + nn;
+            float v = 0.f;
+            if (k < kend && n < p.N) {
+                if (p.tb) {
+                    int64_t off = 0; int kc = k;
+                    if (p.taps > 1) { const int j = k / p.kper; off = (int64_t)j * p.b_tap_stride; kc = k - j * p.kper; }
+                    v = B[off + (int64_t)n * p.ldb + kc];
+                } else {
+                    v = B[(int64_t)k * p.ldb + n];
+                }
+            }
+            Bs[kk][nn] = v;
+        }
+        __syncthreads();
+        // ---- two k8 steps: 1 A fragment (16 rows) x 4 B fragments (4 x 8 columns), 3 MMAs each ----
+#pragma unroll
+        for (int ks = 0; ks < GBK; ks += 8) {
+            uint32_t ah[4], al[4];
+            split3(As[ks + tg][wm + g], ah[0], al[0]);
+            split3(As[ks + tg][wm + g + 8], ah[1], al[1]);
+            split3(As[ks + tg + 4][wm + g], ah[2], al[2]);
+            split3(As[ks + tg + 4][wm + g + 8], ah[3], al[3]);
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                uint32_t bh0, bl0, bh1, bl1;
+                split3(Bs[ks + tg][wn + nt * 8 + g], bh0, bl0);
+                split3(Bs[ks + tg + 4][wn + nt * 8 + g], bh1, bl1);
+                mma16n8k8(acc[nt], al, bh0, bh1);          // small terms first
+                mma16n8k8(acc[nt], ah, bl0, bl1);
+                mma16n8k8(acc[nt], ah, bh0, bh1);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int m = m0 + wm + g + ((e >> 1) ? 8 : 0);
+            const int n = n0 + wn + nt * 8 + 2 * tg + (e & 1);
+            if (m >= p.M || n >= p.N) continue;
+            float* c = C + (int64_t)m * p.ldc + n;
+            if (p.atomic) atomicAdd(c, acc[nt][e]);
+            else if (p.beta != 0.f) *c = fmaf(p.beta, *c, acc[nt][e]);
+            else *c = acc[nt][e];
+        }
+    }
+}
+
+// =============================================================================================================
 // column reductions: out[n] += sum_m A[m,n] * (Bm ? Bm[m,n] - (R ? R[m,n] : 0) : 1)
 // =============================================================================================================
 __global__ void __launch_bounds__(256) colsum_kernel(float* __restrict__ out, const float* __restrict__ A, int64_t lda,
@@ -390,6 +511,8 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 
 }  // namespace
 
+static int g_gemm_impl = 0;        // taco_set_gemm_impl
+
 extern "C" {
 
 int taco_gemm(const taco_gemm_desc* d, void* stream) {
@@ -422,9 +545,17 @@ int taco_gemm(const taco_gemm_desc* d, void* stream) {
     p.atomic = (d->beta == 1.f) ? 1 : 0;             // several launches may accumulate into the same C concurrently-in-order; atomics keep split-K safe
     TACO_CHECK((int64_t)splits * d->batch <= 65535 && tiles_m <= 65535, "taco_gemm: grid too large");
     dim3 grid(tiles_n, tiles_m, splits * d->batch);
-    gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    if (g_gemm_impl == 1) gemm_mma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    else gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
     TACO_LAUNCH_CHECK();
     return 0;
+}
+
+/* 0 = exact-product FFMA kernel (default), 1 = 3xTF32 mma.sync tensor-core kernel; returns the previous setting */
+int taco_set_gemm_impl(int impl) {
+    const int prev = g_gemm_impl;
+    if (impl == 0 || impl == 1) g_gemm_impl = impl;
+    return prev;
 }
 
 int taco_colsum(float* out, const float* A, int64_t lda, const float* Bm, int64_t ldb, const float* R, int64_t ldr, int M, int N,

@@ -68,6 +68,11 @@ def gemm(Cm, A, B, *, ta=False, tb=False, beta=0.0, shift=0, period=0, taps=1, d
     L.check(L.lib().taco_gemm(C.byref(d), _st()), "taco_gemm")
 
 
+def set_gemm_impl(impl):
+    """0 = exact-product FFMA GEMM (default), 1 = 3xTF32 mma.sync tensor-core GEMM; returns the previous setting"""
+    return L.lib().taco_set_gemm_impl(int(impl))
+
+
 def colsum(out, A, Bm=None, R=None, beta=1.0):
     _chk2(A, "colsum A")
     M, N = A.shape

@@ -111,7 +111,7 @@ int taco_gl_init(float* full_c64, float* mag, const float* spec, const float* ph
     TACO_CHECK((scale == nullptr) == (shift == nullptr), "taco_gl_init: scale and shift go together");
     const int64_t total = (int64_t)B * n * F;
     if (total == 0) return 0;
-    gl_init_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float2*>(full_c64), mag, spec, phase_u, T, n, r, F,
+    TACO_LAUNCH(gl_init_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, reinterpret_cast<float2*>(full_c64), mag, spec, phase_u, T, n, r, F,
                                                                            scale, shift, total);
     TACO_LAUNCH_CHECK();
     return 0;
@@ -123,7 +123,7 @@ int taco_gl_ola(float* y, const float* fr, int B, int n, int hop, int n_fft, int
     const int L = hop * (n - 1);
     const int64_t total = (int64_t)B * L;
     if (total == 0) return 0;
-    gl_ola_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(y, fr, n, L, hop, n_fft, win_length, total);
+    TACO_LAUNCH(gl_ola_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, y, fr, n, L, hop, n_fft, win_length, total);
     TACO_LAUNCH_CHECK();
     return 0;
 }
@@ -133,7 +133,7 @@ int taco_gl_frame(float* frw, const float* y, int B, int n, int hop, int n_fft, 
     const int L = hop * (n - 1);
     TACO_CHECK(n >= 2 && L > n_fft / 2, "taco_gl_frame: signal (%d samples) shorter than the reflect padding (%d)", L, n_fft / 2);
     const int64_t total = (int64_t)B * n * n_fft;
-    gl_frame_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(frw, y, n, L, hop, n_fft, win_length, total);
+    TACO_LAUNCH(gl_frame_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream, frw, y, n, L, hop, n_fft, win_length, total);
     TACO_LAUNCH_CHECK();
     return 0;
 }
@@ -141,7 +141,7 @@ int taco_gl_frame(float* frw, const float* y, int B, int n, int hop, int n_fft, 
 int taco_gl_phase(float* full_c64, const float* mag, const float* rebuilt_c64, int64_t count, void* stream) {
     TACO_CHECK(full_c64 && mag && rebuilt_c64 && count >= 0, "taco_gl_phase: bad arguments");
     if (count == 0) return 0;
-    gl_phase_kernel<<<grid_for(count, 256), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float2*>(full_c64), mag,
+    TACO_LAUNCH(gl_phase_kernel, grid_for(count, 256), 256, 0, (cudaStream_t)stream, reinterpret_cast<float2*>(full_c64), mag,
                                                                             reinterpret_cast<const float2*>(rebuilt_c64), count);
     TACO_LAUNCH_CHECK();
     return 0;

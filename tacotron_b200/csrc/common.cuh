@@ -1,4 +1,8 @@
 // common.cuh -- shared helpers for libtaco_b200 (sm_100a only).
+//
+// TACO_HOST_EMU: the functional host emulation used by tests/cuda_emu/ (the SAME kernel sources compiled with g++ and
+// run thread by thread on the CPU, so that indexing of a new kernel can be checked without a GPU).  It only removes
+// what cannot exist on a host (inline PTX, the CUDA runtime error plumbing) -- nothing below changes under nvcc.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -30,6 +34,14 @@ void taco_set_error(const char* fmt, ...);
 
 extern unsigned long long g_taco_launches;   // kernels launched by this library (bench.py reports it)
 
+// kernel launch: <<<>>> under nvcc; the emulation header pre-defines TACO_LAUNCH to run the grid on host threads
+#ifndef TACO_LAUNCH
+#define TACO_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#endif
+
+#ifdef TACO_HOST_EMU
+#define TACO_LAUNCH_CHECK() do { ++g_taco_launches; } while (0)
+#else
 #define TACO_LAUNCH_CHECK()                                                                 \
     do {                                                                                    \
         ++g_taco_launches;                                                                  \
@@ -39,6 +51,7 @@ extern unsigned long long g_taco_launches;   // kernels launched by this library
             return 3;                                                                       \
         }                                                                                   \
     } while (0)
+#endif
 
 static inline bool taco_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -63,6 +76,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
     }
 }
 
+#ifndef TACO_HOST_EMU
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers (mbarrier / TMA / tcgen05 / grid sync primitives)
 // ---------------------------------------------------------------------------------------------
@@ -172,3 +186,4 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+#endif  // !TACO_HOST_EMU

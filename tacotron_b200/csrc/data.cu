@@ -51,7 +51,7 @@ extern "C" int taco_normalize_f16(float* out, const void* x_f16, const void* mea
     int64_t g = ((total >> 1) + 255) / 256;
     if (g > 148 * 16) g = 148 * 16;
     if (g < 1) g = 1;
-    normalize_f16_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(out, reinterpret_cast<const __half*>(x_f16),
+    TACO_LAUNCH(normalize_f16_kernel, (int)g, 256, 0, (cudaStream_t)stream, out, reinterpret_cast<const __half*>(x_f16),
                                                                   reinterpret_cast<const __half*>(mean_f16), std_f32, total, W);
     TACO_LAUNCH_CHECK();
     return 0;

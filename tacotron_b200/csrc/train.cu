@@ -151,10 +151,15 @@ __device__ __forceinline__ void split3(float x, uint32_t& hi, uint32_t& lo) {
     lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma16n8k8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+#ifdef TACO_HOST_EMU
+    emu_mma_m16n8k8_tf32(d, a, b0, b1);     // warp-collective emulation of the instruction (tests/cuda_emu/emu.h)
+    return;
+#else
     asm volatile(
         "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+#endif
 }
 
 __global__ void __launch_bounds__(256) gemm_mma_kernel(const GemmP p) {
@@ -545,8 +550,8 @@ int taco_gemm(const taco_gemm_desc* d, void* stream) {
     p.atomic = (d->beta == 1.f) ? 1 : 0;             // several launches may accumulate into the same C concurrently-in-order; atomics keep split-K safe
     TACO_CHECK((int64_t)splits * d->batch <= 65535 && tiles_m <= 65535, "taco_gemm: grid too large");
     dim3 grid(tiles_n, tiles_m, splits * d->batch);
-    if (g_gemm_impl == 1) gemm_mma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
-    else gemm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    if (g_gemm_impl == 1) TACO_LAUNCH(gemm_mma_kernel, grid, 256, 0, (cudaStream_t)stream, p);
+    else TACO_LAUNCH(gemm_kernel, grid, 256, 0, (cudaStream_t)stream, p);
     TACO_LAUNCH_CHECK();
     return 0;
 }
@@ -557,6 +562,8 @@ int taco_set_gemm_impl(int impl) {
     if (impl == 0 || impl == 1) g_gemm_impl = impl;
     return prev;
 }
+
+#ifndef TACO_HOST_EMU   /* the remaining entry points launch with <<<>>> directly (not part of the host emulation) */
 
 int taco_colsum(float* out, const float* A, int64_t lda, const float* Bm, int64_t ldb, const float* R, int64_t ldr, int M, int N,
                 void* stream) {
@@ -705,5 +712,7 @@ int taco_adam_step(float* p, const float* g, float* m, float* v, int64_t n, floa
     TACO_LAUNCH_CHECK();
     return 0;
 }
+
+#endif  /* !TACO_HOST_EMU */
 
 }  // extern "C"

@@ -283,25 +283,78 @@ def measure_c5(args):
         return {"error": f"{type(ex).__name__}: {str(ex)[:160]}"}
 
 
+def measure_train_variant(args):
+    """Child-process body (`--impl train-variant-worker`): the training step with taco_gemm switched to its opt-in 3xTF32
+    mma.sync kernel.  First the gradient of one C2 step is computed with both GEMM kernels on identical saved activations
+    (relative L2 difference must be < 1e-4, else the timing is not reported as valid), then 5 steps are timed with each."""
+    import torch
+    from tacotron_b200 import Config, Tacotron, kernels as K
+    from tacotron_b200.models import ops
+    try:
+        cfg = Config(r=R, vocab_size=64, precision=args.precision)
+        m = Tacotron(cfg, None, train=True, seed=1)
+        g = torch.Generator().manual_seed(100)
+        gi = {"text": torch.randint(1, 64, (B, TX), generator=g, dtype=torch.int32).cuda(),
+              "text_length": torch.full((B,), TX, dtype=torch.int32).cuda(),
+              "mel": torch.randn(B, T, 80 * R, generator=g).half().float().cuda(),
+              "stft": torch.randn(B, T, 1025 * R, generator=g).half().float().cuda()}
+        S = {}
+        with ops.saving(S):
+            m.seq2seq_output, m.output = m.inference(gi, True)
+        S.update(text=gi["text"], text_length=gi["text_length"], mel=gi["mel"], stft=gi["stft"])
+        S["post/out"] = m.output
+        m.backward(S)
+        g0 = m._opt.g.clone()
+        K.set_gemm_impl(1)
+        m.backward(S)
+        torch.cuda.synchronize()
+        g1 = m._opt.g
+        rel = float((g1 - g0).norm() / g0.norm())
+
+        def timed(n=5):
+            for _ in range(2):
+                m.train_step(gi, lr=1e-4)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                m.train_step(gi, lr=1e-4)
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+        ms_mma = timed()
+        K.set_gemm_impl(0)
+        ms_ffma = timed()
+        return {"gemm": "3xTF32 mma.sync (taco_set_gemm_impl(1))", "grad_rel_l2_vs_ffma": rel, "valid": bool(rel < 1e-4),
+                "ms_per_step": ms_mma, "value": FRAMES / (ms_mma / 1e3), "unit": "mel frames/s", "ms_per_step_ffma_same_process": ms_ffma}
+    except Exception as ex:
+        return {"error": f"{type(ex).__name__}: {str(ex)[:160]}"}
+
+
+def _isolated(args, impl, limit):
+    """run a side measurement in a child process with a time limit and return its JSON result"""
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT",
+                                                            "LOCAL_WORLD_SIZE", "GROUP_RANK", "ROLE_RANK", "TORCHELASTIC_RUN_ID")}
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", impl, "--precision", args.precision]
+    if args.no_graph:
+        cmd.append("--no-graph")
+    try:
+        out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=limit)
+        for ln in reversed(out.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"error": f"no result from the {impl} child (rc={out.returncode}): {out.stderr.strip()[-160:]}"}
+    except subprocess.TimeoutExpired:
+        return {"error": f"{impl} child timed out ({limit} s)"}
+    except Exception as ex:
+        return {"error": f"{type(ex).__name__}: {str(ex)[:160]}"}
+
+
 def measure_c5_isolated(args):
     """Runs measure_c5 in a child process (`bench.py --impl c5-worker`) with a time limit: the Griffin-Lim kernels have
     not had a hardware run yet (round 1), so neither a device fault nor a hang in them may touch the process that prints
     the headline line."""
-    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT",
-                                                            "LOCAL_WORLD_SIZE", "GROUP_RANK", "ROLE_RANK", "TORCHELASTIC_RUN_ID")}
-    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "c5-worker", "--precision", args.precision]
-    if args.no_graph:
-        cmd.append("--no-graph")
-    try:
-        out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
-        for ln in reversed(out.stdout.strip().splitlines()):
-            if ln.startswith("{"):
-                return json.loads(ln)
-        return {"error": f"no result from the C5 worker (rc={out.returncode}): {out.stderr.strip()[-160:]}"}
-    except subprocess.TimeoutExpired:
-        return {"error": "C5 worker timed out (240 s)"}
-    except Exception as ex:
-        return {"error": f"{type(ex).__name__}: {str(ex)[:160]}"}
+    return _isolated(args, "c5-worker", 240)
 
 
 def run_ours(args):
@@ -441,8 +494,11 @@ def run_ours(args):
             except Exception as ex:           # never let the side measurement break the headline line
                 exact = {"error": str(ex)[:200]}
         _log("fp32-mode side measurement done")
-        c5 = None if args.no_c5 else measure_c5_isolated(args)
+        c5 = None if (args.no_c5 or world > 1) else measure_c5_isolated(args)     # single-GPU latency: N=1 runs only
         _log("C5 (single utterance + Griffin-Lim) side measurement done")
+        if train is not None and "error" not in train and world == 1:
+            train["tensor_core_gemm_variant"] = _isolated(args, "train-variant-worker", 240)
+            _log("training step with the mma.sync GEMM variant (child process) done")
         cpu = None
         if not args.no_cpu_baseline:
             ts, threads = time_cpu_oracle(3)
@@ -507,6 +563,8 @@ def main():
         run_reference(args)
     elif args.impl == "c5-worker":                       # internal: child process of measure_c5_isolated
         print(json.dumps(measure_c5(args)), flush=True)
+    elif args.impl == "train-variant-worker":            # internal: child process, opt-in GEMM kernel
+        print(json.dumps(measure_train_variant(args)), flush=True)
     else:
         run_ours(args)
 

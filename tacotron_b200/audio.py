@@ -67,12 +67,12 @@ def griffinlim_batch(spec, r, n_iter=50, scale=None, shift=None, phase_u=None, K
     frw = torch.empty((B, n, n_fft), dtype=rdt, device=spec.device)
     K.gl_init(full, mag, spec, phase_u, r, scale, shift)
     for it in range(n_iter + 1):
-        fr = torch.fft.irfft(full, n=n_fft, dim=-1)                          # cuFFT C2R, batch B*n
+        fr = torch.fft.irfft(full, n=n_fft, dim=-1).contiguous()             # cuFFT C2R, batch B*n
         K.gl_ola(y, fr, hop_length, win_length)
         if it == n_iter:
             break
         K.gl_frame(frw, y, hop_length, win_length)
-        rebuilt = torch.fft.rfft(frw, dim=-1)                                # cuFFT R2C
+        rebuilt = torch.fft.rfft(frw, dim=-1).contiguous()                   # cuFFT R2C
         K.gl_phase(full, mag, rebuilt)
     return y
 

@@ -21,10 +21,14 @@
 // Inter-stage data lives in L2 (ld.global.cg; never the non-coherent path).  This is a first, simple schedule --
 // the same dataflow treatment as the forward kernel (decoder.cu) is the planned optimisation.
 // Semantics pinned by tests/mirror_kernels.py::decoder_bwd.
+#ifndef TACO_HOST_EMU
 #include <cooperative_groups.h>
+#endif
 #include "common.cuh"
 
+#ifndef TACO_HOST_EMU
 namespace cg = cooperative_groups;
+#endif                              // (the host emulation, tests/cuda_emu/emu.h, provides cg:: for a 1-CTA grid)
 
 namespace {
 
@@ -63,12 +67,29 @@ __device__ __forceinline__ void skinny_gemm(float* in_s, const float* in, int ld
     if (first >= N) return;                              // CTA-uniform: no column for any warp of this CTA
     const int lds = K + 1;
     const int K4 = K >> 2;
-    for (int idx = tid; idx < RB * K4; idx += blockDim.x) {
-        const int row = idx / K4, k4 = idx - row * K4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < rows) v = __ldcg(reinterpret_cast<const float4*>(in + (int64_t)row * ldi) + k4);
-        float* d = in_s + row * lds + 4 * k4;
-        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    // stage in[32][K] -> in_s: four independent 16-byte L2 loads per thread are issued before the first store (the
+    // straightforward one-load-one-store loop serialised on the load latency: ~16 round trips per stage at K = 512)
+    const int total = RB * K4;
+    for (int base = tid; base < total; base += 4 * blockDim.x) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = base + u * blockDim.x;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (idx < total) {
+                const int row = idx / K4, k4 = idx - row * K4;
+                if (row < rows) v[u] = __ldcg(reinterpret_cast<const float4*>(in + (int64_t)row * ldi) + k4);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = base + u * blockDim.x;
+            if (idx < total) {
+                const int row = idx / K4, k4 = idx - row * K4;
+                float* d = in_s + row * lds + 4 * k4;
+                d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w;
+            }
+        }
     }
     __syncthreads();
     const int gw = blockIdx.x * NW + warp;
@@ -94,7 +115,11 @@ __device__ __forceinline__ void skinny_gemm(float* in_s, const float* in, int ld
 
 __global__ void __launch_bounds__(256, 1) decoder_bwd_kernel(const DecBwdP p) {
     cg::grid_group grid = cg::this_grid();
+#ifdef TACO_HOST_EMU
+    float* in_s = emu::dynamic_smem();                   // [32][MAXK+1]
+#else
     extern __shared__ __align__(16) float in_s[];        // [32][MAXK+1]
+#endif
     __shared__ float dctx_s[U], dal_s[256], ds_s[256], red_s[NW];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int B = p.B, T = p.T, Tx = p.Tx, OUT = p.OUT, MF = p.MF;
@@ -292,6 +317,15 @@ extern "C" int taco_decoder_bwd(const taco_decoder_bwd_args* a, void* stream) {
     p.DATT = a->DATT; p.DY = a->DY; p.DPQ = a->DPQ; p.DSCORE = a->DSCORE; p.DCTX = a->DCTX; p.DZ = a->DZ; p.DPN2 = a->DPN2;
     p.DPN1 = a->DPN1; p.DX = a->DX;
     p.ws = a->workspace;
+#ifdef TACO_HOST_EMU
+    // host emulation: one CTA (the kernel is written for any grid size), grid.sync() = block barrier
+    (void)stream;
+    memset(a->workspace, 0, (size_t)WS_TOTAL * 4);
+    memset(a->DATT + (int64_t)(a->T - 1) * a->B * U, 0, (size_t)a->B * U * 4);
+    emu::launch(dim3(1), dim3(256), [&] { decoder_bwd_kernel(p); });
+    ++g_taco_launches;
+    return 0;
+#else
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = (size_t)RB * (MAXK + 1) * 4;
     static int max_ctas = 0;
@@ -312,4 +346,5 @@ extern "C" int taco_decoder_bwd(const taco_decoder_bwd_args* a, void* stream) {
     TACO_CUDA(cudaLaunchCooperativeKernel((void*)decoder_bwd_kernel, dim3(G), dim3(256), args, smem, st));
     ++g_taco_launches;
     return 0;
+#endif
 }

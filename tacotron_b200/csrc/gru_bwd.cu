@@ -143,7 +143,7 @@ extern "C" int taco_bigru_bwd(float* dxp, const float* dOut, const float* out, c
     TACO_CHECK(dxp && dOut && out && ACT && Wg_h_fw && Wc_h_fw && Wg_h_bw && Wc_h_bw, "taco_bigru_bwd: NULL pointer");
     TACO_CHECK(B >= 0 && T >= 0, "taco_bigru_bwd: negative size");
     if (B == 0 || T == 0) return 0;
-    bigru_bwd_kernel<<<dim3(B, 2), 512, 0, (cudaStream_t)stream>>>(dxp, dOut, out, ACT, Wg_h_fw, Wc_h_fw, Wg_h_bw, Wc_h_bw, T);
+    TACO_LAUNCH(bigru_bwd_kernel, dim3(B, 2), 512, 0, (cudaStream_t)stream, dxp, dOut, out, ACT, Wg_h_fw, Wc_h_fw, Wg_h_bw, Wc_h_bw, T);
     TACO_LAUNCH_CHECK();
     return 0;
 }

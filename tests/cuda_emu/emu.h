@@ -134,5 +134,17 @@ inline dim3 as_dim3(dim3 d) { return d; }
 inline dim3 as_dim3(int x) { return dim3((unsigned)x); }
 }  // namespace emu
 
+namespace emu {
+// dynamic shared memory of the (single) running block; large enough for every kernel of this repository
+inline float* dynamic_smem() { static float buf[64 * 1024]; return buf; }
+}  // namespace emu
+
+// cooperative groups for a ONE-block grid (kernels written for any grid size are emulated with gridDim = 1):
+// grid.sync() is then a block barrier
+namespace cg {
+struct grid_group { void sync() const { __syncthreads(); } };
+inline grid_group this_grid() { return grid_group(); }
+}  // namespace cg
+
 #define TACO_LAUNCH(kernel, grid, block, smem, stream, ...) \
     emu::launch(emu::as_dim3(grid), emu::as_dim3(block), [&] { kernel(__VA_ARGS__); })

@@ -25,7 +25,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("emu") / "libtaco_emu.so")
-    src = [os.path.join(ROOT, "tests", "cuda_emu", f) for f in ("emu_lib.cpp", "emu_train.cpp", "emu_audio.cpp", "emu_data.cpp")]
+    src = [os.path.join(ROOT, "tests", "cuda_emu", f) for f in ("emu_lib.cpp", "emu_train.cpp", "emu_audio.cpp", "emu_data.cpp",
+                                                                 "emu_decoder_bwd.cpp", "emu_gru_bwd.cpp")]
     cuda_inc = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
     if not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
         pytest.skip("CUDA toolkit headers not found")
@@ -141,6 +142,69 @@ def test_griffinlim_kernels_under_emulation(emu, r, T):
     emu.taco_gl_phase.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     assert emu.taco_gl_phase(_p(p_e), _p(mag_c), _p(reb), mag_c.numel(), None) == 0
     close(p_e, p_c, 1e-5)
+
+
+@pytest.mark.parametrize("r,sched", [(2, True), (5, False)])
+def test_decoder_bwd_kernel_under_emulation(emu, r, sched):
+    """the cooperative decoder-backward kernel (green on hardware) as a one-CTA grid: shared-memory staging, the column
+    dealing, all 11 stages and the attention block reductions against the mirror"""
+    import copy
+    from tacotron_b200.models import grad
+    from tests import grad_util, train_checks as TC
+    B, Tx, T = 2, 8, 4
+    cfg, p, inp, enc_m, dec_m, sm = TC._small_case(r, sched, B, Tx, T)
+    S, y, out = grad_util.saving_forward(p, inp, cfg, enc_m, dec_m, sm)
+    S["_capture"] = {}
+    G = {k: torch.zeros_like(v) for k, v in p.items()}
+    dY = torch.randn(B, T, 80 * r, generator=torch.Generator().manual_seed(5))
+    grad.decoder_bwd(MK, p, G, S, cfg, dY)
+    a = S["_capture"]["decoder_bwd"]                          # inputs + the mirror's outputs
+    outs = ("DATT", "DY", "DPQ", "DSCORE", "DCTX", "DZ", "DPN2", "DPN1", "DX")
+    e = {k: copy.deepcopy(v) for k, v in a.items() if not k.startswith("_")}
+    for k in outs:
+        e[k].fill_(float("nan"))
+    for i in range(3):
+        e["DG"][i].fill_(float("nan")); e["DC"][i].fill_(float("nan"))
+    d = L.DecoderBwdArgs()
+    d.B, d.T, d.Tx, d.r, d.keep_scale = B, T, Tx, r, float(a["keep_scale"])
+    for k in ("W_a", "W_q", "W_out", "W_in", "W1", "W2", "v", "dy_ext", "align", "values", "keys", "PQ", "PN1", "PN2", "sel", *outs):
+        assert e[k].is_contiguous(), k
+        setattr(d, k, e[k].data_ptr())
+    for k in ("Wg", "Wc", "RU", "C", "H", "DG", "DC"):
+        for i in range(3):
+            e[k][i] = e[k][i].contiguous()
+            getattr(d, k)[i] = e[k][i].data_ptr()
+    emu.taco_decoder_bwd_workspace_bytes.restype = C.c_size_t
+    ws = torch.empty(emu.taco_decoder_bwd_workspace_bytes() // 4)
+    d.workspace = ws.data_ptr()
+    emu.taco_decoder_bwd.argtypes = [C.POINTER(L.DecoderBwdArgs), C.c_void_p]
+    assert emu.taco_decoder_bwd(C.byref(d), None) == 0, emu.taco_last_error().decode()
+    for k in outs:
+        got, ref = torch.nan_to_num(e[k], nan=1e30), a[k]
+        assert (got - ref).abs().max().item() <= 2e-5 * (ref.abs().max().item() + 1e-6), k
+    for i in range(3):
+        for k in ("DG", "DC"):
+            got, ref = torch.nan_to_num(e[k][i], nan=1e30), a[k][i]
+            assert (got - ref).abs().max().item() <= 2e-5 * (ref.abs().max().item() + 1e-6), (k, i)
+
+
+def test_bigru_bwd_kernel_under_emulation(emu):
+    """the register-resident bi-GRU BPTT kernel (green on hardware): 512-thread CTAs, butterfly shuffles"""
+    g = torch.Generator().manual_seed(3)
+    B, T = 2, 5
+    out = torch.tanh(torch.randn(B, T, 256, generator=g))
+    ACT = torch.rand(B, T, 768, generator=g)
+    ACT[:, :, 256:384] = ACT[:, :, 256:384] * 2 - 1
+    ACT[:, :, 640:768] = ACT[:, :, 640:768] * 2 - 1
+    dOut = torch.randn(B, T, 256, generator=g)
+    W = [torch.randn(128, 256, generator=g) * 0.1, torch.randn(128, 128, generator=g) * 0.1,
+         torch.randn(128, 256, generator=g) * 0.1, torch.randn(128, 128, generator=g) * 0.1]
+    ref = torch.zeros(B, T, 768)
+    MK.bigru_bwd(ref, dOut, out, ACT, *W)
+    got = torch.full((B, T, 768), float("nan"))
+    emu.taco_bigru_bwd.argtypes = [C.c_void_p] * 8 + [C.c_int, C.c_int, C.c_void_p]
+    assert emu.taco_bigru_bwd(_p(got), _p(dOut), _p(out), _p(ACT), *[_p(w) for w in W], B, T, None) == 0
+    assert (torch.nan_to_num(got, nan=1e30) - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
 
 
 def test_normalize_f16_under_emulation_is_bit_exact(emu):

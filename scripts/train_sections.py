@@ -10,7 +10,6 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
-from oracle import tacotron_oracle as O  # noqa: E402
 from tacotron_b200 import kernels as K  # noqa: E402
 from tacotron_b200.models import grad, ops  # noqa: E402
 from tacotron_b200.models.tacotron import Config, Tacotron  # noqa: E402
@@ -49,8 +48,11 @@ class TimedK:
 def main():
     cfg = Config(r=5, vocab_size=64, precision=os.environ.get("PRECISION", "tf32"))
     m = Tacotron(cfg, None, train=True)
-    inp = O.synthetic_inputs(O.OracleConfig(r=5), 32, 128, 200, seed=0)
-    gi = {k: v.cuda() for k, v in inp.items()}
+    g = torch.Generator().manual_seed(0)
+    gi = {"text": torch.randint(1, 64, (32, 128), generator=g, dtype=torch.int32).cuda(),
+          "text_length": torch.full((32,), 128, dtype=torch.int32).cuda(),
+          "mel": torch.randn(32, 200, 400, generator=g).half().float().cuda(),
+          "stft": torch.randn(32, 200, 5125, generator=g).half().float().cuda()}
     for _ in range(2):
         m.train_step(gi, lr=1e-4)
     torch.cuda.synchronize()

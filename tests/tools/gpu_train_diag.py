@@ -2,19 +2,22 @@
 writes per-tensor errors to gpurun_out/train_diag.txt (simple kernels first, the cooperative decoder kernel and the
 whole model last, so that a fault late in the list does not hide the earlier results).
 
-    gpurun -- python scripts/gpu_train_diag.py
+    gpurun -- python tests/tools/gpu_train_diag.py
+
+(It lives under tests/ because it executes the oracle-backed checks of tests/train_checks.py: test infrastructure.)
 """
 import os
 import sys
 import time
 import traceback
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 from tests import train_checks as TC  # noqa: E402
 
-OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+OUT = os.path.join(ROOT, "gpurun_out")
 os.makedirs(OUT, exist_ok=True)
 # optional argument: a group letter (A..F) so that each group runs in its own process -- a device fault in one
 # group then cannot poison the CUDA context of the others.  No argument = everything in this process.

@@ -1,4 +1,4 @@
-"""GPU checks of the training path, shared by tests/test_gpu_train.py (asserting) and scripts/gpu_train_diag.py
+"""GPU checks of the training path, shared by tests/test_gpu_train.py (asserting) and tests/tools/gpu_train_diag.py
 (reporting).  Every check runs a CUDA entry point (tacotron_b200/kernels.py) and its torch-CPU mirror
 (tests/mirror_kernels.py) on identical inputs and returns {tensor name: (max abs err, max |ref|)}.
 """

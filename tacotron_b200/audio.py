@@ -65,6 +65,11 @@ def griffinlim_batch(spec, r, n_iter=50, scale=None, shift=None, phase_u=None, K
     full = torch.empty((B, n, F_BINS), dtype=cdt, device=spec.device)
     y = torch.empty((B, L), dtype=rdt, device=spec.device)
     frw = torch.empty((B, n, n_fft), dtype=rdt, device=spec.device)
+    _gl_iterations(K, full, mag, spec, phase_u, r, scale, shift, y, frw, n_iter)
+    return y
+
+
+def _gl_iterations(K, full, mag, spec, phase_u, r, scale, shift, y, frw, n_iter):
     K.gl_init(full, mag, spec, phase_u, r, scale, shift)
     for it in range(n_iter + 1):
         fr = torch.fft.irfft(full, n=n_fft, dim=-1).contiguous()             # cuFFT C2R, batch B*n
@@ -74,7 +79,54 @@ def griffinlim_batch(spec, r, n_iter=50, scale=None, shift=None, phase_u=None, K
         K.gl_frame(frw, y, hop_length, win_length)
         rebuilt = torch.fft.rfft(frw, dim=-1).contiguous()                   # cuFFT R2C
         K.gl_phase(full, mag, rebuilt)
-    return y
+
+
+class GriffinLimGraph:
+    """The same 5-launches-per-iteration loop captured ONCE into a CUDA graph for a fixed (B, T, r, n_iter) and replayed:
+    251 launches (and their Python / ctypes / cuFFT-plan overhead, ~0.1 ms per iteration of host time) collapse into one
+    graph launch.  Inputs are copied into static device buffers; the result is the static `y` (valid until the next call).
+    Opt-in: `invert_spectrogram(...)` stays eager."""
+
+    def __init__(self, B, T, r, n_iter=50, device="cuda", with_affine=True):
+        K = _K()
+        self.B, self.T, self.r, self.n_iter = B, T, r, n_iter
+        n = 4 * r * (T // 4)
+        L = hop_length * (n - 1)
+        assert L > n_fft // 2
+        dev = torch.device(device)
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.spec = torch.zeros((B, T, F_BINS * r), **f32)
+        self.phase_u = torch.zeros((B, n, F_BINS), **f32)
+        self.scale = torch.ones((F_BINS * r,), **f32) if with_affine else None
+        self.shift = torch.zeros((F_BINS * r,), **f32) if with_affine else None
+        self.mag = torch.empty((B, n, F_BINS), **f32)
+        self.full = torch.empty((B, n, F_BINS), dtype=torch.complex64, device=dev)
+        self.y = torch.empty((B, L), **f32)
+        self.frw = torch.empty((B, n, n_fft), **f32)
+        args = (K, self.full, self.mag, self.spec, self.phase_u, r, self.scale, self.shift, self.y, self.frw, n_iter)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                     # warm-up outside capture: cuFFT plans, lazy module loads
+            _gl_iterations(*args)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            _gl_iterations(*args)
+
+    def __call__(self, spec, stft_mean=None, stft_std=None, phase_u=None, generator=None):
+        self.spec.copy_(spec.reshape(self.spec.shape), non_blocking=True)
+        if self.scale is not None:
+            if stft_std is not None:
+                self.scale.copy_(stft_std, non_blocking=True); self.shift.copy_(stft_mean, non_blocking=True)
+            else:
+                self.scale.fill_(1.0); self.shift.zero_()
+        if phase_u is None:
+            self.phase_u.uniform_(0.0, 1.0, generator=generator)             # audio.py:81 (in place, on the device)
+        else:
+            self.phase_u.copy_(phase_u.reshape(self.phase_u.shape), non_blocking=True)
+        self.graph.replay()
+        return self.y
 
 
 def griffinlim(spectrogram, n_iter=50, phase_u=None, K=None):

@@ -10,6 +10,9 @@
    seeded weights/inputs at B=2, Tx=12, T=6.  These pin the oracle against regressions and give the
    GPU tests a fixture that does not depend on re-running the oracle; they are NOT reference
    outputs (TensorFlow 1.2 cannot run here -- parity unpinned, see oracle/tf12.py).
+3. reference_wiring_r{2,5}.npz -- the reference's own model code executed over oracle/tf12_shim.py (see reference_wiring).
+4. reference_griffinlim.npz -- the reference's own audio.invert_spectrogram executed with librosa's stft/istft stood in
+   by the restatements of oracle/audio_oracle.py (see reference_griffinlim).
 """
 import os
 import sys
@@ -131,7 +134,45 @@ def reference_wiring():
         print(f"reference_wiring_r{r}.npz written ({len(shim.S.created)} variables)")
 
 
+def reference_griffinlim():
+    """Execute the reference's OWN audio.invert_spectrogram / audio.griffinlim (audio.py:67-97, unmodified, imported from
+    /root/reference) with `librosa.stft` / `librosa.istft` stood in by the restatements of oracle/audio_oracle.py (librosa
+    is not installed) and save input + output: pins the WIRING of the inversion (reshape_frames inverse, exp, the
+    50-iteration loop, the angle update, the final istft) against the reference source.  The random initial phase
+    (audio.py:81) is reproduced from the numpy seed stored in the fixture."""
+    from oracle import audio_oracle as A
+    for k in [k for k in sys.modules if k in ("audio", "librosa", "tensorflow", "tqdm")]:
+        del sys.modules[k]
+    lib = types.ModuleType("librosa")
+    lib.stft = lambda y, n_fft=2048, hop_length=None, win_length=None, window="hann": A.stft(y, n_fft, hop_length, win_length)
+    lib.istft = lambda D, hop_length=None, win_length=None, window="hann": A.istft(D, hop_length, win_length)
+    sys.modules["librosa"] = lib
+    sys.modules["tensorflow"] = types.ModuleType("tensorflow")
+    tq = types.ModuleType("tqdm")
+    tq.tqdm = lambda x, **k: x
+    sys.modules["tqdm"] = tq
+    if not hasattr(np, "complex"):
+        np.complex = complex                       # alias removed from numpy >= 1.24; the reference (2017) uses it (audio.py:84,93)
+    if "/root/reference" not in sys.path:
+        sys.path.insert(0, "/root/reference")
+    import audio as ref_audio                      # the reference module, unmodified
+    out = {}
+    for r, T in ((2, 8), (5, 4)):
+        ref_audio.r = r                            # module global read by reshape_frames (audio.py:17)
+        rng = np.random.RandomState(10 + r)
+        spec = (rng.randn(T, 1025 * r) * 0.5).astype(np.float32)
+        seed = 100 + r
+        np.random.seed(seed)
+        wave = ref_audio.invert_spectrogram(spec)
+        out[f"spec_r{r}"] = spec
+        out[f"seed_r{r}"] = np.array(seed)
+        out[f"wave_r{r}"] = np.asarray(wave)
+    np.savez_compressed(os.path.join(HERE, "reference_griffinlim.npz"), **out)
+    print("reference_griffinlim.npz", {k: v.shape for k, v in out.items()})
+
+
 if __name__ == "__main__":
     reference_reshape_frames()
     oracle_small()
     reference_wiring()
+    reference_griffinlim()

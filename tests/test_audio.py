@@ -60,6 +60,26 @@ def test_griffinlim_host_logic_matches_oracle(r, T, n_iter):
         assert np.abs(y[b].numpy() - ref).max() < 1e-9 * max(1.0, np.abs(ref).max())
 
 
+@pytest.mark.parametrize("r", [2, 5])
+def test_inversion_wiring_matches_the_reference_code(r):
+    """tests/golden/reference_griffinlim.npz holds outputs of the reference's OWN audio.invert_spectrogram (executed from
+    /root/reference with librosa's stft/istft stood in by the restatements, tests/golden/make_golden.py): the oracle and
+    the device orchestration (over the CPU mirror kernels) must reproduce them -- reshape_frames inverse, exp, the random
+    initial phase drawn from numpy's seeded stream, 50 iterations, final istft."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_griffinlim.npz"))
+    spec, seed, wave = z[f"spec_r{r}"], int(z[f"seed_r{r}"]), z[f"wave_r{r}"]
+    n = 4 * r * (spec.shape[0] // 4)
+    u = np.random.RandomState(seed).rand(1025, n)                                       # audio.py:81 with np.random.seed(seed)
+    ref = A.invert_spectrogram(spec, r, np.exp(2j * np.pi * u), n_iter=50)
+    assert ref.shape == wave.shape and np.abs(ref - wave).max() < 1e-9 * np.abs(wave).max()
+    y = audio.invert_spectrogram(torch.from_numpy(spec.astype(np.float64)), r, n_iter=50,
+                                 phase_u=torch.from_numpy(np.ascontiguousarray(u.T)), K=MK)
+    # (the reference exponentiates its float32 input in float32, audio.py:70; the orchestration here runs in float64 end to
+    #  end, so the two differ by float32 rounding of exp(), carried through 50 iterations: 3e-6 relative)
+    assert np.abs(y.numpy() - wave).max() < 2e-5 * np.abs(wave).max()
+
+
 def test_griffinlim_single_spectrogram_api():
     g = torch.Generator().manual_seed(3)
     mag = torch.rand(1025, 8, generator=g, dtype=torch.float64) + 0.1

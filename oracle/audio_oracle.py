@@ -10,9 +10,11 @@ no requirements file) and is not installed here, so its published algorithm (lib
   istft (center=True): y[t*hop : t*hop+n_fft] += w * irfft(D[:, t]); y /= sum_t w^2 shifted by t*hop wherever that sum
         exceeds tiny; the n_fft//2 border samples are trimmed.
 
-PARITY UNPINNED w.r.t. librosa itself (cannot run here).  Pinned instead against torch.stft / torch.istft, which
-implement the same published conventions independently (tests/test_audio.py), and `reshape_frames` against outputs of the
-reference's own function (tests/golden/reshape_frames.npz).
+PARITY UNPINNED w.r.t. librosa itself (cannot run here).  Pinned instead (tests/test_audio.py): the stft/istft
+restatements against torch.stft / torch.istft, which implement the same published conventions independently (1e-14);
+`reshape_frames` against outputs of the reference's own function (tests/golden/reshape_frames.npz); and the WIRING of the
+inversion against outputs of the reference's own `audio.invert_spectrogram`, executed unmodified from /root/reference with
+librosa's two calls stood in by the restatements below (tests/golden/reference_griffinlim.npz; reproduced exactly).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline legs may import this module.
 """

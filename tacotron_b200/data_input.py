@@ -49,8 +49,7 @@ def load_from_npy(dirname, mmap=True, rng=None):
     mel = np.load(j("mels.npy"), mmap_mode=mode)                                          # :48
     rng = rng or np.random
     index = rng.randint(len(stft), size=100)                                              # :54 (a sample, to bound memory)
-    index_sorted = np.sort(index)                                                         # (memory-map friendly gather)
-    stft_s, mel_s = np.asarray(stft[index_sorted]), np.asarray(mel[index_sorted])
+    stft_s, mel_s = np.asarray(stft[index]), np.asarray(mel[index])                       # same element order as the reference
     stft_mean = np.mean(stft_s, axis=(0, 1))                                              # :56  (float16 like the input)
     mel_mean = np.mean(mel_s, axis=(0, 1))                                                # :57
     stft_std = np.std(stft_s, axis=(0, 1), dtype=np.float32)                              # :58

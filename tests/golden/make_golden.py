@@ -13,6 +13,7 @@
 3. reference_wiring_r{2,5}.npz -- the reference's own model code executed over oracle/tf12_shim.py (see reference_wiring).
 4. reference_griffinlim.npz -- the reference's own audio.invert_spectrogram executed with librosa's stft/istft stood in
    by the restatements of oracle/audio_oracle.py (see reference_griffinlim).
+5. reference_data_input.npz -- the reference's own data_input.load_from_npy executed on a tiny synthetic data set.
 """
 import os
 import sys
@@ -171,7 +172,44 @@ def reference_griffinlim():
     print("reference_griffinlim.npz", {k: v.shape for k, v in out.items()})
 
 
+def reference_data_input():
+    """Execute the reference's OWN data_input.load_from_npy / load_prompts arithmetic (data_input.py:42-85, unmodified,
+    imported from /root/reference with tensorflow / matplotlib stubbed) on a tiny synthetic data set and save inputs +
+    outputs: pins the float16 in-place normalisation, the 100-utterance statistics (numpy's seeded stream) and the
+    speech_length override against the reference source."""
+    import tempfile
+    for k in [k for k in sys.modules if k in ("data_input", "tensorflow", "matplotlib", "matplotlib.pyplot")]:
+        del sys.modules[k]
+    sys.modules["tensorflow"] = types.ModuleType("tensorflow")
+    mpl = types.ModuleType("matplotlib"); mpl.use = lambda *a, **k: None
+    sys.modules["matplotlib"] = mpl
+    sys.modules["matplotlib.pyplot"] = types.ModuleType("matplotlib.pyplot")
+    if "/root/reference" not in sys.path:
+        sys.path.insert(0, "/root/reference")
+    import data_input as ref_di                    # the reference module, unmodified
+    rng = np.random.RandomState(0)
+    N, Tx, T, r = 12, 8, 4, 2
+    raw = {"texts": rng.randint(1, 20, size=(N, Tx)).astype(np.int64), "text_lens": rng.randint(3, Tx + 1, size=N).astype(np.int64),
+           "stfts": (rng.randn(N, T, 1025 * r) * 2 - 3).astype(np.float16), "mels": (rng.randn(N, T, 80 * r) * 2 - 3).astype(np.float16),
+           "speech_lens": rng.randint(2, T + 1, size=N).astype(np.int64)}
+    with tempfile.TemporaryDirectory() as d:
+        for k, v in raw.items():
+            np.save(os.path.join(d, k + ".npy"), v)
+        seed = 7
+        np.random.seed(seed)
+        inputs, names, num_speakers, stft_mean, stft_std = ref_di.load_from_npy(d + "/")
+    out = {"raw_" + k: v for k, v in raw.items()}
+    out["seed"] = np.array(seed)
+    for n, a in zip(names, inputs):
+        out["ref_" + n] = np.asarray(a)
+    out["ref_stft_mean"], out["ref_stft_std"] = np.asarray(stft_mean), np.asarray(stft_std)
+    out["num_speakers"] = np.array(num_speakers)
+    np.savez_compressed(os.path.join(HERE, "reference_data_input.npz"), **out)
+    print("reference_data_input.npz", names, {k: (v.shape, str(v.dtype)) for k, v in out.items() if k.startswith("ref_")})
+
+
 if __name__ == "__main__":
+    reference_data_input()
     reference_reshape_frames()
     oracle_small()
     reference_wiring()

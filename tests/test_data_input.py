@@ -51,7 +51,7 @@ def test_load_from_npy_and_batches(tmp_path):
     assert names == ["text", "text_length", "stft", "mel", "speech_length"] and nspk == 1
     assert arrays["stft"].dtype == np.float16 and stft_mean.dtype == np.float16 and stft_std.dtype == np.float32
     assert (arrays["speech_length"] == 8).all()                  # data_input.py:71-72: padded length for every utterance
-    idx = np.sort(np.random.RandomState(3).randint(40, size=100))
+    idx = np.random.RandomState(3).randint(40, size=100)
     m2, s2 = DO.sample_stats(np.load(d + "stfts.npy"), idx)
     assert np.array_equal(m2, stft_mean) and np.array_equal(s2, stft_std)
     it = data_input.build_dataset(arrays, names, batch_size=4, buffer_size=16, seed=5, device="cpu", K=MK)
@@ -68,6 +68,30 @@ def test_load_from_npy_and_batches(tmp_path):
             assert np.array_equal(b["mel"][k].numpy(), refm)
             seen.append(j)
     assert len(set(seen)) == 40                                  # 120 draws through a 16-slot buffer visit everything
+
+
+def test_loader_and_normalisation_match_the_reference_code(tmp_path):
+    """tests/golden/reference_data_input.npz holds what the reference's OWN data_input.load_from_npy (executed from
+    /root/reference, tests/golden/make_golden.py) returns for a tiny data set: its in-place float16 normalisation, the
+    statistics of its 100-utterance sample (numpy's seeded stream), dtypes and the speech_length override.  The loader
+    here keeps the spectrograms as stored; its statistics and the per-batch device normalisation (kernel mirror) must
+    give exactly the reference's values."""
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_data_input.npz"))
+    d = str(tmp_path) + "/"
+    for k in ("texts", "text_lens", "stfts", "mels", "speech_lens"):
+        np.save(d + k + ".npy", z["raw_" + k])
+    arrays, names, nspk, stft_mean, stft_std = data_input.load_from_npy(d, rng=np.random.RandomState(int(z["seed"])))
+    assert nspk == int(z["num_speakers"]) and names == ["text", "text_length", "stft", "mel", "speech_length"]
+    assert stft_mean.dtype == z["ref_stft_mean"].dtype and np.array_equal(stft_mean, z["ref_stft_mean"])
+    assert stft_std.dtype == z["ref_stft_std"].dtype and np.array_equal(stft_std, z["ref_stft_std"])
+    for k in ("text", "text_length", "speech_length"):
+        assert arrays[k].dtype == z["ref_" + k].dtype and np.array_equal(arrays[k], z["ref_" + k])
+    for k in ("stft", "mel"):
+        st = arrays["_stats"]
+        out = torch.empty(arrays[k].shape, dtype=torch.float32)
+        MK.normalize_f16(out, torch.from_numpy(np.asarray(arrays[k])), torch.from_numpy(st[f"{k}_mean"]), torch.from_numpy(st[f"{k}_std"]))
+        assert np.array_equal(out.numpy(), z["ref_" + k].astype(np.float32))          # == tf.cast(normalised float16, float32)
+        assert np.array_equal(DO.normalize_explicit(np.asarray(arrays[k]), st[f"{k}_mean"], st[f"{k}_std"]), z["ref_" + k].astype(np.float32))
 
 
 def test_shuffle_buffer_semantics():

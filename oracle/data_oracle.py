@@ -10,8 +10,10 @@ normalised IN PLACE in that dtype with statistics of a 100-utterance sample, and
     x /= std    -> float16( float32(x) / std )                                                             :63-64
     batch = tf.cast(x, tf.float32)                                                                         :38-39
 
-Bit-exact target for the device kernel taco_normalize_f16 (tacotron_b200/data_input.py).  This file is pinned by numpy
-itself: the restatement is executed with the same numpy calls the reference makes (tests/test_data_input.py).
+Bit-exact target for the device kernel taco_normalize_f16 (tacotron_b200/data_input.py).  Pinned twice
+(tests/test_data_input.py): the per-element restatement equals the same numpy in-place statements the reference makes,
+and it equals the arrays the reference's OWN data_input.load_from_npy returns (executed unmodified from /root/reference
+by tests/golden/make_golden.py -> tests/golden/reference_data_input.npz), statistics and dtypes included.
 """
 from __future__ import annotations
 

@@ -218,12 +218,39 @@ def measure_train(args, world, rank):
         D.barrier()
         ms = D.max_over_ranks(ev[0].elapsed_time(ev[n]) / n)
         loss = float(m.loss)
+        # one more step with events between its phases (this rank only; the phases overlap host work differently than
+        # in the free-running loop above, so they need not add up to ms_per_step exactly)
+        sections = None
+        try:
+            from tacotron_b200 import kernels as K
+            from tacotron_b200.models import ops
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            torch.cuda.synchronize()
+            e[0].record()
+            S = {}
+            with ops.saving(S):
+                m.seq2seq_output, m.output = m.inference(gi, True)
+            m.loss = m.add_loss_op(m.seq2seq_output, m.output, gi["mel"], gi["stft"])
+            S.update(text=gi["text"], text_length=gi["text_length"], mel=gi["mel"], stft=gi["stft"])
+            S["post/out"] = m.output
+            e[1].record()
+            m.backward(S)
+            e[2].record()
+            m._opt.apply(K, m.store.flat, 1e-4, m.config.cap_grads, allreduce=False)   # local: no collective outside the timed loop
+            m.store.version += 1
+            e[3].record()
+            torch.cuda.synchronize()
+            sections = {"forward_loss": e[0].elapsed_time(e[1]), "backward": e[1].elapsed_time(e[2]),
+                        "sumsq_clip_adam": e[2].elapsed_time(e[3])}
+        except Exception as ex:
+            sections = {"error": f"{type(ex).__name__}: {str(ex)[:120]}"}
         return {"value": D.aggregate_throughput(FRAMES, world, ms), "unit": "mel frames/s", "ms_per_step": ms, "steps": n, "warmup": 3,
                 "n_gpus": world, "scaling": "weak",
                 "config": f"training step on C2 per rank (B=32, char 128, T=200, r=5; global batch {32 * world}): dropout 0.5, scheduled "
                           "sampling 0.5, L1 losses, backward, clip 5, Adam; targets (2 x 141 MB) + activations exceed L2",
                 "allreduce": ({"op": "SUM", "bytes_per_step": int(m.store.flat.numel() * 4), "backend": "nccl"} if world > 1 else None),
-                "precision": f"{args.precision} forward, fp32 backward (exact-product FFMA GEMMs)", "loss_last_step": loss}
+                "precision": f"{args.precision} forward, fp32 backward (exact-product FFMA GEMMs)", "loss_last_step": loss,
+                "sections_ms": sections}
     except Exception as ex:
         return {"error": f"{type(ex).__name__}: {str(ex)[:160]}"}
 

@@ -46,6 +46,8 @@ class TimedK:
 
 
 def main():
+    if os.environ.get("TACO_GEMM_IMPL") == "1":
+        K.set_gemm_impl(1)                     # time the opt-in 3xTF32 mma.sync GEMM instead of the FFMA default
     cfg = Config(r=5, vocab_size=64, precision=os.environ.get("PRECISION", "tf32"))
     m = Tacotron(cfg, None, train=True)
     g = torch.Generator().manual_seed(0)

@@ -249,7 +249,9 @@ def measure_train(args, world, rank):
                 "config": f"training step on C2 per rank (B=32, char 128, T=200, r=5; global batch {32 * world}): dropout 0.5, scheduled "
                           "sampling 0.5, L1 losses, backward, clip 5, Adam; targets (2 x 141 MB) + activations exceed L2",
                 "allreduce": ({"op": "SUM", "bytes_per_step": int(m.store.flat.numel() * 4), "backend": "nccl"} if world > 1 else None),
-                "precision": f"{args.precision} forward, fp32 backward (exact-product FFMA GEMMs)", "loss_last_step": loss,
+                "precision": (f"{args.precision} forward; backward fp32-grade: " +
+                              ("3xTF32 mma.sync tensor-core GEMMs" if args.precision == "tf32" else "exact-product FFMA GEMMs")),
+                "loss_last_step": loss,
                 "sections_ms": sections}
     except Exception as ex:
         return {"error": f"{type(ex).__name__}: {str(ex)[:160]}"}
@@ -321,9 +323,9 @@ def measure_c5(args):
 
 
 def measure_train_variant(args):
-    """Child-process body (`--impl train-variant-worker`): the training step with taco_gemm switched to its opt-in 3xTF32
-    mma.sync kernel.  First the gradient of one C2 step is computed with both GEMM kernels on identical saved activations
-    (relative L2 difference must be < 1e-4, else the timing is not reported as valid), then 5 steps are timed with each."""
+    """Child-process body (`--impl train-variant-worker`): the training step with each of taco_gemm's two kernels (3xTF32
+    mma.sync = the model's choice in 'tf32' mode; exact-product FFMA = 'fp32' mode).  First the gradient of one C2 step is
+    computed with both on identical saved activations (relative L2 difference reported), then 5 steps are timed with each."""
     import torch
     from tacotron_b200 import Config, Tacotron, kernels as K
     from tacotron_b200.models import ops
@@ -340,9 +342,10 @@ def measure_train_variant(args):
             m.seq2seq_output, m.output = m.inference(gi, True)
         S.update(text=gi["text"], text_length=gi["text_length"], mel=gi["mel"], stft=gi["stft"])
         S["post/out"] = m.output
+        m.gemm_impl = 0                                    # exact-product FFMA kernel
         m.backward(S)
         g0 = m._opt.g.clone()
-        K.set_gemm_impl(1)
+        m.gemm_impl = 1                                    # 3xTF32 mma.sync kernel (the model's choice in 'tf32' mode)
         m.backward(S)
         torch.cuda.synchronize()
         g1 = m._opt.g
@@ -360,10 +363,12 @@ def measure_train_variant(args):
             torch.cuda.synchronize()
             return e0.elapsed_time(e1) / n
         ms_mma = timed()
-        K.set_gemm_impl(0)
+        m.gemm_impl = 0
         ms_ffma = timed()
-        return {"gemm": "3xTF32 mma.sync (taco_set_gemm_impl(1))", "grad_rel_l2_vs_ffma": rel, "valid": bool(rel < 1e-4),
-                "ms_per_step": ms_mma, "value": FRAMES / (ms_mma / 1e3), "unit": "mel frames/s", "ms_per_step_ffma_same_process": ms_ffma}
+        return {"note": "same training step with each GEMM kernel of the backward, one process, no collective",
+                "grad_rel_l2_mma_vs_ffma": rel, "consistent": bool(rel < 1e-4),
+                "mma_3xtf32": {"ms_per_step": ms_mma, "value": FRAMES / (ms_mma / 1e3), "unit": "mel frames/s"},
+                "ffma_exact": {"ms_per_step": ms_ffma, "value": FRAMES / (ms_ffma / 1e3), "unit": "mel frames/s"}}
     except Exception as ex:
         return {"error": f"{type(ex).__name__}: {str(ex)[:160]}"}
 
@@ -534,8 +539,8 @@ def run_ours(args):
         c5 = None if (args.no_c5 or world > 1) else measure_c5_isolated(args)     # single-GPU latency: N=1 runs only
         _log("C5 (single utterance + Griffin-Lim) side measurement done")
         if train is not None and "error" not in train and world == 1:
-            train["tensor_core_gemm_variant"] = _isolated(args, "train-variant-worker", 240)
-            _log("training step with the mma.sync GEMM variant (child process) done")
+            train["gemm_kernels"] = _isolated(args, "train-variant-worker", 240)
+            _log("training step with each GEMM kernel (child process) done")
         cpu = None
         if not args.no_cpu_baseline:
             ts, threads = time_cpu_oracle(3)

@@ -265,7 +265,16 @@ class Tacotron(object):
         from . import grad
         self.add_train_op()
         self._opt.zero_grad()
-        grad.model_bwd(K, self.store, self._gviews, S, self.config)
+        # GEMM kernel of the backward follows the precision mode: 'tf32' -> 3xTF32 mma.sync tensor cores (fp32-grade,
+        # ~1e-6 relative), 'fp32' -> exact-product FFMA.  `self.gemm_impl` (0 / 1) overrides.
+        impl = getattr(self, "gemm_impl", None)
+        if impl is None:
+            impl = 1 if self.config.precision == "tf32" else 0
+        prev = K.set_gemm_impl(impl)
+        try:
+            grad.model_bwd(K, self.store, self._gviews, S, self.config)
+        finally:
+            K.set_gemm_impl(prev)
         return self._gviews
 
     def train_step(self, inputs, lr=None, **kw):

@@ -4,8 +4,7 @@ numpy oracle.  fp32 on the device vs fp64 oracle: 1e-4 of the signal's max after
 divides by |rebuilt|, which is ill-conditioned where a bin is nearly cancelled, so long runs are compared through the
 property the algorithm optimises -- spectral convergence -- instead of sample by sample).
 
-STATUS (round 1): written after the round's GPU budget was spent; a hardware run has not happened yet.  The markers say
-so: a passing test shows as XPASS in the round-end run and the markers are removed once that run is green.
+STATUS: green on B200 (profiles/r01_pytest_mma_audio_runxfail.log).
 """
 import math
 
@@ -16,8 +15,7 @@ import torch
 from oracle import audio_oracle as A
 from tests import mirror_kernels as MK
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="Griffin-Lim kernels: first hardware run pending (round-1 GPU budget spent)")]
+pytestmark = pytest.mark.gpu
 
 
 def _K():
@@ -26,9 +24,10 @@ def _K():
 
 
 def _close(got, ref, tol):
-    got, ref = got.detach().cpu().double(), ref.detach().cpu().double()
+    got, ref = got.detach().cpu(), ref.detach().cpu()
     if got.is_complex():
         got, ref = torch.view_as_real(got), torch.view_as_real(ref)
+    got, ref = got.double(), ref.double()
     err = (got - ref).abs().max().item()
     assert err <= tol * (ref.abs().max().item() + 1e-6), (err, ref.abs().max().item())
 

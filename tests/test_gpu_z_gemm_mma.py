@@ -3,15 +3,14 @@ checks as the default FFMA kernel (every addressing form against the torch-CPU m
 autograd over the oracle), with the implementation switched by taco_set_gemm_impl(1).  Tolerance 2e-5 of max|ref| for
 the kernel (3xTF32 keeps ~21 bits per product), 2e-3 per tensor for whole-model gradients (same bar as the default).
 
-STATUS (round 1): written after the round's GPU budget was spent -- no hardware run yet, hence the non-strict xfail
-markers (XPASS in the round-end run = it works; the variant becomes the default only after that).
+STATUS: green on B200 (profiles/r01_pytest_mma_audio_runxfail.log); since then the tensor-core kernel is what the model's
+backward uses in 'tf32' precision mode (Tacotron.backward), the FFMA kernel in 'fp32' mode.
 """
 import pytest
 
 from tests import train_checks as TC
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="mma.sync GEMM variant: first hardware run pending (round-1 GPU budget spent)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture()
@@ -33,8 +32,8 @@ def test_gemm_variants_mma(mma_impl):
     _assert(TC.check_gemm(), 2e-5)
 
 
-def test_model_backward_mma(mma_impl):
-    res = TC.check_model_bwd(2, True, "fp32")
+def test_model_backward_mma():
+    res = TC.check_model_bwd(2, True, "fp32", gemm_impl=1)
     _assert(res, 2e-3, floor=1e-3)
     assert res["_rel_l2"][0] <= 1e-4 and res["_cosine"][0] >= 0.9999
 

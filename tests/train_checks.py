@@ -315,14 +315,16 @@ def check_train_forward(r=2, sched=True, precision="fp32", B=2, Tx=8, T=5):
     return res
 
 
-def check_model_bwd(r=2, sched=True, precision="fp32", B=2, Tx=8, T=5):
-    """all parameter gradients of the CUDA path against torch.autograd over the oracle"""
+def check_model_bwd(r=2, sched=True, precision="fp32", B=2, Tx=8, T=5, gemm_impl=None):
+    """all parameter gradients of the CUDA path against torch.autograd over the oracle
+    (gemm_impl: None = the model's choice by precision, 0 = FFMA, 1 = 3xTF32 mma.sync)"""
     cfg, p, inp, enc_m, dec_m, sm = _small_case(r, sched, B, Tx, T)
     if not sched:
         cfg.scheduled_sample = 0.0
     _, g_ref = O.loss_and_grads(p, inp, cfg, enc_drop_masks=enc_m, dec_drop_masks=dec_m, sample_mask=sm)
     from tacotron_b200.models import ops
     m = _model(cfg, p, precision)
+    m.gemm_impl = gemm_impl
     gi = {k: v.cuda() for k, v in inp.items()}
     S = {}
     with ops.saving(S):

@@ -3,8 +3,8 @@ restatement of the reference's in-place statements, the double-buffered device b
 (tacotron_b200/train.py, test.py) end to end on a tiny synthetic data set: train a few steps, checkpoint, resume,
 synthesise from prompts, invert with the GPU Griffin-Lim.
 
-STATUS (round 1): written after the round's GPU budget was spent; no hardware run yet.  Non-strict xfail markers say
-so: passing tests show as XPASS in the round-end run, and the markers go once that run is green.
+STATUS (round 1): the normalisation kernel and the device batch iterator are green on B200; the driver test is the one
+piece without a hardware run (non-strict xfail: XPASS in the round-end run = it works).
 """
 import os
 import pickle
@@ -15,8 +15,10 @@ import torch
 
 from oracle import data_oracle as DO
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="data path / drivers: first hardware run pending (round-1 GPU budget spent)")]
+pytestmark = pytest.mark.gpu
+# the kernel and the batch iterator are green on B200 (profiles/r01_pytest_data_runxfail.log); the end-to-end driver test has
+# not had a hardware run yet (the round's GPU budget ended there): non-strict xfail until it has
+pending = pytest.mark.xfail(strict=False, reason="drivers end to end: first hardware run pending (round-1 GPU budget spent)")
 
 
 def _dataset(root, N=40, Tx=12, T=8, r=2, seed=0):
@@ -61,6 +63,7 @@ def test_device_batches_bit_exact(tmp_path):
             assert np.array_equal(b["stft"][k].cpu().numpy(), DO.normalize_explicit(np.asarray(arrays["stft"][j]), stft_mean, stft_std))
 
 
+@pending
 def test_drivers_train_checkpoint_resume_synthesise(tmp_path, monkeypatch):
     from tacotron_b200 import checkpoint, test as synth, train as trainer
     from tacotron_b200.models.tacotron import Config, Tacotron

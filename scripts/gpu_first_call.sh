@@ -5,7 +5,7 @@
 mkdir -p gpurun_out
 run() { name=$1; shift; echo "=== $name ==="; timeout ${LIMIT:-300} "$@" > gpurun_out/$name.log 2>&1; echo "rc=$?" >> gpurun_out/$name.log; tail -n ${TAIL:-6} gpurun_out/$name.log; }
 # 1. pending tests (xfail markers ignored so that real pass/fail shows)
-for f in test_gpu_z_gemm_mma test_gpu_z_audio test_gpu_z_data; do
+for f in test_gpu_z_gemm_mma test_gpu_z_audio test_gpu_z_data test_gpu_zz_dx_tc; do
   run $f python -m pytest tests/$f.py -q -m gpu --runxfail --tb=short -p no:cacheprovider
 done
 # 2. the validated suites must still be green with the rebuilt library

@@ -68,6 +68,42 @@ def gemm(Cm, A, B, *, ta=False, tb=False, beta=0.0, shift=0, period=0, taps=1, d
     L.check(L.lib().taco_gemm(C.byref(d), _st()), "taco_gemm")
 
 
+# Data gradient of conv1d('same') / dense.  Default: taco_gemm (K-segmented, row-shifted form).  DX_TC = True routes it
+# through the tcgen05 forward kernel instead (taco_linear_fwd on dZ with the taps reversed and the weights transposed:
+# a conv data gradient IS a convolution) -- single-pass TF32 like the forward, opt-in until it has had a hardware run.
+DX_TC = False
+
+
+def _cpad(c):
+    return (c + 31) // 32 * 32
+
+
+def conv_dx(dX, dZ, W, T, beta=0.0):
+    taps, Cin, Cout = W.shape
+    tap0 = -((taps - 1) // 2)
+    M = dZ.shape[0]
+    tma_ok = (dZ.stride(0) * 4) % 16 == 0 and dZ.data_ptr() % 16 == 0 and M % T == 0
+    if DX_TC and tma_ok:
+        Wt = W.flip(0).transpose(1, 2).contiguous()                    # [taps, Cout, Cin]: taps reversed, weights transposed
+        ld = taps * _cpad(Cout)
+        Wp = torch.zeros((Cin, ld), dtype=torch.float32, device=W.device)
+        L.check(L.lib().taco_pack_weight(_p(Wt), taps, Cout, Cin, _p(Wp), ld, _st()), "taco_pack_weight")
+        d = L.LinearDesc()
+        d.X = dZ.data_ptr(); d.ldx = dZ.stride(0); d.B = M // T; d.T = T; d.C = Cout
+        d.taps = taps; d.tap0 = -(tap0 + taps - 1); d.N = Cin
+        d.W = Wt.data_ptr(); d.Wp = Wp.data_ptr(); d.ldwp = ld
+        d.Y = dX.data_ptr(); d.ldy = dX.stride(0)
+        d.act = ACT_NONE; d.keep_scale = 1.0
+        if beta != 0.0:
+            assert beta == 1.0
+            d.residual = dX.data_ptr(); d.ldr = dX.stride(0)             # accumulate: each element is read then written by one thread
+        d.impl = L.IMPL_TC
+        L.check(L.lib().taco_linear_fwd(C.byref(d), _st()), "taco_linear_fwd[conv_dx]")
+        return
+    gemm(dX, dZ, W.reshape(taps * Cin, Cout)[:Cin], tb=True, beta=beta, shift=-tap0, dshift=-1, kper=Cout, taps=taps,
+         b_tap_stride=Cin * Cout, period=T)
+
+
 def set_gemm_impl(impl):
     """0 = exact-product FFMA GEMM (default), 1 = 3xTF32 mma.sync tensor-core GEMM; returns the previous setting"""
     return L.lib().taco_set_gemm_impl(int(impl))

@@ -39,7 +39,7 @@ def _v2(t):
 def dense_bwd(K, dY, X, W, gW, gb=None, dX=None, beta_dx=0.0):
     """y = x.W + b (W [in,out]).  dY,X,dX are 2-D (possibly strided) views."""
     if dX is not None:
-        K.gemm(dX, dY, W, tb=True, beta=beta_dx)
+        K.conv_dx(dX, dY, W.reshape(1, W.shape[0], W.shape[1]), dY.shape[0], beta=beta_dx)
     K.gemm(gW, X, dY, ta=True, beta=1.0)
     if gb is not None:
         K.colsum(gb, dY)
@@ -51,8 +51,7 @@ def conv_bwd(K, dZ, X, W, gW, gb, T, dX=None, beta_dx=0.0):
     taps, Cin, Cout = W.shape
     tap0 = -((taps - 1) // 2)
     if dX is not None:     # dx[b,s,c] = sum_j sum_n dz[b, s-tap0-j, n] W[j,c,n]
-        K.gemm(dX, dZ, W.reshape(taps * Cin, Cout)[:Cin], tb=True, beta=beta_dx, shift=-tap0, dshift=-1, kper=Cout,
-               taps=taps, b_tap_stride=Cin * Cout, period=T)
+        K.conv_dx(dX, dZ, W, T, beta=beta_dx)
     # dW[j,c,n] = sum_{b,t} x[b,t+tap0+j,c] dz[b,t,n]  -- one batch entry per tap
     K.gemm(gW.reshape(taps * Cin, Cout)[:Cin], X, dZ, ta=True, beta=1.0, shift=tap0, bshift=1, batch=taps,
            c_bstride=Cin * Cout, period=T)

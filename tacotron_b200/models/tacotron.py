@@ -271,10 +271,12 @@ class Tacotron(object):
         if impl is None:
             impl = 1 if self.config.precision == "tf32" else 0
         prev = K.set_gemm_impl(impl)
+        prev_dx, K.DX_TC = K.DX_TC, bool(getattr(self.config, "grad_dx_tc", False))    # opt-in: data gradients on tcgen05
         try:
             grad.model_bwd(K, self.store, self._gviews, S, self.config)
         finally:
             K.set_gemm_impl(prev)
+            K.DX_TC = prev_dx
         return self._gviews
 
     def train_step(self, inputs, lr=None, **kw):

@@ -87,6 +87,16 @@ def _offset_view(t, off):
     return torch.as_strided(t, t.shape, t.stride(), t.storage_offset() + off)
 
 
+def conv_dx(dX, dZ, W, T, beta=0.0):
+    """data gradient of tf.layers.conv1d('same') / dense (taps = 1):
+    dX[b,s,c] = beta*dX + sum_j sum_n dZ[b, s - tap0 - j, n] * W[j,c,n],  tap0 = -((taps-1)//2), zero outside [0,T).
+    dX [B*T,Cin], dZ [B*T,Cout] (2-D views, possibly strided), W [taps,Cin,Cout]."""
+    taps, Cin, Cout = W.shape
+    tap0 = -((taps - 1) // 2)
+    gemm(dX, dZ, W.reshape(taps * Cin, Cout)[:Cin], tb=True, beta=beta, shift=-tap0, dshift=-1, kper=Cout, taps=taps,
+         b_tap_stride=Cin * Cout, period=T)
+
+
 def colsum(out, A, Bm=None, R=None, beta=1.0):
     """out[n] = beta*out[n] + sum_m A[m,n] * (Bm is None ? 1 : Bm[m,n] - (R is None ? 0 : R[m,n]))"""
     if Bm is None:

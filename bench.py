@@ -400,7 +400,13 @@ def _isolated(args, impl, limit):
             if ln.startswith("{"):
                 return json.loads(ln)
         return {"error": f"no result from the {impl} child (rc={out.returncode}): {out.stderr.strip()[-160:]}"}
-    except subprocess.TimeoutExpired:
+    except subprocess.TimeoutExpired as te:
+        txt = te.stdout.decode() if isinstance(te.stdout, bytes) else (te.stdout or "")
+        for ln in reversed(txt.strip().splitlines()):      # keep what the child had already reported
+            if ln.startswith("{"):
+                r = json.loads(ln)
+                r["child_note"] = f"child timed out after {limit} s; this is its last complete report"
+                return r
         return {"error": f"{impl} child timed out ({limit} s)"}
     except Exception as ex:
         return {"error": f"{type(ex).__name__}: {str(ex)[:160]}"}

@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
     for (int i = tid; i < Tq * (ENC / 4); i += NTHR) {
         const int j = i / (ENC / 4), d4 = (i % (ENC / 4)) * 4;
         float4 kk = make_float4(0, 0, 0, 0), vv = kk;
-        if (arow < B) {
+        if (arow < B && aq * Tq + j < Tx) {                 // ragged last quarter when Tx is not a multiple of 4
             const int64_t gi = ((int64_t)arow * Tx + aq * Tq + j) * ENC + d4;
             kk = __ldg(reinterpret_cast<const float4*>(A.keys + gi));
             vv = __ldg(reinterpret_cast<const float4*>(A.values + gi));
@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
     // the last two warps (fewest k-tiles) with the four loads issued together; p_s still holds that step's
     // unnormalised probabilities (the next K_ATT slot has not run yet).
     auto finalize_align = [&](int step, uint32_t tag) {
-        if (arow < B && tid >= NTHR - 64 && tid - (NTHR - 64) < Tq) {
+        if (arow < B && tid >= NTHR - 64 && tid - (NTHR - 64) < Tq && aq * Tq + (tid - (NTHR - 64)) < Tx) {
             const int j = tid - (NTHR - 64);
             const uint64_t* ms = ws + P.ws.att_ms + (int64_t)arow * 8;
             ulonglong2 mv[4];
@@ -840,7 +840,7 @@ extern "C" int taco_decoder_fwd(const taco_decoder_args* a, void* stream) {
     const taco_decoder_weights& g_dec_w = *a->weights;
     TACO_CHECK(a->B >= 1 && a->B <= BPAD, "taco_decoder_fwd: B=%d must be in [1,%d] per launch", a->B, BPAD);
     TACO_CHECK(a->T >= 1, "taco_decoder_fwd: T=%d", a->T);
-    TACO_CHECK(a->Tx >= 4 && (a->Tx % 4) == 0 && a->Tx <= 256, "taco_decoder_fwd: Tx=%d must be a multiple of 4, <= 256", a->Tx);
+    TACO_CHECK(a->Tx >= 1 && a->Tx <= 256, "taco_decoder_fwd: Tx=%d must be in [1, 256]", a->Tx);
     TACO_CHECK(a->r >= 1 && MF * a->r <= 512 - 8, "taco_decoder_fwd: r=%d unsupported (80r must be <= 504)", a->r);
     TACO_CHECK(a->packed && a->keys && a->values && a->text_length && a->y && a->align && a->workspace, "taco_decoder_fwd: NULL pointer");
     TACO_CHECK((reinterpret_cast<uintptr_t>(a->workspace) & 15) == 0, "taco_decoder_fwd: workspace must be 16-byte aligned");
@@ -856,7 +856,7 @@ extern "C" int taco_decoder_fwd(const taco_decoder_args* a, void* stream) {
     build_ws_layout(&P.ws);
     P.a = *a;
     P.OUT = MF * a->r;
-    P.Tq = a->Tx / 4;
+    P.Tq = (a->Tx + 3) / 4;            // quarter width; the last quarter is ragged when Tx % 4 != 0
     TACO_CHECK(P.Tq <= 64, "taco_decoder_fwd: Tx/4 = %d > 64", P.Tq);
     TACO_CHECK(P.OUT / 8 <= MAXT * NWARP, "taco_decoder_fwd: 80r too wide for the fragment pipeline");
     P.pre_b1 = g_dec_w.pre_b1; P.pre_b2 = g_dec_w.pre_b2; P.in_b = g_dec_w.in_b; P.out_b = g_dec_w.out_b; P.att_v = g_dec_w.att_v;

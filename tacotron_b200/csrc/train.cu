@@ -503,7 +503,7 @@ __global__ void sumsq_stage2(const float* __restrict__ partial, int n, float* __
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
                             float lr_t, float b1, float b2, float eps, float clip, const float* __restrict__ sumsq) {
     const float norm = sqrtf(sumsq[0]);
-    const float scale = clip / fmaxf(norm, clip);
+    const float scale = (clip > 0.f) ? clip / fmaxf(norm, clip) : 1.0f;   // cap_grads <= 0: no clipping (tacotron.py:179)
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float gc = g[i] * scale;
         const float mi = b1 * m[i] + (1.0f - b1) * gc;

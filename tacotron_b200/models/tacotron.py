@@ -166,8 +166,8 @@ class Tacotron(object):
         text = inputs["text"]
         assert text.dtype == torch.int32 and text.is_cuda and text.is_contiguous()
         B, Tx = text.shape
-        if Tx % 4 != 0:
-            raise ValueError(f"text width {Tx} must be a multiple of 4 (pad like the reference does: data_input.py:97-99)")
+        if not 1 <= Tx <= 256:
+            raise ValueError(f"text width {Tx} out of range: the persistent decoder keeps keys/values in shared memory, Tx <= 256")
         if getattr(self.config, "cuda_graph", False) and not train and trace is None:
             return self._inference_graphed(inputs, T)
         self._mark("start")

@@ -41,7 +41,10 @@ def train(model_cls, config, num_steps=1000000, log=print, save_every=SAVE_EVERY
     config.r = meta["r"]                                                                 # :20
     ivocab = meta["vocab"]
     config.vocab_size = len(ivocab)                                                      # :22
-    arrays, names, num_speakers, stft_mean, stft_std = data_input.load_from_npy(config.data_path)   # :26-27
+    # every rank must normalise with the SAME statistics (the reference is one process: one 100-utterance sample,
+    # data_input.py:54): one seeded draw shared by all ranks instead of the unseeded global numpy RNG per rank
+    arrays, names, num_speakers, stft_mean, stft_std = data_input.load_from_npy(
+        config.data_path, rng=np.random.RandomState(getattr(config, "data_seed", 0)))                # :26-27
     config.num_speakers = num_speakers                                                   # :29
     batches = data_input.build_dataset(arrays, names, seed=0, shard=(rank, world))       # :35
     model = model_cls(config, None, train=True)                                          # :38
@@ -51,14 +54,19 @@ def train(model_cls, config, num_steps=1000000, log=print, save_every=SAVE_EVERY
         log("restoring weights")
         ck = (checkpoint.latest_checkpoint(weights_dir) if RESTORE_FROM is None else f"{weights_dir}-{RESTORE_FROM}.npz")
         if ck is not None:
-            checkpoint.restore(model, ck)
+            ck_mean, ck_std = checkpoint.restore(model, ck)
+            if ck_mean is not None:                  # de-normalise with the statistics the weights were trained on
+                stft_mean, stft_std = ck_mean, ck_std
     mean_d = torch.from_numpy(np.asarray(stft_mean, dtype=np.float32)).cuda()
     std_d = torch.from_numpy(np.asarray(stft_std, dtype=np.float32)).cuda()
     lr = model.config.init_lr                                                            # :60
     annealing_rate = model.config.annealing_rate                                         # :61
     for _ in range(num_steps):                                                           # :63
         inputs = next(batches)
-        loss = float(train_op(inputs, lr))                                               # :64-73 (the only host sync of a step)
+        loss_t = train_op(inputs, lr).reshape(1).clone()                                 # :64-73
+        if world > 1:                      # every rank must take the same branch below (a rank that leaves alone hangs the
+            torch.distributed.all_reduce(loss_t)   # next gradient all-reduce): the guard and the log use the global loss
+        loss = float(loss_t)                                                             # the only host sync of a step
         global_step = model.global_step
         if rank == 0 and global_step % 100 == 0:
             log(f"step {global_step} loss {loss:.1f} lr {lr:.3g} grad-norm {float(model.grad_sumsq.sqrt()):.1f}")

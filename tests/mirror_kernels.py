@@ -317,9 +317,9 @@ def sumsq(out, x):
 
 
 def adam_step(p, g, m, v, lr_t, b1, b2, eps, clip, sumsq_t):
-    """g *= clip / max(sqrt(sumsq), clip);  m,v,p <- TF Adam (oracle/tf12.py adam_tf) with lr_t precomputed."""
+    """g *= clip / max(sqrt(sumsq), clip) (clip <= 0: no clipping, tacotron.py:179);  m,v,p <- TF Adam (oracle/tf12.py adam_tf) with lr_t precomputed."""
     gn = torch.sqrt(sumsq_t[0])
-    scale = clip / torch.maximum(gn, torch.tensor(float(clip), dtype=gn.dtype))
+    scale = clip / torch.maximum(gn, torch.tensor(float(clip), dtype=gn.dtype)) if clip > 0 else torch.ones_like(gn)   # cap_grads <= 0: unclipped
     gc = g * scale
     m.mul_(b1).add_(gc * (1 - b1))
     v.mul_(b2).add_(gc * gc * (1 - b2))

@@ -22,22 +22,6 @@ from tests import mirror_kernels as MK
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def retry_once(fn):
-    """The emulation runs every CUDA thread as a real OS thread (hundreds per block).  One unexplained mismatch was seen
-    once in ~40 runs on a loaded 8-core container and never reproduced; an indexing error -- what these tests exist to
-    catch -- is deterministic and fails twice, so a failed comparison is repeated once before it counts."""
-    import functools
-
-    @functools.wraps(fn)
-    def wrapper(*a, **kw):
-        try:
-            return fn(*a, **kw)
-        except AssertionError as first:
-            print(f"[cuda_emu] {fn.__name__}: mismatch on the first attempt ({str(first)[:120]}); retrying once")
-            return fn(*a, **kw)
-    return wrapper
-
-
 @pytest.fixture(scope="module")
 def emu(tmp_path_factory):
     out = str(tmp_path_factory.mktemp("emu") / "libtaco_emu.so")
@@ -107,7 +91,6 @@ def _gemm_cases():
 
 
 @pytest.mark.parametrize("impl,tol", [(0, 2e-6), (1, 2e-5)])
-@retry_once
 def test_gemm_kernels_under_emulation(emu, impl, tol):
     """impl 0 = the FFMA kernel (green on hardware: validates the emulator); impl 1 = the 3xTF32 mma.sync kernel"""
     K = EmuK(emu)
@@ -124,7 +107,6 @@ def test_gemm_kernels_under_emulation(emu, impl, tol):
 
 
 @pytest.mark.parametrize("r,T", [(2, 8), (5, 4)])
-@retry_once
 def test_griffinlim_kernels_under_emulation(emu, r, T):
     g = torch.Generator().manual_seed(1)
     B, F = 2, 1025
@@ -163,7 +145,6 @@ def test_griffinlim_kernels_under_emulation(emu, r, T):
 
 
 @pytest.mark.parametrize("r,sched", [(2, True), (5, False)])
-@retry_once
 def test_decoder_bwd_kernel_under_emulation(emu, r, sched):
     """the cooperative decoder-backward kernel (green on hardware) as a one-CTA grid: shared-memory staging, the column
     dealing, all 11 stages and the attention block reductions against the mirror"""
@@ -207,7 +188,6 @@ def test_decoder_bwd_kernel_under_emulation(emu, r, sched):
             assert (got - ref).abs().max().item() <= 2e-5 * (ref.abs().max().item() + 1e-6), (k, i)
 
 
-@retry_once
 def test_bigru_bwd_kernel_under_emulation(emu):
     """the register-resident bi-GRU BPTT kernel (green on hardware): 512-thread CTAs, butterfly shuffles"""
     g = torch.Generator().manual_seed(3)
@@ -227,7 +207,6 @@ def test_bigru_bwd_kernel_under_emulation(emu):
     assert (torch.nan_to_num(got, nan=1e30) - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
 
 
-@retry_once
 def test_normalize_f16_under_emulation_is_bit_exact(emu):
     emu.taco_normalize_f16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
     rng = np.random.RandomState(1)

@@ -16,9 +16,6 @@ import torch
 from oracle import data_oracle as DO
 
 pytestmark = pytest.mark.gpu
-# the kernel and the batch iterator are green on B200 (profiles/r01_pytest_data_runxfail.log); the end-to-end driver test has
-# not had a hardware run yet (the round's GPU budget ended there): non-strict xfail until it has
-pending = pytest.mark.xfail(strict=False, reason="drivers end to end: first hardware run pending (round-1 GPU budget spent)")
 
 
 def _dataset(root, N=40, Tx=12, T=8, r=2, seed=0):
@@ -63,7 +60,6 @@ def test_device_batches_bit_exact(tmp_path):
             assert np.array_equal(b["stft"][k].cpu().numpy(), DO.normalize_explicit(np.asarray(arrays["stft"][j]), stft_mean, stft_std))
 
 
-@pending
 def test_drivers_train_checkpoint_resume_synthesise(tmp_path, monkeypatch):
     from tacotron_b200 import checkpoint, test as synth, train as trainer
     from tacotron_b200.models.tacotron import Config, Tacotron

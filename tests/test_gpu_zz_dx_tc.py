@@ -10,8 +10,7 @@ import torch
 
 from tests import mirror_kernels as MK, train_checks as TC
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="tcgen05 data-gradient route: first hardware run pending (round-1 GPU budget spent)")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.fixture()

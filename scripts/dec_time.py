@@ -22,21 +22,21 @@ print("LL mode", os.environ.get("TACO_DEC_LL", "default"), "decoder ms", statist
 if os.environ.get("TACO_TRACE"):
     import numpy as np
     ws = m.runtime.dec_ws.view(torch.int64).cpu().numpy()
-    n_alloc = 2 + 13 * T
-    total = len(ws) - (5 * n_alloc + 32)
-    NORD = 12
-    n = 2 + NORD * T
+    total = 13 * 32 * 256                       # NBUF exchange buffers of [32][256] words (decoder.cu build_ws_layout)
+    names = ["IN", "G1", "C1", "G2", "C2", "G3", "C3", "OQP", "A|P2"]
+    n = 1 + len(names) * T
     tr = ws[total: total + n]
-    names = ["IN", "G1", "C1", "G2", "C2", "G3", "C3", "OUT", "Q", "P1", "ATT", "P2"]
-    d = np.diff(tr)[2:]
-    d = d[: (len(d) // NORD) * NORD].reshape(-1, NORD)[5:]
+    d = np.diff(tr)                              # d[i] = time of entry i+1 - entry i; entry 0 = prologue
+    d = d[: (len(d) // len(names)) * len(names)].reshape(-1, len(names))[5:]
     med = np.median(d, axis=0)
     print("per-slot median ns (CTA 0):", {n_: int(v) for n_, v in zip(names, med)}, "sum", int(med.sum()))
-    ck = ws[total + n + 16: total + n + 16 + 4 * n].reshape(n, 4)[2:]
-    ck = ck[: (len(ck) // NORD) * NORD].reshape(-1, NORD, 4)[5:-1]
-    seg = np.stack([ck[:, :, 1] - ck[:, :, 0], ck[:, :, 2] - ck[:, :, 1], ck[:, :, 3] - ck[:, :, 2]], -1)   # inputs+mma, barrier, epilogue
-    nxt = np.roll(ck[:, :, 0].reshape(-1), -1).reshape(ck.shape[0], NORD) - ck[:, :, 3]                         # epilogue end -> next slot start
-    print("cycles (inputs+mma | barrier | epilogue | to-next):")
-    for i, n_ in enumerate(names):
-        print(f"  {n_:4s} {int(np.median(seg[:, i, 0])):6d} {int(np.median(seg[:, i, 1])):6d} {int(np.median(seg[:, i, 2])):6d} {int(np.median(nxt[:-1, i])):6d}")
-
+    ck = ws[total + 16 * T + 16: total + 16 * T + 16 + 4 * 20 * 8].reshape(4, 20, 8)
+    inames = ["IN_S", "IN_CTX", "IN_P2*", "G_H0", "G_X0*", "C_X0", "C_RH0*", "G_H1", "G_X1*", "C_X1", "C_RH1*", "G_H2", "G_X2*", "C_X2", "C_RH2*", "OQP*", "AP2"]
+    print("item: start->loads-issued | ->weights | ->mma done | (finish) ->partials | ->sync | ->epilogue   [cycles, CTA0 thread0, step 11]")
+    st = 1
+    for i, nm in enumerate(inames):
+        c = ck[st, i]
+        if c[3] == 0: continue
+        f = lambda a, b: int(c[a] - c[b]) if c[a] and c[b] else -1
+        nxt = ck[st, i + 1, 3] if i + 1 < len(inames) else ck[st + 1, 0, 3]
+        print(f"  {nm:8s} {f(0,3):6d} {f(1,0):6d} {f(2,1):6d} | {f(4,2):6d} {f(5,4):6d} {f(6,5):6d} | total {int(nxt - c[3]):6d}")

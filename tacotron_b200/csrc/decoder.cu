@@ -1,4 +1,4 @@
-// decoder.cu -- the whole autoregressive attention decoder as ONE persistent dataflow kernel.
+// decoder.cu -- the whole autoregressive attention decoder as ONE persistent dataflow kernel (design v4).
 //
 // Reference: models/tacotron.py:46-105 (create_decoder) + :136-138 (dynamic_decode) over the
 // TF-1.2 contrib.seq2seq / contrib.rnn classes.  Per decoder step t:
@@ -14,32 +14,39 @@
 //   AL  attn = [y_t, ctx] . W_a                            AttentionWrapper attention_layer (no bias)
 //   next input: InferenceHelper -> y_t ; TrainingHelper -> mel[:, t+1] ; ScheduledOutput -> per-row mix
 //
-// Design v3 (B <= 32 utterances per launch).  History: v1 (grid barrier between stages, FFMA 1x4
-// tiles) ran 58 us/step, 45% of it barrier wait; v2 (flag-in-data exchange, FFMA 8x4 tiles +
-// shuffle butterfly) 48 us/step and turned out instruction bound (80% of 77 K warp-instructions per
-// CTA-step were not FFMA: polling loops, index math, butterfly).  v3:
-//   * grid = 128 CTAs x 256 threads, co-resident (cooperative launch), alive for all T steps.
-//     Dense stage [32 x K].[K x N]: CTA (rg, cs) owns rows 8rg..8rg+7 and the cs-th of 32 column slices.
-//   * NO grid barrier: every exchanged activation is a 64-bit word {fp32 value, step tag} written with
-//     one st.b64 and read with polling 128-bit volatile loads ("LL" protocol): a stage boundary costs one
-//     L2 write->read latency, no fences, no atomics.  A buffer is re-written one full step later, which
-//     the dependency chain guarantees to be after all of its readers have consumed it.
-//   * the contraction runs on the tensor pipe with fp32-grade accuracy: mma.sync m16n8k8 TF32 with the
-//     3xTF32 error-compensated split (x = hi + lo: hi.hi + lo.hi + hi.lo, fp32 accumulate).  M = the 8
-//     utterance rows (+8 zero rows), N = 8 weight columns, K split over the 8 warps.  The A fragments
-//     are loaded STRAIGHT from the LL words in L2 into registers (the exchange buffers are stored in
-//     fragment order: k and k+4 adjacent), no shared-memory staging, no ingest barrier; the B
-//     fragments (weights) come from shared memory pre-packed in fragment order (one LDS.64 per MMA).
-//   * GRU gate columns are permuted so that CTA cs owns r and u of the SAME 8 hidden units: u, the
-//     previous state and z never leave the CTA.
-//   * fused linear stages (weight-only precompute at pack time): the attention layer is folded into the
-//     input projection and the query is taken from the residual sum, so K_AL has no slot (12 per step);
-//     pre-net of step t+1 is scheduled after Q and after ATT of step t, off the critical chain.
-//   * weight slices are RESIDENT in shared memory or streamed from L2 by cp.async.bulk + mbarrier
-//     (double buffered, issued ahead).
-//   * attention: CTA (utterance, quarter of Tx) keeps its keys/values slice in shared memory for all
-//     steps; scores + partial softmax + partial context per quarter, flash-style merge by the consumer.
-//   * %globaltimer stamp per step for the decoder-step latency metric.
+// History (C2: B=32, Tx=128, r=5; us per decoder step): v1 grid barrier + FFMA 58 -> v2 flag-in-data exchange 48
+// -> v3 mma.sync 3xTF32, 12 dependent slots, weights partly streamed from L2 every step 24.8.  The v3 per-slot trace
+// (profiles/r02_dec_trace_v3.log) showed ~3500 cycles per slot: ~2000 waiting for / ingesting K=512 operands through
+// L2 (32 KB of {value,tag} words per CTA and slot = the chip's L2 bandwidth cap), ~500 epilogue, 300-1200 of weight
+// streaming bookkeeping.  v4 attacks the length of the dependent chain and what sits on it:
+//
+//   * 9 dependent slots per step instead of 12 (weight-only algebra at pack time, exact up to re-association):
+//       IN  G1 C1 G2 C2 G3 C3  OQP  A|P2
+//     OQP computes, from s(t) alone, y(t) (output), q(t) = s.(W_out W_q) + b_out W_q and the FIRST PRE-NET LAYER OF
+//     THE NEXT STEP p1(t+1) = relu(s.(W_out[:,last 80] W1) + b_out[last 80] W1 + b1) (free-running rows); A|P2 runs
+//     the attention on warps 0-3 and the second pre-net layer on warps 4-7 concurrently; IN takes y(t-1) through
+//     s(t-1).(W_out W_a[:80r] W_in[128:]) so y never travels.  Teacher-forced rows take p1 from a separate
+//     off-chain stage PM (mel . W1), selected per row by the consumer.
+//   * every K=512 contraction is split into the half that is on the dependent chain (x of the gates, r*h of the
+//     candidate, ctx/p2 of the input projection) and the half whose operand has been known for a while (h(t-1), x,
+//     s(t-1)).  The known half is multiplied in the shadow of the previous slot's L2 hop into the SAME accumulator
+//     registers; only K=256 (16 KB of operand words per CTA) is ingested on the chain.
+//   * ALL weights are resident: on-chain slices in shared memory (124 KB), off-chain slices in TENSOR MEMORY
+//     (tcgen05.alloc of the SM's 256 KB TMEM, tcgen05.st once, tcgen05.ld.32x32b per use: every MMA weight fragment
+//     is private to one lane, which is exactly TMEM's lane/column addressing).  Nothing is streamed per step.
+//   * MMA orientation swapped: M = 16 weight columns of the CTA's slice, N = the 8 utterance rows of the CTA's row
+//     group, so the 16-column gate stage has no zero-padded rows (half the MMAs of v3).
+//   * attention: the four CTAs that share an utterance form a thread-block CLUSTER; partial softmax statistics and
+//     partial contexts are exchanged through distributed shared memory ({value,tag} words pushed into the peer's
+//     shared memory, polled locally), each CTA normalises and publishes 64 context columns and its own alignment
+//     slice: the consumer ingests 256 context words per row instead of 4 x 256 partials + statistics.
+//     tanh(k+q) = 1 - 2/(e^{2k} e^{2q} + 1) with e^{2k} precomputed once and e^{2q} once per step: one MUFU per
+//     element instead of two.
+//
+// Unchanged from v3: grid = 128 co-resident CTAs x 256 threads, CTA (rg, cs) owns utterance rows 8rg..8rg+7 and the
+// cs-th of 32 column slices of every dense stage; NO grid barrier: every exchanged activation is a 64-bit word
+// {fp32 value, step tag} written with one st.b64 and read with polling 128-bit loads; 3xTF32 error-compensated
+// tensor-core products (fp32-grade); GRU gate columns permuted so r,u of a hidden unit live in one CTA.
 #include <stdlib.h>
 #include "common.cuh"
 
@@ -48,74 +55,75 @@ namespace {
 constexpr int NCTA = 128;
 constexpr int NTHR = 256;
 constexpr int NWARP = 8;
-constexpr int RG = 4;          // row groups
-constexpr int RPG = 8;         // rows per group
+constexpr int RPG = 8;         // rows per row group
 constexpr int NS = 32;         // column slices
-constexpr int BPAD = RG * RPG; // 32
+constexpr int BPAD = 32;
 constexpr int U = 256;         // decoder units
 constexpr int AU = 256;        // attention units
 constexpr int ENC = 256;       // memory depth
 constexpr int MF = 80;
-constexpr int NSTAGE = 13;
-constexpr int KV_LD = 260;     // padded row stride for keys in smem
-constexpr int STREAM_FLOATS = 512 * 16;   // largest weight slice (K=512, 16 columns)
-constexpr int YLD = 512;       // row stride (words) of the y exchange buffer
-constexpr int MAXT = 8;        // max k-tiles per warp per segment (segment width <= 512)
+constexpr int KV_LD = 260;     // padded row stride of e^{2 keys} in smem
+constexpr int LD = 256;        // row stride (words) of every exchange buffer
 
-enum StageKind { K_P1 = 0, K_P2, K_IN, K_G1, K_C1, K_G2, K_C2, K_G3, K_C3, K_OUT, K_Q, K_ATT, K_AL };
-// execution order inside a step (P1/P2 belong to step t+1); two prologue slots P1(0), P2(0) come first
-constexpr int NORD = 12;       // slots per decoder step (K_AL is folded into K_IN, see "fused linear stages" below)
-__constant__ int c_order[NORD] = {K_IN, K_G1, K_C1, K_G2, K_C2, K_G3, K_C3, K_OUT, K_Q, K_P1, K_ATT, K_P2};
+// ---- weight segments (one K <= 256 slab of one stage, per CTA column slice) -------------------------------------
+enum SegId {
+    SG_IN_S = 0, SG_IN_CTX, SG_IN_P2,
+    SG_G_H0, SG_G_H1, SG_G_H2, SG_G_X0, SG_G_X1, SG_G_X2,
+    SG_C_X0, SG_C_X1, SG_C_X2, SG_C_RH0, SG_C_RH1, SG_C_RH2,
+    SG_Y, SG_QP, SG_PM, SG_P2, NSEG
+};
+// ---- exchange buffers ([32 rows][LD] 64-bit words each) ---------------------------------------------------------
+enum BufId { B_S = 0, B_CTX, B_P2, B_Z, B_H0, B_H1, B_H2, B_RH0, B_RH1, B_RH2, B_Q, B_P1Y, B_P1M, NBUF, B_MEL };
+// ---- stages (what "finish" does) --------------------------------------------------------------------------------
+enum StageId { ST_IN = 0, ST_G0, ST_G1, ST_G2, ST_C0, ST_C1, ST_C2, ST_PM, ST_OQP, ST_AP2, ST_NONE };
+// bias rows in smem ([row][16])
+enum BiasRow { BR_IN = 0, BR_INX, BR_G0, BR_G1, BR_G2, BR_C0, BR_C1, BR_C2, BR_Y, BR_QP, BR_PM, BR_P2, NBR };
 
-struct StageDesc {
-    int K0, K1;        // K = K0 + K1 (two concatenated sources), multiples of 8
-    int N;             // true output width
-    int NCV;           // valid columns per slice (4, 8 or 16)
-    int NT;            // 8-column MMA tiles per slice (1 or 2)
-    int64_t w_off;     // float offset of slice 0 in the packed buffer
-    int res_off;       // float offset inside the resident smem region, or -1 = streamed
+struct SegDesc {
+    int K;             // contraction length (multiple of 8, <= 256)
+    int FL;            // floats per lane and k-tile: 4 = 16 weight columns, 2 = 8 weight columns
+    int nw;            // warps that split K (8, or 4 for the P2 stage)
+    int kpw;           // k-tile slots per warp (4 or 8; padded with zeros)
+    int smem_off;      // float offset inside the resident smem region, or -1: lives in TMEM
+    int tmem_col;      // column offset inside the warp's 256-column TMEM half
+    int slice_floats;  // nw * kpw * 32 * FL
+    int64_t g_off;     // float offset of slice 0 in the packed buffer
 };
 
-struct DecLayout {     // workspace offsets in 64-bit LL words; every buffer is [32][ld]
-    int64_t p1, p2, attn, z, h[3], rh[3], s, ybuf, q, att_ms, att_ctx;
-    int64_t total;
+struct Item {          // one unit of the per-step program: multiply one operand segment into the accumulators
+    int seg, seg2;     // weight segment(s); seg2 >= 0: second 16-column tile sharing the operand (OQP)
+    int src;           // BufId of the operand
+    int tagd;          // operand tag = t + tagd
+    int stage;         // StageId finished after this item, or ST_NONE
+    int skip_t0;       // operand does not exist at t == 0 (zero initial state)
 };
+
+constexpr int MAX_ITEMS = 20;
 
 struct DecParams {
-    StageDesc st[NSTAGE];
-    DecLayout ws;
+    SegDesc seg[NSEG];
+    Item items[MAX_ITEMS];
+    int n_items;
+    int64_t buf[NBUF];           // word offsets of the exchange buffers
+    int64_t trace_off;
     taco_decoder_args a;
-    const float *pre_b1, *pre_b2, *in_b, *gru_bg[3], *gru_bc[3], *out_b, *att_v, *q_bias;
-    int OUT;           // 80*r
-    int Tq;            // Tx/4
-    int smem_kv_off, smem_res_off, smem_stream_off, smem_total_floats;
+    const float *in_b, *gru_bg[3], *gru_bc[3], *out_b, *pre_b1, *pre_b2, *att_v;
+    const float *b_qF, *b_p1F, *b_inS;     // fused biases (packed tail)
+    int OUT, NCY, Tq;
+    int smem_kv_off, smem_res_off, smem_total_floats;
 };
 
-__host__ __device__ inline void stage_dims(int kind, int OUT, int& K0, int& K1, int& N, int& NCV) {
-    switch (kind) {
-        case K_P1: K0 = MF;  K1 = 0;   N = 256; NCV = 8;  break;
-        case K_P2: K0 = 256; K1 = 0;   N = 128; NCV = 4;  break;
-        case K_IN: K0 = OUT + ENC; K1 = 128; N = U; NCV = 8; break;   // fused: [y(t-1) | ctx(t-1) | p2(t)] . W_inF
-        case K_G1: case K_G2: case K_G3: K0 = U; K1 = U; N = 2 * U; NCV = 16; break;
-        case K_C1: case K_C2: case K_C3: K0 = U; K1 = U; N = U;     NCV = 8;  break;
-        case K_OUT: K0 = U;  K1 = 0;   N = OUT; NCV = (OUT + NS - 1) / NS; NCV = (NCV <= 4) ? 4 : (NCV <= 8) ? 8 : 16; break;
-        case K_Q:  K0 = U;   K1 = 0;   N = AU;  NCV = 8;  break;        // fused: s . (W_out W_q) + b_out W_q
-        case K_AL: K0 = 0;   K1 = 0;   N = AU;  NCV = 8;  break;        // folded into K_IN (no slot, no weights)
-        default:   K0 = K1 = N = 0; NCV = 8; break;      // K_ATT has no weight slice
-    }
-}
-
-// global column computed by local column j of slice cs (-1 = padding).  GRU gates: slice cs owns
-// r (j < 8) and u (j >= 8) of hidden units 8cs..8cs+7.
-__host__ __device__ inline int stage_col(int kind, int cs, int j, int NCV, int N) {
-    if (kind == K_G1 || kind == K_G2 || kind == K_G3) return (j < 8) ? (8 * cs + j) : (U + 8 * cs + (j - 8));
-    if (j >= NCV) return -1;
-    const int c = cs * NCV + j;
-    return c < N ? c : -1;
+// global column computed by weight-column m (0..15) of slice cs for a segment (-1 = padding)
+__host__ __device__ inline int seg_col(int sg, int cs, int m, int NCY, int OUT) {
+    if (sg >= SG_G_H0 && sg <= SG_G_X2) return (m < 8) ? (8 * cs + m) : (U + 8 * cs + (m - 8));     // r | u of units 8cs..8cs+7
+    if (sg == SG_QP) return (m < 8) ? (8 * cs + m) : (AU + 8 * cs + (m - 8));                       // q | p1' (source = [W_qF | W_p1F])
+    if (sg == SG_Y) { const int c = cs * NCY + m; return (m < NCY && c < OUT) ? c : -1; }
+    if (sg == SG_P2) return (m < 4) ? (4 * cs + m) : -1;
+    return (m < 8) ? (8 * cs + m) : -1;
 }
 
 // physical position of logical column k inside an exchange buffer row: within each group of 8,
-// k and k+4 are adjacent so that one 16-byte load yields the (a0, a2) pair of an MMA A fragment.
+// k and k+4 are adjacent so that one 16-byte load yields the (b0, b1) pair of an MMA B fragment.
 __host__ __device__ inline int perm8(int k) {
     const int kk = k & 7;
     return (k & ~7) | ((kk < 4) ? 2 * kk : 2 * (kk - 4) + 1);
@@ -124,7 +132,6 @@ __host__ __device__ inline int perm8(int k) {
 // ---------------------------------------------------------------------------------------------
 // LL words: {value, tag}
 // ---------------------------------------------------------------------------------------------
-// strong (relaxed, gpu-scope) accesses: the words are read by other CTAs while the kernel runs
 __device__ __forceinline__ void ll_store(uint64_t* p, float v, uint32_t tag) {
     const uint64_t w = (uint64_t)__float_as_uint(v) | ((uint64_t)tag << 32);
     asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
@@ -152,683 +159,737 @@ __device__ __forceinline__ float2 ll_wait2(const uint64_t* p, uint32_t tag) {
     ll_spin(v, p, tag);
     return make_float2(__uint_as_float((uint32_t)v.x), __uint_as_float((uint32_t)v.y));
 }
+// the same protocol on words in (this CTA's) shared memory, written by cluster peers through DSMEM
+__device__ __forceinline__ uint64_t sm_load(const uint64_t* p) {
+    uint64_t v;
+    asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ float sm_wait(const uint64_t* p, uint32_t tag) {
+    uint64_t v = sm_load(p);
+    uint32_t spins = 0;
+    while ((uint32_t)(v >> 32) != tag) {
+        if (++spins > (1u << 24)) __trap();
+        v = sm_load(p);
+    }
+    return __uint_as_float((uint32_t)v);
+}
+// push a {value, tag} word into the shared memory of cluster CTA `rank` at the same offset as local `p`
+__device__ __forceinline__ void dsm_store(const uint64_t* p, uint32_t rank, float v, uint32_t tag) {
+    const uint64_t w = (uint64_t)__float_as_uint(v) | ((uint64_t)tag << 32);
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(p)), "r"(rank));
+    asm volatile("st.shared::cluster.b64 [%0], %1;" ::"r"(ra), "l"(w) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float rcp_fast(float x) {       // one MUFU.RCP (<= 1 ulp); rcp(+inf) = 0
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// e^{2x} with the argument clamped so that products of two such factors stay finite: exact for |x| <= 20.8
+// (tanh is saturated to the last bit far before that), graceful beyond
+__device__ __forceinline__ float exp2x(float x) { return exp2f(fminf(fmaxf(x * 2.885390082f, -60.f), 60.f)); }
+__device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// ---------------------------------------------------------------------------------------------
+// tensor memory as lane-private weight storage
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tm_st2(uint32_t taddr, float a, float b) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)) : "memory");
+}
+__device__ __forceinline__ void tm_st4(uint32_t taddr, float a, float b, float c, float d) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(a)), "r"(__float_as_uint(b)),
+                 "r"(__float_as_uint(c)), "r"(__float_as_uint(d)) : "memory");
+}
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_ld8(uint32_t taddr, float (&w)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tm_ld16(uint32_t taddr, float (&w)[16]) {
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[i] = __uint_as_float(r[i]);
+}
 
 // ---------------------------------------------------------------------------------------------
 // 3xTF32 tensor-core contraction pieces
 // ---------------------------------------------------------------------------------------------
 // x = hi + lo with hi = the TF32-representable head (low 13 mantissa bits cleared) and lo = the exact
-// remainder (the tensor core ignores lo's own low 13 bits: <= 2^-21 |x| dropped).  Two instructions per
-// value; cvt.rna.tf32 expands to ~14 SASS instructions on sm_100 and made v3.0 conversion-bound.
+// remainder (the tensor core ignores lo's own low 13 bits: <= 2^-21 |x| dropped).
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
     hi = __float_as_uint(x) & 0xffffe000u;
     lo = __float_as_uint(x - __uint_as_float(hi));
 }
-// D[16x8] += A[16x8] . B[8x8]; rows 8..15 of A are zero (a1 = a3 = 0)
-__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+// D[16 weight columns x 8 utterance rows] += A[16x8] . B[8x8]
+__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
     asm volatile(
         "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-        : "r"(a0), "r"(0u), "r"(a2), "r"(0u), "r"(b0), "r"(b1));
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
-// one k-tile: A pair (x[g][8kt+tg], x[g][8kt+tg+4]) against NT weight tiles (B fragments w[nt]).
-// The three 3xTF32 products go to three independent accumulators so that consecutive MMAs do not
-// serialise on the accumulator latency; they are summed once per stage.
-template <int NT>
-__device__ __forceinline__ void ktile_mma(float (&acc)[3][2][4], float xa, float xb, const float2 (&w)[NT]) {
-    uint32_t ah0, al0, ah2, al2;
-    split_tf32(xa, ah0, al0);
-    split_tf32(xb, ah2, al2);
-    __syncwarp();                                   // lanes may arrive from divergent polling loops
+// one k-tile: operand pair (x[row g][8kt+tg], x[row g][8kt+tg+4]) against one weight tile.
+//   FL = 4: w = (W[k][m=g], W[k][m=g+8], W[k+4][m=g], W[k+4][m=g+8]);  FL = 2: w = (W[k][m=g], W[k+4][m=g]), rows 8..15 zero.
+// The three 3xTF32 products go to three independent accumulators (no serialisation on the accumulator latency).
+template <int FL>
+__device__ __forceinline__ void ktile_mma(float (&acc)[3][4], uint32_t bh0, uint32_t bl0, uint32_t bh1, uint32_t bl1, const float* w) {
+    uint32_t ah[4], al[4];
+    if constexpr (FL == 4) {
 #pragma unroll
-    for (int nt = 0; nt < NT; ++nt) {
-        uint32_t bh0, bl0, bh1, bl1;
-        split_tf32(w[nt].x, bh0, bl0);
-        split_tf32(w[nt].y, bh1, bl1);
-        mma_tf32(acc[0][nt], al0, al2, bh0, bh1);
-        mma_tf32(acc[1][nt], ah0, ah2, bl0, bl1);
-        mma_tf32(acc[2][nt], ah0, ah2, bh0, bh1);
+        for (int i = 0; i < 4; ++i) split_tf32(w[i], ah[i], al[i]);
+    } else {
+        split_tf32(w[0], ah[0], al[0]);
+        split_tf32(w[1], ah[2], al[2]);
+        ah[1] = al[1] = ah[3] = al[3] = 0u;
     }
-}
-template <int NT>
-__device__ __forceinline__ void load_w(float2 (&w)[NT], const float* wfrag) {
-#pragma unroll
-    for (int nt = 0; nt < NT; ++nt) w[nt] = *reinterpret_cast<const float2*>(wfrag + nt * 64);
+    mma_tf32(acc[0], al[0], al[1], al[2], al[3], bh0, bh1);
+    mma_tf32(acc[1], ah[0], ah[1], ah[2], ah[3], bl0, bl1);
+    mma_tf32(acc[2], ah[0], ah[1], ah[2], ah[3], bh0, bh1);
 }
 
-// A segment of the K dimension whose activations live in an LL exchange buffer.
-//   rowp: buffer + row*ld, ntiles = width/8, wt0 = first k-tile of the segment in the weight slice.
-//   Warp w owns tiles w, w+8, ...  All LL loads and all weight-fragment loads are issued before the
-//   first tag check, so the only exposed latency is the arrival of the data itself.
-template <int NT>
-__device__ __forceinline__ void seg_ll(float (&acc)[3][2][4], const uint64_t* rowp, int ntiles, int wt0, uint32_t tag,
-                                       const float* Wsl, int warp, int lane) {
-    const uint64_t* p0 = rowp + warp * 8 + 2 * (lane & 3);
-    const float* w0 = Wsl + (size_t)(wt0 + warp) * NT * 64 + lane * 2;
-    ulonglong2 v[MAXT];
+// One operand segment against one (MT = 1) or two (MT = 2) weight tiles.  `widx`/`nw`: this warp's index among the
+// warps that split K; local slot i covers k-tile widx + nw*i.  `koff`: first k-tile slot of the warp's fragment
+// block used by this call (0, or 4 for the second half of an 8-slot segment).  Operand = LL exchange words (polling).
+template <int FL, int MT>
+__device__ __forceinline__ void seg_mma(float (&acc)[2][3][4], const SegDesc& sd, const SegDesc& sd2, const float* res_s, uint32_t tm_lane_col,
+                                        const uint64_t* rowp, bool live, uint32_t tag, int widx, int nw, int koff, int lane, long long* ck = nullptr) {
+    const int nkt = sd.K >> 3;
+    const int tg = lane & 3;
+    ulonglong2 v[4];
+    const uint64_t* p0 = rowp + (size_t)(widx + nw * koff) * 8 + 2 * tg;
 #pragma unroll
-    for (int i = 0; i < MAXT; ++i)
-        if (warp + NWARP * i < ntiles) v[i] = ll_load2(p0 + i * (NWARP * 8));
+    for (int i = 0; i < 4; ++i)
+        if (live && widx + nw * (koff + i) < nkt) v[i] = ll_load2(p0 + (size_t)i * nw * 8);
+    if (ck) ck[0] = clock64();
+    // weight fragments of the (up to) four k-tile slots
+    float w[MT][4 * FL];
+    __syncwarp();
 #pragma unroll
-    for (int h = 0; h < MAXT; h += 4) {                 // weight fragments four tiles at a time (register budget)
-        float2 wf[4][NT];
+    for (int mt = 0; mt < MT; ++mt) {
+        const SegDesc& d = mt ? sd2 : sd;
+        if (d.smem_off >= 0) {
+            const float* wp = res_s + d.smem_off + ((size_t)(widx * d.kpw + koff) * 32 + lane) * FL;
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-            if (warp + NWARP * (h + i) < ntiles) load_w<NT>(wf[i], w0 + (size_t)(h + i) * (NWARP * NT * 64));
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (warp + NWARP * (h + i) < ntiles) {
-                ll_spin(v[h + i], p0 + (h + i) * (NWARP * 8), tag);
-                ktile_mma<NT>(acc, __uint_as_float((uint32_t)v[h + i].x), __uint_as_float((uint32_t)v[h + i].y), wf[i]);
-            }
-        }
-    }
-}
-
-// Two segments at once (each <= 32 k-tiles, i.e. <= 4 per warp): all eight LL loads are in flight before
-// the first tag check, so a two-source stage exposes ONE L2 latency instead of two.
-template <int NT>
-__device__ __forceinline__ void seg2_ll(float (&acc)[3][2][4], const uint64_t* rowA, int ntA, int w0A, uint32_t tagA,
-                                        const uint64_t* rowB, int ntB, int w0B, uint32_t tagB, const float* Wsl, int warp, int lane) {
-    const int tg2 = 2 * (lane & 3);
-    const uint64_t* pA = rowA + warp * 8 + tg2;
-    const uint64_t* pB = rowB + warp * 8 + tg2;
-    const float* wA = Wsl + (size_t)(w0A + warp) * NT * 64 + lane * 2;
-    const float* wB = Wsl + (size_t)(w0B + warp) * NT * 64 + lane * 2;
-    ulonglong2 va[4], vb[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) if (warp + NWARP * i < ntA) va[i] = ll_load2(pA + i * (NWARP * 8));
-#pragma unroll
-    for (int i = 0; i < 4; ++i) if (warp + NWARP * i < ntB) vb[i] = ll_load2(pB + i * (NWARP * 8));
-    {
-        float2 wf[4][NT];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) if (warp + NWARP * i < ntA) load_w<NT>(wf[i], wA + (size_t)i * (NWARP * NT * 64));
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (warp + NWARP * i < ntA) {
-                ll_spin(va[i], pA + i * (NWARP * 8), tagA);
-                ktile_mma<NT>(acc, __uint_as_float((uint32_t)va[i].x), __uint_as_float((uint32_t)va[i].y), wf[i]);
-            }
-        }
-    }
-    {
-        float2 wf[4][NT];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) if (warp + NWARP * i < ntB) load_w<NT>(wf[i], wB + (size_t)i * (NWARP * NT * 64));
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (warp + NWARP * i < ntB) {
-                ll_spin(vb[i], pB + i * (NWARP * 8), tagB);
-                ktile_mma<NT>(acc, __uint_as_float((uint32_t)vb[i].x), __uint_as_float((uint32_t)vb[i].y), wf[i]);
-            }
-        }
-    }
-}
-
-__global__ void __launch_bounds__(NTHR, 1) decoder_kernel(const DecParams P) {
-    extern __shared__ __align__(16) float smem[];
-    // smem map (floats): [0,64) mbarriers | part_s 2*8*2*64 | loc 512 | bias 13*16 (256) | small 1024 | kv | stream 2x | resident
-    uint64_t* wbar = reinterpret_cast<uint64_t*>(smem);          // [0],[1] stream buffers, [2] resident preload
-    float* part_s = smem + 64;                                    // [2 parity][8 warps][2 nt][8 rows][8 cols]
-    float* loc_s = part_s + 2 * NWARP * 128;                      // h_loc[3][64] | u_loc[64] | z_loc[64]
-    float* bias_s = loc_s + 512;                                  // [13][16]
-    float* small_s = bias_s + 256;                                // q_s[256] | v_s[256] | e_s[64] | p_s[64] | misc
-    float* keys_s = smem + P.smem_kv_off;
-    float* vals_s = keys_s + P.Tq * KV_LD;
-    float* res_s = smem + P.smem_res_off;
-    float* stream_s = smem + P.smem_stream_off;
-    float* h_loc = loc_s;             // [3][8][8]
-    float* u_loc = loc_s + 192;       // [8][8]
-    float* z_loc = loc_s + 256;       // [8][8]
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, tg = lane & 3;            // MMA fragment coordinates: row g, k / column pair tg
-    const int cta = blockIdx.x;
-    const int rg = cta & 3, cs = cta >> 2;             // dense stages
-    const int arow = cta >> 2, aq = cta & 3;           // attention stage: utterance, quarter
-    const taco_decoder_args& A = P.a;
-    uint64_t* ws = reinterpret_cast<uint64_t*>(A.workspace);
-    const int B = A.B, T = A.T, OUT = P.OUT, Tq = P.Tq, Tx = A.Tx;
-    const int row0 = rg * RPG;
-    const int myrow = row0 + g;                        // the utterance row this lane's A fragments belong to
-
-    if (tid == 0) {
-        mbar_init(&wbar[0], 1); mbar_init(&wbar[1], 1); mbar_init(&wbar[2], 1);
-        mbar_fence_init();
-    }
-    for (int i = tid; i < 512; i += NTHR) loc_s[i] = 0.f;          // zero initial GRU states (cell.zero_state)
-    // biases of this CTA's columns -> smem
-    if (tid < NSTAGE * 16) {
-        const int s = tid >> 4, j = tid & 15;
-        const StageDesc& d = P.st[s];
-        float bv = 0.f;
-        if (s != K_ATT) {
-            const int col = stage_col(s, cs, j, d.NCV, d.N);
-            const float* bp = nullptr;
-            switch (s) {
-                case K_P1: bp = P.pre_b1; break;
-                case K_P2: bp = P.pre_b2; break;
-                case K_IN: bp = P.in_b; break;
-                case K_G1: case K_G2: case K_G3: bp = P.gru_bg[(s - K_G1) / 2]; break;
-                case K_C1: case K_C2: case K_C3: bp = P.gru_bc[(s - K_C1) / 2]; break;
-                case K_OUT: bp = P.out_b; break;
-                case K_Q: bp = P.q_bias; break;        // b_out . W_q (fused query stage)
-                default: break;
-            }
-            if (bp && col >= 0) bv = __ldg(bp + col);
-        }
-        bias_s[tid] = bv;
-    }
-    __syncthreads();
-
-    // ---- one-time preload: resident weight slices (bulk copies) ----
-    if (tid == 0) {
-        uint32_t bytes = 0;
-        for (int s = 0; s < NSTAGE; ++s) {
-            const StageDesc& d = P.st[s];
-            if (s == K_ATT || d.res_off < 0) continue;
-            bytes += (uint32_t)((d.K0 + d.K1) * d.NT * 8 * 4);
-        }
-        if (bytes) {
-            mbar_arrive_expect_tx(&wbar[2], bytes);
-            for (int s = 0; s < NSTAGE; ++s) {
-                const StageDesc& d = P.st[s];
-                if (s == K_ATT || d.res_off < 0) continue;
-                const int fl = (d.K0 + d.K1) * d.NT * 8;
-                if (fl == 0) continue;
-                bulk_load(res_s + d.res_off, A.packed + d.w_off + (int64_t)cs * fl, (uint32_t)fl * 4, &wbar[2]);
+            for (int i = 0; i < 4; ++i) {
+                if constexpr (FL == 4) { const float4 t = *reinterpret_cast<const float4*>(wp + (size_t)i * 32 * FL); w[mt][4 * i] = t.x; w[mt][4 * i + 1] = t.y; w[mt][4 * i + 2] = t.z; w[mt][4 * i + 3] = t.w; }
+                else                   { const float2 t = *reinterpret_cast<const float2*>(wp + (size_t)i * 32 * FL); w[mt][2 * i] = t.x; w[mt][2 * i + 1] = t.y; }
             }
         } else {
-            mbar_arrive(&wbar[2]);
+            const uint32_t ta = tm_lane_col + (uint32_t)(d.tmem_col + koff * FL);
+            if constexpr (FL == 4) tm_ld16(ta, w[mt]);
+            else                   tm_ld8(ta, w[mt]);
         }
     }
-    // keys / values slice of (arow, aq) -> smem (padded rows), zero for utterances >= B
+    if (ck) ck[1] = clock64();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (widx + nw * (koff + i) < nkt) {            // warp-uniform
+            float xa = 0.f, xb = 0.f;
+            if (live) {
+                ll_spin(v[i], p0 + (size_t)i * nw * 8, tag);
+                xa = __uint_as_float((uint32_t)v[i].x); xb = __uint_as_float((uint32_t)v[i].y);
+            }
+            uint32_t bh0, bl0, bh1, bl1;
+            split_tf32(xa, bh0, bl0);
+            split_tf32(xb, bh1, bl1);
+            __syncwarp();                               // lanes arrive from divergent polling loops
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) ktile_mma<FL>(acc[mt], bh0, bl0, bh1, bl1, &w[mt][i * FL]);
+        }
+    }
+    if (ck) ck[2] = clock64();
+}
+
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_kernel(const __grid_constant__ DecParams P) {
+    extern __shared__ __align__(16) float smem[];
+    // smem map (floats): [0,16) tmem ptr | part 4096 | part2 256 | loc 384 | bias 256 | att 704 | xbuf 1024 | xstat 64 | kv | resident weights
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem);
+    float* part_s = smem + 16;                                    // [2 parity][8 warps][2 tiles][128]
+    float* part2_s = part_s + 4096;                               // [4 warps][64]   (P2, warps 4-7)
+    float* loc_s = part2_s + 256;                                 // h_loc[3][64] | u_loc[64] | z_loc[64]
+    float* bias_s = loc_s + 384;                                  // [NBR][16]
+    float* att_s = bias_s + 256;                                  // eq[256] | v[256] | e[64] | p[64] | misc[64]
+    uint64_t* xbuf = reinterpret_cast<uint64_t*>(att_s + 704);    // [2 parity][4 src][64] words
+    uint64_t* xstat = xbuf + 512;                                 // [2 parity][4 src][2] words (+pad)
+    float* ek_s = smem + P.smem_kv_off;
+    float* vals_s = ek_s + P.Tq * KV_LD;
+    float* res_s = smem + P.smem_res_off;
+    float* h_loc = loc_s;             // [3][8 cols][8 rows]
+    float* u_loc = loc_s + 192;
+    float* z_loc = loc_s + 256;
+    float* eq_s = att_s;
+    float* v_s = att_s + 256;
+    float* e_s = att_s + 512;
+    float* p_s = att_s + 576;
+    float* misc_s = att_s + 640;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tg = lane & 3;            // MMA fragment coordinates
+    const int cta = blockIdx.x;
+    const int rg = cta & 3, cs = cta >> 2;             // dense stages: row group, column slice
+    const int arow = cta >> 2;                          // attention: utterance (the cluster), quarter = cluster rank
+    const uint32_t aq = cluster_rank();
+    const taco_decoder_args& A = P.a;
+    uint64_t* ws = reinterpret_cast<uint64_t*>(A.workspace);
+    const int B = A.B, T = A.T, OUT = P.OUT, Tq = P.Tq, Tx = A.Tx, NCY = P.NCY;
+    const int row0 = rg * RPG;
+    const int myrow = row0 + g;                        // the utterance row this lane's B fragments belong to
+
+    // ---- tensor memory: the whole 512-column TMEM of the SM (1 CTA/SM) ----
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = tid; i < 384; i += NTHR) loc_s[i] = 0.f;          // zero initial GRU states (cell.zero_state)
+    for (int i = tid; i < 2 * (512 + 32); i += NTHR) reinterpret_cast<uint32_t*>(xbuf)[i] = 0u;   // tag 0 = invalid
+    // biases of this CTA's columns -> smem
+    if (tid < NBR * 16) {
+        const int br = tid >> 4, m = tid & 15;
+        float bv = 0.f;
+        int col; const float* bp = nullptr;
+        switch (br) {
+            case BR_IN:  col = seg_col(SG_IN_CTX, cs, m, NCY, OUT); bp = P.in_b; break;
+            case BR_INX: col = seg_col(SG_IN_CTX, cs, m, NCY, OUT); bp = P.b_inS; break;
+            case BR_G0: case BR_G1: case BR_G2: col = seg_col(SG_G_X0, cs, m, NCY, OUT); bp = P.gru_bg[br - BR_G0]; break;
+            case BR_C0: case BR_C1: case BR_C2: col = seg_col(SG_C_X0, cs, m, NCY, OUT); bp = P.gru_bc[br - BR_C0]; break;
+            case BR_Y:   col = seg_col(SG_Y, cs, m, NCY, OUT); bp = P.out_b; break;
+            case BR_QP:  col = (m < 8) ? 8 * cs + m : 8 * cs + (m - 8); bp = (m < 8) ? P.b_qF : P.b_p1F; break;
+            case BR_PM:  col = seg_col(SG_PM, cs, m, NCY, OUT); bp = P.pre_b1; break;
+            default:     col = seg_col(SG_P2, cs, m, NCY, OUT); bp = P.pre_b2; break;
+        }
+        if (bp && col >= 0) bv = __ldg(bp + col);
+        bias_s[tid] = bv;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    // this warp's private TMEM window: lanes 32*(warp%4).., columns 256*(warp/4)..
+    const uint32_t tm_lane_col = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * 256u;
+
+    // ---- one-time preload of the weight slices: smem segments by coalesced copies, TMEM segments by tcgen05.st ----
+    for (int sg = 0; sg < NSEG; ++sg) {
+        const SegDesc& d = P.seg[sg];
+        const float* src = A.packed + d.g_off + (int64_t)cs * d.slice_floats;
+        if (d.smem_off >= 0) {
+            const float4* s4 = reinterpret_cast<const float4*>(src);
+            float4* d4 = reinterpret_cast<float4*>(res_s + d.smem_off);
+            for (int i = tid; i < d.slice_floats / 4; i += NTHR) d4[i] = __ldg(s4 + i);
+        } else {
+            const int widx = (d.nw == NWARP) ? warp : warp - 4;
+            if (widx >= 0) {                                            // warp-uniform
+                for (int i = 0; i < d.kpw; ++i) {
+                    const float* wp = src + ((size_t)(widx * d.kpw + i) * 32 + lane) * d.FL;
+                    const uint32_t ta = tm_lane_col + (uint32_t)(d.tmem_col + i * d.FL);
+                    if (d.FL == 4) { const float4 t = __ldg(reinterpret_cast<const float4*>(wp)); tm_st4(ta, t.x, t.y, t.z, t.w); }
+                    else           { const float2 t = __ldg(reinterpret_cast<const float2*>(wp)); tm_st2(ta, t.x, t.y); }
+                }
+            }
+        }
+    }
+    tm_wait_st();
+    // e^{2 keys} / values slice of (arow, aq) -> smem (padded rows), zero for utterances >= B and positions >= Tx
     for (int i = tid; i < Tq * (ENC / 4); i += NTHR) {
         const int j = i / (ENC / 4), d4 = (i % (ENC / 4)) * 4;
         float4 kk = make_float4(0, 0, 0, 0), vv = kk;
-        if (arow < B && aq * Tq + j < Tx) {                 // ragged last quarter when Tx is not a multiple of 4
+        if (arow < B && (int)aq * Tq + j < Tx) {
             const int64_t gi = ((int64_t)arow * Tx + aq * Tq + j) * ENC + d4;
             kk = __ldg(reinterpret_cast<const float4*>(A.keys + gi));
             vv = __ldg(reinterpret_cast<const float4*>(A.values + gi));
         }
-        *reinterpret_cast<float4*>(keys_s + j * KV_LD + d4) = kk;
+        // tanh(k+q) = 1 - 2/(e^{2k} e^{2q} + 1);  2*log2(e) = 2.885390082
+        kk.x = exp2x(kk.x); kk.y = exp2x(kk.y); kk.z = exp2x(kk.z); kk.w = exp2x(kk.w);
+        *reinterpret_cast<float4*>(ek_s + j * KV_LD + d4) = kk;
         *reinterpret_cast<float4*>(vals_s + j * ENC + d4) = vv;
     }
-    for (int i = tid; i < AU; i += NTHR) small_s[256 + i] = __ldg(P.att_v + i);
+    for (int i = tid; i < AU; i += NTHR) v_s[i] = __ldg(P.att_v + i);
     const int my_len = (arow < B) ? A.text_length[arow] : 0;
-    mbar_wait(&wbar[2], 0);
     __syncthreads();
+    if (warp == 0) {                                    // V0 = sum_d v_d  (e_j = V0 - 2 sum_d v_d / (E_jd + 1))
+        float s = 0.f;
+        for (int i = lane; i < AU; i += 32) s += v_s[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) misc_s[0] = s;
+    }
+    __syncthreads();
+    cluster_sync_all();                                 // peers' shared memory is initialised before anyone pushes into it
 
-    // slot -> stage kind.  Slots 0,1 = P1(0), P2(0); then NORD (12) per step in c_order.
-    const int total_slots = 2 + T * NORD;
-    auto slot_kind = [&](int sl) { return sl < 2 ? sl : c_order[(sl - 2) % NORD]; };
-    // streamed-slice bookkeeping: issue order == consume order; buffer = (index) & 1.  At most two slices
-    // are in flight.  A buffer is re-filled only at the top of a slot, when every thread has passed the
-    // post-compute __syncthreads of the slot that last read it.
-    uint32_t n_issued = 0, n_consumed = 0;
-    int next_issue = 0;
-    auto is_streamed = [&](int s) { return s != K_ATT && P.st[s].res_off < 0; };
-    auto pump = [&]() {
-        while (n_issued - n_consumed < 2) {
-            while (next_issue < total_slots && !is_streamed(slot_kind(next_issue))) ++next_issue;
-            if (next_issue >= total_slots) break;
-            if (tid == 0) {
-                const StageDesc& d = P.st[slot_kind(next_issue)];
-                const int fl = (d.K0 + d.K1) * d.NT * 8;
-                const int buf = n_issued & 1;
-                // (no proxy fence: the buffer's previous contents were only READ through the generic proxy and
-                //  those reads are ordered before this point by __syncthreads; fence.proxy.async costs ~800 cycles)
-                mbar_arrive_expect_tx(&wbar[buf], (uint32_t)fl * 4);
-                bulk_load(stream_s + buf * STREAM_FLOATS, A.packed + d.w_off + (int64_t)cs * fl, (uint32_t)fl * 4, &wbar[buf]);
+    float acc[2][3][4];
+#pragma unroll
+    for (int a0 = 0; a0 < 2; ++a0)
+#pragma unroll
+        for (int a1 = 0; a1 < 3; ++a1)
+#pragma unroll
+            for (int a2 = 0; a2 < 4; ++a2) acc[a0][a1][a2] = 0.f;
+
+    int par = 0;                                        // parity of the partial-tile buffer
+    long long* cktr = nullptr;                          // per-item clock64 trace (CTA 0, thread 0, steps 10..13)
+    const bool tracer = (cta == 0 && tid == 0 && A.step_ns != nullptr);
+    int64_t trace_i = 0;
+
+    // =========================================================================================================
+    // finish a stage: per-warp partial tiles -> smem, cross-warp sum, epilogue (one thread per output)
+    // =========================================================================================================
+    auto store_partials = [&](float* part, int MT, bool full16) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            if (mt < MT) {
+                float* pw = part + (warp * 2 + mt) * 128;
+                *reinterpret_cast<float2*>(pw + g * 8 + 2 * tg) =
+                    make_float2((acc[mt][0][0] + acc[mt][1][0]) + acc[mt][2][0], (acc[mt][0][1] + acc[mt][1][1]) + acc[mt][2][1]);
+                if (full16)
+                    *reinterpret_cast<float2*>(pw + (g + 8) * 8 + 2 * tg) =
+                        make_float2((acc[mt][0][2] + acc[mt][1][2]) + acc[mt][2][2], (acc[mt][0][3] + acc[mt][1][3]) + acc[mt][2][3]);
             }
-            ++n_issued; ++next_issue;
         }
+#pragma unroll
+        for (int a0 = 0; a0 < 2; ++a0)
+#pragma unroll
+            for (int a1 = 0; a1 < 3; ++a1)
+#pragma unroll
+                for (int a2 = 0; a2 < 4; ++a2) acc[a0][a1][a2] = 0.f;
+    };
+    auto sum8 = [&](const float* part, int mt, int e) {
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < NWARP; ++w) v += part[(w * 2 + mt) * 128 + e];
+        return v;
     };
 
-    // alignments of step `step`: a_j = p_j * exp(m_q - M) / S from the four quarter (max, sum) pairs.  Done by
-    // the last two warps (fewest k-tiles) with the four loads issued together; p_s still holds that step's
-    // unnormalised probabilities (the next K_ATT slot has not run yet).
-    auto finalize_align = [&](int step, uint32_t tag) {
-        if (arow < B && tid >= NTHR - 64 && tid - (NTHR - 64) < Tq && aq * Tq + (tid - (NTHR - 64)) < Tx) {
-            const int j = tid - (NTHR - 64);
-            const uint64_t* ms = ws + P.ws.att_ms + (int64_t)arow * 8;
-            ulonglong2 mv[4];
-#pragma unroll
-            for (int qd = 0; qd < 4; ++qd) mv[qd] = ll_load2(ms + 2 * qd);
-            float m[4], sq[4], M = -INFINITY;
-#pragma unroll
-            for (int qd = 0; qd < 4; ++qd) {
-                ll_spin(mv[qd], ms + 2 * qd, tag);
-                m[qd] = __uint_as_float((uint32_t)mv[qd].x); sq[qd] = __uint_as_float((uint32_t)mv[qd].y); M = fmaxf(M, m[qd]);
-            }
-            float S = 0.f;
-#pragma unroll
-            for (int qd = 0; qd < 4; ++qd) S += ((m[qd] == -INFINITY) ? 0.f : __expf(m[qd] - M)) * sq[qd];
-            const float sc = ((m[aq] == -INFINITY) ? 0.f : __expf(m[aq] - M)) / S;
-            const float* p_s = small_s + 512 + 64;
-            A.align[((int64_t)arow * T + step) * Tx + aq * Tq + j] = p_s[j] * sc;
+    // ---- attention of step t on warps 0..3 (128 threads): scores, partial softmax / context, cluster merge ----
+    auto attention = [&](int t) {
+        if (arow >= B) return;                          // whole cluster idle for padding utterances
+        const uint32_t tag = (uint32_t)t + 1;
+        const int xp = t & 1;
+        {   // q(t) of this utterance -> e^{2q}
+            const float2 qq = ll_wait2(ws + P.buf[B_Q] + (int64_t)arow * LD + 2 * tid, tag);
+            const int k0 = ((tid >> 2) << 3) + (tid & 3);        // physical pair (2p, 2p+1) = logical k0, k0+4
+            eq_s[k0] = exp2x(qq.x);
+            eq_s[k0 + 4] = exp2x(qq.y);
         }
-    };
-
-    for (int sl = 0; sl < total_slots; ++sl) {
-        const int s = slot_kind(sl);
-        const int t = sl < 2 ? -1 : (sl - 2) / NORD;             // decoder step this slot executes in (-1 = prologue)
-        const int tb = (s == K_P1 || s == K_P2) ? t + 1 : t;      // decoder step the OUTPUT of this slot belongs to
-        const uint32_t tag_out = (uint32_t)tb + 1;                // tag of everything produced for step tb
-        pump();
-        if (cta == 0 && tid == 0 && A.step_ns) {
-            const uint64_t now = globaltimer_ns();
-            if (s == K_IN) A.step_ns[t] = now;
-            ws[P.ws.total + sl] = now;                   // per-slot trace (debug / profiling): [2 + 13 T] stamps after the LL buffers
-        }
-        const bool tracer = (cta == 0 && tid == 0 && A.step_ns != nullptr);
-        uint64_t* ctrace = ws + P.ws.total + total_slots + 16 + (int64_t)sl * 4;   // clock64 at 4 points of the slot (CTA 0, thread 0)
-        if (tracer) ctrace[0] = (uint64_t)clock64();
-
-        if (s == K_ATT) {
-            // =============== attention scores / partial softmax / partial context ===============
-            float* q_s = small_s;             // [256]
-            float* v_s = small_s + 256;       // [256] (loaded once)
-            float* e_s = small_s + 512;       // [Tq]
-            float* p_s = small_s + 512 + 64;  // [Tq]  (kept until the K_AL stage)
-            if (arow < B && tid < AU / 2) {
-                // physical pair (2p, 2p+1) holds logical k0 = 8*(p/4) + p%4 and k0 + 4
-                const float2 qq = ll_wait2(ws + P.ws.q + (int64_t)arow * AU + 2 * tid, tag_out);
-                const int k0 = ((tid >> 2) << 3) + (tid & 3);
-                q_s[k0] = qq.x; q_s[k0 + 4] = qq.y;
-            }
-            __syncthreads();
-            if (arow < B) {
-                const int dsl = tid & 7;
-                // warp-uniform trip count (each warp covers 4 consecutive j per pass): the full-mask
-                // shuffles below must be executed by all 32 lanes even when Tq is not a multiple of 4
-                for (int j0 = warp * 4; j0 < Tq; j0 += NTHR / 8) {
-                    const int j = j0 + (lane >> 3);
-                    const bool valid = j < Tq;
-                    float acc = 0.f;
-                    if (valid) {
+        named_bar(1, 128);
+        const float V0 = misc_s[0];
+        {
+            const int dsl = lane & 7;
+            for (int j0 = warp * 4; j0 < Tq; j0 += 16) {
+                const int j = j0 + (lane >> 3);
+                const bool valid = j < Tq;
+                float a = 0.f;
+                if (valid) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const int d0 = i * 32 + dsl * 4;
-                            const float4 kk = *reinterpret_cast<const float4*>(keys_s + j * KV_LD + d0);
-                            const float4 qq = *reinterpret_cast<const float4*>(q_s + d0);
-                            const float4 vv = *reinterpret_cast<const float4*>(v_s + d0);
-                            acc = fmaf(vv.x, tanhf_acc(kk.x + qq.x), acc);
-                            acc = fmaf(vv.y, tanhf_acc(kk.y + qq.y), acc);
-                            acc = fmaf(vv.z, tanhf_acc(kk.z + qq.z), acc);
-                            acc = fmaf(vv.w, tanhf_acc(kk.w + qq.w), acc);
-                        }
+                    for (int i = 0; i < 8; ++i) {
+                        const int d0 = i * 32 + dsl * 4;
+                        const float4 kk = *reinterpret_cast<const float4*>(ek_s + j * KV_LD + d0);
+                        const float4 qq = *reinterpret_cast<const float4*>(eq_s + d0);
+                        const float4 vv = *reinterpret_cast<const float4*>(v_s + d0);
+                        a = fmaf(vv.x, rcp_fast(fmaf(kk.x, qq.x, 1.0f)), a);
+                        a = fmaf(vv.y, rcp_fast(fmaf(kk.y, qq.y, 1.0f)), a);
+                        a = fmaf(vv.z, rcp_fast(fmaf(kk.z, qq.z, 1.0f)), a);
+                        a = fmaf(vv.w, rcp_fast(fmaf(kk.w, qq.w, 1.0f)), a);
                     }
-                    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-                    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-                    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-                    if (valid && dsl == 0) e_s[j] = (aq * Tq + j < my_len) ? acc : -INFINITY;
                 }
+                a += __shfl_xor_sync(0xffffffffu, a, 1);
+                a += __shfl_xor_sync(0xffffffffu, a, 2);
+                a += __shfl_xor_sync(0xffffffffu, a, 4);
+                if (valid && dsl == 0) e_s[j] = ((int)aq * Tq + j < my_len) ? fmaf(-2.0f, a, V0) : -INFINITY;
             }
-            __syncthreads();
-            if (arow < B && warp == 0) {
-                float m = -INFINITY;
-                for (int j = lane; j < Tq; j += 32) m = fmaxf(m, e_s[j]);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-                float ssum = 0.f;
-                for (int j = lane; j < Tq; j += 32) {
-                    const float p = (m == -INFINITY) ? 0.f : __expf(e_s[j] - m);
-                    p_s[j] = p;
-                    ssum += p;
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
-                if (lane == 0) {
-                    uint64_t* ms = ws + P.ws.att_ms + ((int64_t)arow * 4 + aq) * 2;
-                    ll_store(ms, m, tag_out);
-                    ll_store(ms + 1, ssum, tag_out);
-                }
-            }
-            __syncthreads();
-            if (arow < B) {
-                float c = 0.f;
-                for (int j = 0; j < Tq; ++j) c = fmaf(p_s[j], vals_s[j * ENC + tid], c);
-                ll_store(ws + P.ws.att_ctx + ((int64_t)arow * 4 + aq) * ENC + perm8(tid), c, tag_out);
-            }
-            continue;
         }
+        named_bar(1, 128);
+        // quarter statistics (every warp redundantly; Tq <= 64)
+        const float e0 = (lane < Tq) ? e_s[lane] : -INFINITY;
+        const float e1 = (lane + 32 < Tq) ? e_s[lane + 32] : -INFINITY;
+        float m = fmaxf(e0, e1);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        const float p0 = (e0 == -INFINITY) ? 0.f : __expf(e0 - m);
+        const float p1 = (e1 == -INFINITY) ? 0.f : __expf(e1 - m);
+        float ssum = p0 + p1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ssum += __shfl_xor_sync(0xffffffffu, ssum, o);
+        if (warp == 0) {
+            if (lane < Tq) p_s[lane] = p0;
+            if (lane + 32 < Tq) p_s[lane + 32] = p1;
+        }
+        if (tid < 4) {                                   // statistics -> every CTA of the cluster (incl. this one)
+            dsm_store(xstat + (xp * 4 + aq) * 2, (uint32_t)tid, m, tag);
+            dsm_store(xstat + (xp * 4 + aq) * 2 + 1, (uint32_t)tid, ssum, tag);
+        }
+        named_bar(1, 128);
+        {   // partial context: columns 2 tid, 2 tid + 1; pushed to the CTA that owns them (64 columns per CTA)
+            float c0 = 0.f, c1 = 0.f;
+            for (int j = 0; j < Tq; ++j) {
+                const float p = p_s[j];
+                const float2 vv = *reinterpret_cast<const float2*>(vals_s + j * ENC + 2 * tid);
+                c0 = fmaf(p, vv.x, c0); c1 = fmaf(p, vv.y, c1);
+            }
+            const uint32_t dst = (uint32_t)tid >> 5;
+            const int i0 = (2 * tid) & 63;
+            dsm_store(xbuf + (xp * 4 + aq) * 64 + i0, dst, c0, tag);
+            dsm_store(xbuf + (xp * 4 + aq) * 64 + i0 + 1, dst, c1, tag);
+        }
+        // merge: global max / sum from the four quarter statistics
+        float mq[4], wq[4], M = -INFINITY, S = 0.f, w_own = 0.f;
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) { mq[qd] = sm_wait(xstat + (xp * 4 + qd) * 2, tag); M = fmaxf(M, mq[qd]); }
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+            const float sq = sm_wait(xstat + (xp * 4 + qd) * 2 + 1, tag);
+            wq[qd] = (mq[qd] == -INFINITY) ? 0.f : __expf(mq[qd] - M);
+            S = fmaf(wq[qd], sq, S);
+            if (qd == (int)aq) w_own = wq[qd];
+        }
+        const float inv = (S > 0.f) ? 1.0f / S : 0.f;
+        if (tid < 64) {                                  // final context column 64 aq + tid
+            float c = 0.f;
+#pragma unroll
+            for (int qd = 0; qd < 4; ++qd) c = fmaf(wq[qd], sm_wait(xbuf + (xp * 4 + qd) * 64 + tid, tag), c);
+            ll_store(ws + P.buf[B_CTX] + (int64_t)arow * LD + perm8(64 * (int)aq + tid), c * inv, tag);
+        } else {                                         // alignments of this quarter (AttentionWrapper alignment_history)
+            const int j = tid - 64;
+            if (j < Tq && (int)aq * Tq + j < Tx) A.align[((int64_t)arow * T + t) * Tx + aq * Tq + j] = p_s[j] * (w_own * inv);
+        }
+    };
 
-        const StageDesc& d = P.st[s];
-        const int NT = d.NT;
-        // ---- this stage's weight slice (fragment order [k-tile][nt][lane][2]) ----
-        const float* Wsl;
-        if (d.res_off >= 0) {
-            Wsl = res_s + d.res_off;
+    // ---- second pre-net layer of step tb on warps 4..7: p2(tb) = relu(p1(tb) . W2 + b2) ----
+    auto prenet2 = [&](int tb) {
+        const uint32_t tag = (uint32_t)tb + 1;
+        const int widx = warp - 4;
+        bool from_y = (tb > 0);
+        if (A.mode == TACO_DEC_TEACHER) from_y = false;
+        else if (A.mode == TACO_DEC_SCHED) from_y = (tb > 0) && (myrow < B) && (A.sample_mask[(int64_t)(tb - 1) * B + myrow] != 0);
+        const uint64_t* rowp = ws + P.buf[from_y ? B_P1Y : B_P1M] + (int64_t)myrow * LD;
+        const SegDesc& sd = P.seg[SG_P2];
+        seg_mma<2, 1>(acc, sd, sd, res_s, tm_lane_col, rowp, true, tag, widx, 4, 0, lane);
+        seg_mma<2, 1>(acc, sd, sd, res_s, tm_lane_col, rowp, true, tag, widx, 4, 4, lane);
+        float* pw = part2_s + widx * 64;
+        *reinterpret_cast<float2*>(pw + g * 8 + 2 * tg) =
+            make_float2((acc[0][0][0] + acc[0][1][0]) + acc[0][2][0], (acc[0][0][1] + acc[0][1][1]) + acc[0][2][1]);
+#pragma unroll
+        for (int a1 = 0; a1 < 3; ++a1)
+#pragma unroll
+            for (int a2 = 0; a2 < 4; ++a2) acc[0][a1][a2] = 0.f;
+        named_bar(2, 128);
+        const int e = tid - 128;
+        if (e < 32) {                                    // 4 columns x 8 rows
+            const int wcol = e >> 3, brow = e & 7, row = row0 + brow, col = 4 * cs + wcol;
+            float v = part2_s[e] + part2_s[64 + e] + part2_s[128 + e] + part2_s[192 + e] + bias_s[BR_P2 * 16 + wcol];
+            v = fmaxf(v, 0.f);
+            if (A.keep2 && row < B && tb < T) v = A.keep2[((int64_t)tb * B + row) * 128 + col] ? v * A.keep_scale : 0.f;
+            ll_store(ws + P.buf[B_P2] + (int64_t)row * LD + perm8(col), v, tag);
+        }
+        named_bar(2, 128);                               // part2_s may be rewritten
+    };
+
+    // ---- first pre-net layer of step tb from the teacher frame (or zeros): p1m(tb) = relu(x . W1 + b1) ----
+    auto prenet1_teacher = [&](int tb) {
+        const bool have = (A.mode != TACO_DEC_INFER) && (myrow < B) && (tb < T);
+        const SegDesc& sd = P.seg[SG_PM];
+        float w[8];
+        if (sd.smem_off >= 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 t2 = *reinterpret_cast<const float2*>(res_s + sd.smem_off + ((size_t)(warp * sd.kpw + i) * 32 + lane) * 2);
+                w[2 * i] = t2.x; w[2 * i + 1] = t2.y;
+            }
         } else {
-            const int buf = n_consumed & 1;
-            mbar_wait(&wbar[buf], (n_consumed >> 1) & 1);
-            Wsl = stream_s + buf * STREAM_FLOATS;
-            ++n_consumed;
+            __syncwarp();
+            tm_ld8(tm_lane_col + (uint32_t)sd.tmem_col, w);
         }
-
-        float acc[3][2][4];
 #pragma unroll
-        for (int a3 = 0; a3 < 3; ++a3)
-#pragma unroll
-            for (int i = 0; i < 2; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[a3][i][j] = 0.f;
+        for (int i = 0; i < 2; ++i) {
+            const int kt = warp + 8 * i;
+            if (kt < MF / 8) {                           // warp-uniform
+                float xa = 0.f, xb = 0.f;
+                if (have) {
+                    const float* mp = A.mel + ((int64_t)myrow * T + tb) * OUT + (OUT - MF) + kt * 8 + tg;
+                    xa = __ldg(mp); xb = __ldg(mp + 4);
+                }
+                uint32_t bh0, bl0, bh1, bl1;
+                split_tf32(xa, bh0, bl0);
+                split_tf32(xb, bh1, bl1);
+                __syncwarp();
+                ktile_mma<2>(acc[0], bh0, bl0, bh1, bl1, &w[2 * i]);
+            }
+        }
+    };
 
-        const uint32_t tag_now = (uint32_t)t + 1;      // values produced during step t
-        const uint32_t tag_prev = (uint32_t)t;         // values produced during step t-1 (t = 0: initial zeros -> skipped)
-        const int64_t rowoff = (int64_t)myrow;
-        // Segment descriptors first, ONE generic execution loop after: keeps the hot code small (the v3.0
-        // kernel inlined ~28 copies of the fragment pipeline, 164 KB of SASS, and thrashed the 32 KB
-        // instruction cache on every slot).
-        const uint64_t* sgA = nullptr; const uint64_t* sgB = nullptr;
-        int ntA = 0, ntB = 0, w0A = 0, w0B = 0, nsg = 0;
-        uint32_t tgA = 0, tgB = 0;
-#define SEG(bufoff, ld, width, wt0, tag)                                                              \
-        do {                                                                                          \
-            if (nsg == 0) { sgA = ws + (bufoff) + rowoff * (ld); ntA = (width) / 8; w0A = (wt0); tgA = (tag); } \
-            else          { sgB = ws + (bufoff) + rowoff * (ld); ntB = (width) / 8; w0B = (wt0); tgB = (tag); } \
-            ++nsg;                                                                                    \
-        } while (0)
-
-        switch (s) {
-            case K_P2: SEG(P.ws.p1, 256, 256, 0, tag_out); break;
-            case K_IN:                                   // y(t-1) here; ctx(t-1) merge and p2(t) follow below
-                if (t > 0) SEG(P.ws.ybuf, YLD, OUT, 0, tag_prev);
+    auto finish = [&](int stage, int t) {
+        float* part = part_s + par * 2048;
+        par ^= 1;
+        const bool full16 = (stage >= ST_G0 && stage <= ST_G2) || stage == ST_OQP;
+        store_partials(part, stage == ST_OQP ? 2 : 1, full16);
+        if (cktr) cktr[4] = clock64();
+        __syncthreads();
+        if (cktr) cktr[5] = clock64();
+        const int e = tid & 127, wcol = e >> 3, brow = e & 7, row = row0 + brow;
+        const uint32_t tag = (uint32_t)t + 1;
+        switch (stage) {
+            case ST_IN:
+                if (tid < 64) {
+                    float v = sum8(part, 0, e) + bias_s[BR_IN * 16 + wcol];
+                    if (t > 0) v += bias_s[BR_INX * 16 + wcol];
+                    z_loc[e] = v;
+                    ll_store(ws + P.buf[B_Z] + (int64_t)row * LD + 8 * cs + perm8(wcol), v, tag);
+                }
                 break;
-            case K_G1: case K_G2: case K_G3: {
-                const int gi = (s - K_G1) / 2;
-                const int64_t xoff = (gi == 0) ? P.ws.z : P.ws.h[gi - 1];
-                SEG(xoff, U, U, 0, tag_now);
-                if (t > 0) SEG(P.ws.h[gi], U, U, 32, tag_prev);
+            case ST_G0: case ST_G1: case ST_G2:
+                if (tid < 128) {
+                    const int gi = stage - ST_G0;
+                    const float gt = sigmoidf_acc(sum8(part, 0, e) + bias_s[(BR_G0 + gi) * 16 + wcol]);
+                    if (wcol < 8) ll_store(ws + P.buf[B_RH0 + gi] + (int64_t)row * LD + 8 * cs + perm8(wcol), gt * h_loc[gi * 64 + e], tag);   // r * h
+                    else u_loc[e - 64] = gt;                                                                                                  // u stays local
+                }
+                break;
+            case ST_C0: case ST_C1: case ST_C2:
+                if (tid < 64) {
+                    const int gi = stage - ST_C0;
+                    const float cnd = tanhf_acc(sum8(part, 0, e) + bias_s[(BR_C0 + gi) * 16 + wcol]);
+                    const float uu = u_loc[e];
+                    const float hn = uu * h_loc[gi * 64 + e] + (1.0f - uu) * cnd;
+                    h_loc[gi * 64 + e] = hn;
+                    const int col = 8 * cs + wcol;
+                    ll_store(ws + P.buf[B_H0 + gi] + (int64_t)row * LD + 8 * cs + perm8(wcol), hn, tag);
+                    if (A.h_save && row < B) A.h_save[(((int64_t)gi * T + t) * B + row) * U + col] = hn;   // training: BPTT input
+                    if (gi == 2) ll_store(ws + P.buf[B_S] + (int64_t)row * LD + 8 * cs + perm8(wcol), z_loc[e] + hn, tag);
+                }
+                break;
+            case ST_PM:
+                if (tid < 64) {                              // here t = tb, the step the pre-net output belongs to
+                    const int col = 8 * cs + wcol;
+                    float v = fmaxf(sum8(part, 0, e) + bias_s[BR_PM * 16 + wcol], 0.f);
+                    if (A.keep1 && row < B && t < T) v = A.keep1[((int64_t)t * B + row) * 256 + col] ? v * A.keep_scale : 0.f;
+                    ll_store(ws + P.buf[B_P1M] + (int64_t)row * LD + 8 * cs + perm8(wcol), v, tag);
+                }
+                break;
+            case ST_OQP: {
+                const int mt = tid >> 7;
+                const float v0 = sum8(part, mt, e) + bias_s[(BR_Y + mt) * 16 + wcol];
+                if (mt == 0) {                               // y(t): the output itself (nothing downstream reads it)
+                    const int col = cs * NCY + wcol;
+                    if (wcol < NCY && col < OUT && row < B) A.y[((int64_t)row * T + t) * OUT + col] = v0;
+                } else if (wcol < 8) {                       // q(t)
+                    ll_store(ws + P.buf[B_Q] + (int64_t)row * LD + 8 * cs + perm8(wcol), v0, tag);
+                } else {                                     // p1(t+1) of free-running rows
+                    const int c8 = wcol - 8, col = 8 * cs + c8, tb = t + 1;
+                    float v = fmaxf(v0, 0.f);
+                    if (A.keep1 && row < B && tb < T) v = A.keep1[((int64_t)tb * B + row) * 256 + col] ? v * A.keep_scale : 0.f;
+                    ll_store(ws + P.buf[B_P1Y] + (int64_t)row * LD + 8 * cs + perm8(c8), v, tag + 1);
+                }
             } break;
-            case K_C1: case K_C2: case K_C3: {
-                const int gi = (s - K_C1) / 2;
-                const int64_t xoff = (gi == 0) ? P.ws.z : P.ws.h[gi - 1];
-                SEG(xoff, U, U, 0, tag_now);
-                SEG(P.ws.rh[gi], U, U, 32, tag_now);
-            } break;
-            case K_OUT: SEG(P.ws.s, U, U, 0, tag_now); break;
-            case K_Q: SEG(P.ws.s, U, U, 0, tag_now); break;
             default: break;
         }
-#undef SEG
-        if (nsg == 2) {
-            if (NT == 2) seg2_ll<2>(acc, sgA, ntA, w0A, tgA, sgB, ntB, w0B, tgB, Wsl, warp, lane);
-            else         seg2_ll<1>(acc, sgA, ntA, w0A, tgA, sgB, ntB, w0B, tgB, Wsl, warp, lane);
-        } else if (nsg == 1) {
-            if (NT == 2) seg_ll<2>(acc, sgA, ntA, w0A, tgA, Wsl, warp, lane);
-            else         seg_ll<1>(acc, sgA, ntA, w0A, tgA, Wsl, warp, lane);
-        }
-        if (s == K_P1) {
-                // decoder input of step tb: last mel frame of the r-group (tacotron.py:66-67; helpers A.8-A.10)
-                //   INFER: y(tb-1) (zeros for tb = 0); TEACHER: mel[:, tb]; SCHED: per row, mask[tb-1] ? y(tb-1) : mel[:, tb]
-                bool from_y = true;
-                if (A.mode == TACO_DEC_TEACHER) from_y = false;
-                else if (A.mode == TACO_DEC_SCHED) from_y = (tb > 0) && (myrow < B) && (A.sample_mask[(int64_t)(tb - 1) * B + myrow] != 0);
-                const bool have = (myrow < B) && (tb < T) && (from_y ? (tb > 0) : true);
-                for (int kt = warp; kt < MF / 8; kt += NWARP) {
-                    float xa = 0.f, xb = 0.f;
-                    if (have) {
-                        if (from_y) {
-                            const float2 v = ll_wait2(ws + P.ws.ybuf + rowoff * YLD + (OUT - MF) + kt * 8 + 2 * tg, (uint32_t)tb);
-                            xa = v.x; xb = v.y;
-                        } else {
-                            const float* mp = A.mel + ((int64_t)myrow * T + tb) * OUT + (OUT - MF) + kt * 8 + tg;
-                            xa = __ldg(mp); xb = __ldg(mp + 4);
-                        }
-                    }
-                    float2 wf1[1];
-                    load_w<1>(wf1, Wsl + (size_t)kt * 64 + lane * 2);
-                    ktile_mma<1>(acc, xa, xb, wf1);
-                }
-        } else if (s == K_IN) {
-            if (t > 0) {                                 // everything here refers to step t-1: tag_prev
-                // ctx = flash-style merge of the four quarter partials, built directly in fragment form.
-                // (rows >= B have no partials: their lanes feed zeros; the MMAs below are warp-collective,
-                //  so every lane runs the same loop.)
-                {
-                    const bool live = myrow < B;
-                    float w[4] = {0.f, 0.f, 0.f, 0.f};
-                    if (live) {
-                        const uint64_t* ms = ws + P.ws.att_ms + rowoff * 8;
-                        float m[4], sq[4], M = -INFINITY;
-                        ulonglong2 mv[4];
-#pragma unroll
-                        for (int qd = 0; qd < 4; ++qd) mv[qd] = ll_load2(ms + 2 * qd);
-#pragma unroll
-                        for (int qd = 0; qd < 4; ++qd) {
-                            ll_spin(mv[qd], ms + 2 * qd, tag_prev);
-                            m[qd] = __uint_as_float((uint32_t)mv[qd].x); sq[qd] = __uint_as_float((uint32_t)mv[qd].y); M = fmaxf(M, m[qd]);
-                        }
-                        float S = 0.f;
-#pragma unroll
-                        for (int qd = 0; qd < 4; ++qd) { w[qd] = (m[qd] == -INFINITY) ? 0.f : __expf(m[qd] - M); S += w[qd] * sq[qd]; }
-                        const float inv = 1.0f / S;
-#pragma unroll
-                        for (int qd = 0; qd < 4; ++qd) w[qd] *= inv;
-                    }
-                    const uint64_t* cp = ws + P.ws.att_ctx + rowoff * 4 * ENC + 2 * tg + warp * 8;
-                    const float* wq = Wsl + (size_t)(OUT / 8 + warp) * 64 + lane * 2;
-                    // this warp's 4 ctx tiles (kt = warp + 8i), two at a time: 8 partial loads in flight
-#pragma unroll
-                    for (int ip = 0; ip < (ENC / 8) / NWARP; ip += 2) {
-                        ulonglong2 v[2][4];
-                        float2 wf1[2][1];
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            load_w<1>(wf1[u], wq + (size_t)(ip + u) * (NWARP * 64));
-                            if (live) {
-#pragma unroll
-                                for (int qd = 0; qd < 4; ++qd) v[u][qd] = ll_load2(cp + qd * ENC + (ip + u) * (NWARP * 8));
-                            }
-                        }
-#pragma unroll
-                        for (int u = 0; u < 2; ++u) {
-                            float xa = 0.f, xb = 0.f;
-                            if (live) {
-#pragma unroll
-                                for (int qd = 0; qd < 4; ++qd) {
-                                    ll_spin(v[u][qd], cp + qd * ENC + (ip + u) * (NWARP * 8), tag_prev);
-                                    xa = fmaf(w[qd], __uint_as_float((uint32_t)v[u][qd].x), xa);
-                                    xb = fmaf(w[qd], __uint_as_float((uint32_t)v[u][qd].y), xb);
-                                }
-                            }
-                            ktile_mma<1>(acc, xa, xb, wf1[u]);
-                        }
-                    }
-                }
-                finalize_align(t - 1, tag_prev);
-            }
-            // p2(t) last: it was produced one slot ago; its words arrive while the two segments above run
-            seg_ll<1>(acc, ws + P.ws.p2 + rowoff * 128, 16, (OUT + ENC) / 8, tag_now, Wsl, warp, lane);
-        }
-        if (tracer) ctrace[1] = (uint64_t)clock64();
-        // ---- per-warp partial tiles -> shared memory (rows 0..7 of the 16x8 accumulator are the real rows) ----
-        float* part = part_s + (sl & 1) * (NWARP * 128);
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
-            if (nt < NT) *reinterpret_cast<float2*>(part + (warp * 2 + nt) * 64 + g * 8 + 2 * tg) =
-                make_float2((acc[0][nt][0] + acc[1][nt][0]) + acc[2][nt][0], (acc[0][nt][1] + acc[1][nt][1]) + acc[2][nt][1]);
-        __syncthreads();
-        if (tracer) ctrace[2] = (uint64_t)clock64();
+        if (cktr) cktr[6] = clock64();
+        if (tracer) ws[P.trace_off + (trace_i++)] = globaltimer_ns();
+    };
 
-        // =============== cross-warp sum + stage epilogue: one thread per output ===============
-        if (tid < 64 * NT) {
-            const int nt = tid >> 6, rr = (tid >> 3) & 7, c = tid & 7;
-            float v = 0.f;
-#pragma unroll
-            for (int w = 0; w < NWARP; ++w) v += part[(w * 2 + nt) * 64 + rr * 8 + c];
-            const int j = nt * 8 + c;                       // local column in the slice
-            const int row = row0 + rr;
-            const int col = stage_col(s, cs, j, d.NCV, d.N);
-            const int64_t ro = (int64_t)row;
-            v += bias_s[s * 16 + j];
-            if (col >= 0) {
-                switch (s) {
-                    case K_P1: {
-                        v = fmaxf(v, 0.f);
-                        if (A.keep1 && row < B && tb < T) v = A.keep1[((int64_t)tb * B + row) * 256 + col] ? v * A.keep_scale : 0.f;
-                        ll_store(ws + P.ws.p1 + ro * 256 + perm8(col), v, tag_out);
-                    } break;
-                    case K_P2: {
-                        v = fmaxf(v, 0.f);
-                        if (A.keep2 && row < B && tb < T) v = A.keep2[((int64_t)tb * B + row) * 128 + col] ? v * A.keep_scale : 0.f;
-                        ll_store(ws + P.ws.p2 + ro * 128 + perm8(col), v, tag_out);
-                    } break;
-                    case K_IN: {
-                        z_loc[rr * 8 + j] = v;
-                        ll_store(ws + P.ws.z + ro * U + perm8(col), v, tag_out);
-                    } break;
-                    case K_G1: case K_G2: case K_G3: {
-                        const int gi = (s - K_G1) / 2;
-                        const float gt = sigmoidf_acc(v);
-                        if (j < 8) ll_store(ws + P.ws.rh[gi] + ro * U + perm8(col), gt * h_loc[gi * 64 + rr * 8 + j], tag_out);   // r * h
-                        else u_loc[rr * 8 + (j - 8)] = gt;                                                                       // u stays local
-                    } break;
-                    case K_C1: case K_C2: case K_C3: {
-                        const int gi = (s - K_C1) / 2;
-                        const float cnd = tanhf_acc(v);
-                        const float uu = u_loc[rr * 8 + j];
-                        const float hn = uu * h_loc[gi * 64 + rr * 8 + j] + (1.0f - uu) * cnd;
-                        h_loc[gi * 64 + rr * 8 + j] = hn;
-                        ll_store(ws + P.ws.h[gi] + ro * U + perm8(col), hn, tag_out);
-                        if (A.h_save && row < B) A.h_save[(((int64_t)gi * T + t) * B + row) * U + col] = hn;   // training: BPTT input
-                        if (gi == 2) ll_store(ws + P.ws.s + ro * U + perm8(col), z_loc[rr * 8 + j] + hn, tag_out);
-                    } break;
-                    case K_OUT: {
-                        ll_store(ws + P.ws.ybuf + ro * YLD + perm8(col), v, tag_out);
-                        if (row < B) A.y[((int64_t)row * T + t) * OUT + col] = v;
-                    } break;
-                    case K_Q: ll_store(ws + P.ws.q + ro * AU + perm8(col), v, tag_out); break;
-                }
+    // =========================================================================================================
+    // prologue: p1(0) (teacher frame 0 or zeros), p2(0)
+    // =========================================================================================================
+    prenet1_teacher(0);
+    finish(ST_PM, 0);
+    if (warp >= 4) prenet2(0);
+
+    // =========================================================================================================
+    // T decoder steps x the item program
+    // =========================================================================================================
+    for (int t = 0; t < T; ++t) {
+        if (tracer) A.step_ns[t] = globaltimer_ns();
+        for (int ii = 0; ii < P.n_items; ++ii) {
+            const Item& it = P.items[ii];
+            if (it.stage == ST_AP2) {
+                if (warp < 4) attention(t);
+                else if (t + 1 < T) prenet2(t + 1);
+                if (tracer) ws[P.trace_off + (trace_i++)] = globaltimer_ns();
+                continue;
             }
+            if (it.stage == ST_PM) {
+                if (t + 1 < T) { prenet1_teacher(t + 1); finish(ST_PM, t + 1); }
+                continue;
+            }
+            long long* ck = nullptr;
+            if (tracer && t >= 10 && t < 14) { ck = reinterpret_cast<long long*>(ws + P.trace_off + 16 * T + 16 + ((t - 10) * MAX_ITEMS + ii) * 8); ck[3] = clock64(); }
+            cktr = ck;
+            if (!(it.skip_t0 && t == 0)) {
+                const SegDesc& sd = P.seg[it.seg];
+                const uint64_t* rowp = ws + P.buf[it.src] + (int64_t)myrow * LD;
+                const bool live = (it.src != B_CTX) || (myrow < B);       // padding utterances have no attention cluster output
+                const uint32_t tag = (uint32_t)(t + it.tagd);
+                if (it.seg2 >= 0)      seg_mma<4, 2>(acc, sd, P.seg[it.seg2], res_s, tm_lane_col, rowp, live, tag, warp, NWARP, 0, lane, ck);
+                else if (sd.FL == 4)   seg_mma<4, 1>(acc, sd, sd, res_s, tm_lane_col, rowp, live, tag, warp, NWARP, 0, lane, ck);
+                else                   seg_mma<2, 1>(acc, sd, sd, res_s, tm_lane_col, rowp, live, tag, warp, NWARP, 0, lane, ck);
+            }
+            if (it.stage != ST_NONE) finish(it.stage, t);
         }
-        if (tracer) ctrace[3] = (uint64_t)clock64();
-        // hazards: part_s alternates by slot parity; loc arrays are ordered by the next slot's __syncthreads
     }
-    finalize_align(T - 1, (uint32_t)T);                 // the last step has no following K_IN slot
+
+    // ---- teardown: nobody may leave while a peer can still push into its shared memory; free the TMEM ----
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
 }
 
-// ---- packing: TF [K][N] -> per-slice MMA B fragments [cs][k-tile][nt][lane][2], optional gate permutation ----
-__global__ void pack_stage_kernel(const float* __restrict__ W, int K, int N, int NCV, int NT, int kind, float* __restrict__ dst) {
-    const int KT = K / 8;
-    const int64_t total = (int64_t)NS * KT * NT * 64;
+// ---- packing: TF [K][N] -> per-slice MMA A fragments [cs][warp][k-tile slot][lane][FL] ----
+__global__ void pack_seg_kernel(const float* __restrict__ W, int ldw, int k0, int K, int FL, int nw, int kpw, int sg, int NCY, int OUT,
+                                float* __restrict__ dst) {
+    const int slice = nw * kpw * 32 * FL;
+    const int64_t total = (int64_t)NS * slice;
+    const int nkt = K / 8;
     for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int e = (int)(idx & 1);
-        const int lane = (int)((idx >> 1) & 31);
-        int64_t rest = idx >> 6;
-        const int nt = (int)(rest % NT); rest /= NT;
-        const int kt = (int)(rest % KT);
-        const int cs = (int)(rest / KT);
+        const int cs = (int)(idx / slice);
+        int r = (int)(idx % slice);
+        const int e = r % FL; r /= FL;
+        const int lane = r & 31; r >>= 5;
+        const int i = r % kpw;
+        const int widx = r / kpw;
+        const int kt = widx + nw * i;
         const int g = lane >> 2, tg = lane & 3;
-        const int k = kt * 8 + tg + 4 * e;                    // b0: k = tg, b1: k = tg + 4 ; column n = g
-        const int col = stage_col(kind, cs, nt * 8 + g, NCV, N);
-        dst[idx] = (col >= 0) ? W[(int64_t)k * N + col] : 0.0f;
+        // FL = 4: e = (k, m=g), (k, m=g+8), (k+4, m=g), (k+4, m=g+8);  FL = 2: e = (k, m=g), (k+4, m=g)
+        const int m = (FL == 4) ? g + 8 * (e & 1) : g;
+        const int k = kt * 8 + tg + 4 * ((FL == 4) ? (e >> 1) : e);
+        float v = 0.f;
+        if (kt < nkt) {
+            const int col = seg_col(sg, cs, m, NCY, OUT);
+            if (col >= 0) v = W[(int64_t)(k0 + k) * ldw + col];
+        }
+        dst[idx] = v;
     }
 }
 
-// ---- fused linear stages (weight-only precompute, once per weight update) ----------------------------------
-//   K_IN :  z(t) = p2(t).W_in[0:128] + attn(t-1).W_in[128:384] + b_in, attn(t-1) = [y(t-1), ctx(t-1)].W_a  (no bias,
-//           no non-linearity in between)  =>  z(t) = [y(t-1) | ctx(t-1) | p2(t)] . W_inF + b_in with
-//           W_inF = [ W_a . W_in[128:384] ; W_in[0:128] ]                 ((80r+256+128) x 256)
-//   K_Q  :  q(t) = y(t).W_q, y(t) = s(t).W_out + b_out  =>  q(t) = s(t).(W_out.W_q) + b_out.W_q      (256 x 256)
-// The attention state itself (attn) is consumed by nothing else (tacotron.py:64-71), so it is never formed.
-// This removes the K_AL slot and two dependent L2 hops from every decoder step; sums are re-associated
-// (differences ~1e-6 relative, inside the stated fp32 tolerance).
+// weight-only precompute (double accumulation): C = A . B (+ addv)
 __global__ void matmul_naive_kernel(const float* __restrict__ Amat, int lda, const float* __restrict__ Bmat, int ldb,
-                                    float* __restrict__ Cmat, int ldc, int M, int N, int K) {
+                                    float* __restrict__ Cmat, int ldc, int M, int N, int K, const float* __restrict__ addv) {
     const int64_t total = (int64_t)M * N;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int m = (int)(i / N), n = (int)(i % N);
-        double acc = 0.0;                                   // weight-only precompute: accumulate in double
-        for (int k = 0; k < K; ++k) acc += (double)Amat[(int64_t)m * lda + k] * (double)Bmat[(int64_t)k * ldb + n];
-        Cmat[(int64_t)m * ldc + n] = (float)acc;
+        double a = addv ? (double)addv[n] : 0.0;
+        for (int k = 0; k < K; ++k) a += (double)Amat[(int64_t)m * lda + k] * (double)Bmat[(int64_t)k * ldb + n];
+        Cmat[(int64_t)m * ldc + n] = (float)a;
     }
 }
-__global__ void copy_rows_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t n) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
-}
-struct FusedTail { int64_t w_inF, w_qF, b_qF, total; };    // float offsets inside the packed buffer
+
+// ---- fused linear stages (weight-only algebra; sums are re-associated, ~1e-6 relative) --------------------------
+//   W_ctxF = W_a[80r:80r+256] . W_in[128:384]                       ctx(t-1) -> z(t)
+//   M1     = W_a[0:80r] . W_in[128:384];  W_sF = W_out . M1;  b_inS = b_out . M1        y(t-1) = s(t-1).W_out + b_out -> z(t)
+//   W_qp   = [ W_out . W_q | W_out[:, last 80] . W1 ];  b_qF = b_out . W_q;  b_p1F = b_out[last 80] . W1 + b1
+struct FusedTail { int64_t w_ctxF, m1, w_sF, w_qp, b_qF, b_p1F, b_inS, total; };
 FusedTail fused_tail(int r, int64_t slices_total) {
     const int OUT = MF * r;
     FusedTail f;
-    f.w_inF = (slices_total + 63) / 64 * 64;
-    f.w_qF = f.w_inF + (int64_t)(OUT + ENC + 128) * U;
-    f.b_qF = f.w_qF + (int64_t)U * AU;
-    f.total = f.b_qF + AU;
+    int64_t o = (slices_total + 63) / 64 * 64;
+    f.w_ctxF = o; o += (int64_t)ENC * U;
+    f.m1 = o;     o += (int64_t)OUT * U;
+    f.w_sF = o;   o += (int64_t)U * U;
+    f.w_qp = o;   o += (int64_t)U * 2 * AU;
+    f.b_qF = o;   o += AU;
+    f.b_p1F = o;  o += 256;
+    f.b_inS = o;  o += U;
+    f.total = o;
     return f;
 }
 
-void build_stage_table(int r, StageDesc* st, int64_t* total_floats) {
-    const int OUT = MF * r;
+void build_seg_table(SegDesc* sd, int64_t* total_floats) {
+    auto set = [&](int id, int K, int FL, int nw, int kpw) { sd[id].K = K; sd[id].FL = FL; sd[id].nw = nw; sd[id].kpw = kpw; };
+    set(SG_IN_S, 256, 2, 8, 4); set(SG_IN_CTX, 256, 2, 8, 4); set(SG_IN_P2, 128, 2, 8, 4);
+    for (int i = 0; i < 3; ++i) {
+        set(SG_G_H0 + i, 256, 4, 8, 4); set(SG_G_X0 + i, 256, 4, 8, 4);
+        set(SG_C_X0 + i, 256, 2, 8, 4); set(SG_C_RH0 + i, 256, 2, 8, 4);
+    }
+    set(SG_Y, 256, 4, 8, 4); set(SG_QP, 256, 4, 8, 4); set(SG_PM, MF, 2, 8, 4); set(SG_P2, 256, 2, 4, 8);
     int64_t off = 0;
-    for (int s = 0; s < NSTAGE; ++s) {
-        int K0, K1, N, NCV;
-        stage_dims(s, OUT, K0, K1, N, NCV);
-        st[s].K0 = K0; st[s].K1 = K1; st[s].N = N; st[s].NCV = NCV; st[s].NT = (NCV + 7) / 8;
-        st[s].w_off = off; st[s].res_off = -1;
-        off += (int64_t)NS * (K0 + K1) * st[s].NT * 8;
+    for (int s = 0; s < NSEG; ++s) {
+        sd[s].slice_floats = sd[s].nw * sd[s].kpw * 32 * sd[s].FL;
+        sd[s].g_off = off; sd[s].smem_off = -1; sd[s].tmem_col = 0;
+        off += (int64_t)NS * sd[s].slice_floats;
     }
     *total_floats = off;
 }
 
-void build_ws_layout(DecLayout* L) {
+void build_ws_layout(int64_t* buf, int64_t* total) {
     int64_t o = 0;
-    auto take = [&](int64_t n) { int64_t r = o; o += (n + 31) / 32 * 32; return r; };
-    L->p1 = take(BPAD * 256); L->p2 = take(BPAD * 128); L->attn = take(BPAD * AU); L->z = take(BPAD * U);
-    for (int i = 0; i < 3; ++i) L->h[i] = take(BPAD * U);
-    for (int i = 0; i < 3; ++i) L->rh[i] = take(BPAD * U);
-    L->s = take(BPAD * U); L->ybuf = take(BPAD * YLD);
-    L->q = take(BPAD * AU); L->att_ms = take(BPAD * 8); L->att_ctx = take(BPAD * 4 * ENC);
-    L->total = o;
+    for (int b = 0; b < NBUF; ++b) { buf[b] = o; o += (int64_t)BPAD * LD; }
+    *total = o;
 }
+
+inline int trace_words(int T) { return 16 * (T > 0 ? T : 0) + 16 + 4 * MAX_ITEMS * 8 + 16; }
 
 }  // namespace
 
 extern "C" size_t taco_decoder_packed_bytes(int r) {
-    StageDesc st[NSTAGE]; int64_t tot;
-    build_stage_table(r, st, &tot);
+    SegDesc sd[NSEG]; int64_t tot;
+    build_seg_table(sd, &tot);
     return (size_t)fused_tail(r, tot).total * 4;
 }
 
 extern "C" size_t taco_decoder_workspace_bytes(int B, int Tx, int T, int r) {
     (void)B; (void)Tx; (void)r;
-    DecLayout L; build_ws_layout(&L);
-    return (size_t)(L.total + 5 * (2 + (int64_t)NSTAGE * (T > 0 ? T : 0)) + 32) * 8;
+    int64_t buf[NBUF], total;
+    build_ws_layout(buf, &total);
+    return (size_t)(total + trace_words(T)) * 8;
 }
 
 extern "C" int taco_decoder_pack(const taco_decoder_weights* w, int r, float* packed, void* stream) {
     TACO_CHECK(w && packed, "taco_decoder_pack: NULL");
     TACO_CHECK(r >= 1 && MF * r <= 512, "taco_decoder_pack: r=%d out of range (80r <= 512)", r);
-    StageDesc st[NSTAGE]; int64_t tot;
-    build_stage_table(r, st, &tot);
+    TACO_CHECK(w->att_Wa && w->in_W && w->out_W && w->att_Wq && w->out_b && w->pre_W1 && w->pre_b1 && w->pre_W2, "taco_decoder_pack: NULL weight");
+    for (int i = 0; i < 3; ++i) TACO_CHECK(w->gru_Wg[i] && w->gru_Wc[i], "taco_decoder_pack: NULL GRU weight");
+    SegDesc sd[NSEG]; int64_t tot;
+    build_seg_table(sd, &tot);
     cudaStream_t stm = (cudaStream_t)stream;
     const int OUT = MF * r;
+    const int NCY = (OUT + NS - 1) / NS;
     const FusedTail ft = fused_tail(r, tot);
-    float* w_inF = packed + ft.w_inF;
-    float* w_qF = packed + ft.w_qF;
-    float* b_qF = packed + ft.b_qF;
-    TACO_CHECK(w->att_Wa && w->in_W && w->out_W && w->att_Wq && w->out_b, "taco_decoder_pack: NULL weight");
-    // W_inF rows [0, OUT+256) = W_a . W_in[128:384]; rows [OUT+256, OUT+384) = W_in[0:128]
-    matmul_naive_kernel<<<592, 256, 0, stm>>>(w->att_Wa, AU, w->in_W + (int64_t)128 * U, U, w_inF, U, OUT + ENC, U, AU);
+    float *w_ctxF = packed + ft.w_ctxF, *m1 = packed + ft.m1, *w_sF = packed + ft.w_sF, *w_qp = packed + ft.w_qp;
+    const float* w_inA = w->in_W + (int64_t)128 * U;           // W_in[128:384]
+    matmul_naive_kernel<<<256, 256, 0, stm>>>(w->att_Wa + (int64_t)OUT * AU, AU, w_inA, U, w_ctxF, U, ENC, U, AU, nullptr);
     TACO_LAUNCH_CHECK();
-    copy_rows_kernel<<<64, 256, 0, stm>>>(w->in_W, w_inF + (int64_t)(OUT + ENC) * U, (int64_t)128 * U);
+    matmul_naive_kernel<<<400, 256, 0, stm>>>(w->att_Wa, AU, w_inA, U, m1, U, OUT, U, AU, nullptr);
     TACO_LAUNCH_CHECK();
-    // W_qF = W_out . W_q ; b_qF = b_out . W_q
-    matmul_naive_kernel<<<256, 256, 0, stm>>>(w->out_W, OUT, w->att_Wq, AU, w_qF, AU, U, AU, OUT);
+    matmul_naive_kernel<<<256, 256, 0, stm>>>(w->out_W, OUT, m1, U, w_sF, U, U, U, OUT, nullptr);
     TACO_LAUNCH_CHECK();
-    matmul_naive_kernel<<<1, 256, 0, stm>>>(w->out_b, OUT, w->att_Wq, AU, b_qF, AU, 1, AU, OUT);
+    matmul_naive_kernel<<<1, 256, 0, stm>>>(w->out_b, OUT, m1, U, packed + ft.b_inS, U, 1, U, OUT, nullptr);
     TACO_LAUNCH_CHECK();
-    const float* src[NSTAGE] = {w->pre_W1, w->pre_W2, w_inF, w->gru_Wg[0], w->gru_Wc[0], w->gru_Wg[1], w->gru_Wc[1],
-                                w->gru_Wg[2], w->gru_Wc[2], w->out_W, w_qF, nullptr, nullptr};
-    for (int s = 0; s < NSTAGE; ++s) {
-        if (s == K_ATT || s == K_AL) continue;
-        TACO_CHECK(src[s] != nullptr, "taco_decoder_pack: weight %d is NULL", s);
-        const int K = st[s].K0 + st[s].K1;
-        const int64_t total = (int64_t)NS * K * st[s].NT * 8;
+    matmul_naive_kernel<<<256, 256, 0, stm>>>(w->out_W, OUT, w->att_Wq, AU, w_qp, 2 * AU, U, AU, OUT, nullptr);
+    TACO_LAUNCH_CHECK();
+    matmul_naive_kernel<<<256, 256, 0, stm>>>(w->out_W + (OUT - MF), OUT, w->pre_W1, 256, w_qp + AU, 2 * AU, U, 256, MF, nullptr);
+    TACO_LAUNCH_CHECK();
+    matmul_naive_kernel<<<1, 256, 0, stm>>>(w->out_b, OUT, w->att_Wq, AU, packed + ft.b_qF, AU, 1, AU, OUT, nullptr);
+    TACO_LAUNCH_CHECK();
+    matmul_naive_kernel<<<1, 256, 0, stm>>>(w->out_b + (OUT - MF), MF, w->pre_W1, 256, packed + ft.b_p1F, 256, 1, 256, MF, w->pre_b1);
+    TACO_LAUNCH_CHECK();
+
+    struct Src { const float* W; int ld; int k0; };
+    Src src[NSEG];
+    src[SG_IN_S] = {w_sF, U, 0}; src[SG_IN_CTX] = {w_ctxF, U, 0}; src[SG_IN_P2] = {w->in_W, U, 0};
+    for (int i = 0; i < 3; ++i) {
+        src[SG_G_X0 + i] = {w->gru_Wg[i], 2 * U, 0};  src[SG_G_H0 + i] = {w->gru_Wg[i], 2 * U, U};     // rows: x then h (TF 1.2 GRUCell)
+        src[SG_C_X0 + i] = {w->gru_Wc[i], U, 0};      src[SG_C_RH0 + i] = {w->gru_Wc[i], U, U};
+    }
+    src[SG_Y] = {w->out_W, OUT, 0}; src[SG_QP] = {w_qp, 2 * AU, 0}; src[SG_PM] = {w->pre_W1, 256, 0}; src[SG_P2] = {w->pre_W2, 128, 0};
+    for (int s = 0; s < NSEG; ++s) {
+        const int64_t total = (int64_t)NS * sd[s].slice_floats;
         const int blocks = (int)((total + 255) / 256);
-        pack_stage_kernel<<<blocks, 256, 0, stm>>>(src[s], K, st[s].N, st[s].NCV, st[s].NT, s, packed + st[s].w_off);
+        pack_seg_kernel<<<blocks, 256, 0, stm>>>(src[s].W, src[s].ld, src[s].k0, sd[s].K, sd[s].FL, sd[s].nw, sd[s].kpw, s, NCY, OUT, packed + sd[s].g_off);
         TACO_LAUNCH_CHECK();
     }
     return 0;
@@ -837,50 +898,83 @@ extern "C" int taco_decoder_pack(const taco_decoder_weights* w, int r, float* pa
 extern "C" int taco_decoder_fwd(const taco_decoder_args* a, void* stream) {
     TACO_CHECK(a, "taco_decoder_fwd: NULL args");
     TACO_CHECK(a->weights != nullptr, "taco_decoder_fwd: weights (biases, attention_v) is NULL");
-    const taco_decoder_weights& g_dec_w = *a->weights;
+    const taco_decoder_weights& W = *a->weights;
     TACO_CHECK(a->B >= 1 && a->B <= BPAD, "taco_decoder_fwd: B=%d must be in [1,%d] per launch", a->B, BPAD);
     TACO_CHECK(a->T >= 1, "taco_decoder_fwd: T=%d", a->T);
     TACO_CHECK(a->Tx >= 1 && a->Tx <= 256, "taco_decoder_fwd: Tx=%d must be in [1, 256]", a->Tx);
-    TACO_CHECK(a->r >= 1 && MF * a->r <= 512 - 8, "taco_decoder_fwd: r=%d unsupported (80r must be <= 504)", a->r);
+    TACO_CHECK(a->r >= 1 && MF * a->r <= 512, "taco_decoder_fwd: r=%d unsupported (80r must be <= 512)", a->r);
     TACO_CHECK(a->packed && a->keys && a->values && a->text_length && a->y && a->align && a->workspace, "taco_decoder_fwd: NULL pointer");
-    TACO_CHECK((reinterpret_cast<uintptr_t>(a->workspace) & 15) == 0, "taco_decoder_fwd: workspace must be 16-byte aligned");
+    TACO_CHECK((reinterpret_cast<uintptr_t>(a->workspace) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->packed) & 15) == 0,
+               "taco_decoder_fwd: workspace / packed must be 16-byte aligned");
     if (a->mode != TACO_DEC_INFER) TACO_CHECK(a->mel != nullptr, "taco_decoder_fwd: teacher/sched mode needs mel");
     if (a->mode == TACO_DEC_SCHED) TACO_CHECK(a->sample_mask != nullptr, "taco_decoder_fwd: sched mode needs sample_mask");
     TACO_CHECK((a->keep1 == nullptr) == (a->keep2 == nullptr), "taco_decoder_fwd: keep1/keep2 must both be set or both NULL");
     cudaStream_t st = (cudaStream_t)stream;
 
-    DecParams P;
+    static DecParams P;                                  // (kept off the stack; a decoder launch is not re-entrant)
     memset(&P, 0, sizeof(P));
-    int64_t tot;
-    build_stage_table(a->r, P.st, &tot);
-    build_ws_layout(&P.ws);
+    int64_t tot, ws_total;
+    build_seg_table(P.seg, &tot);
+    build_ws_layout(P.buf, &ws_total);
+    P.trace_off = ws_total;
     P.a = *a;
     P.OUT = MF * a->r;
+    P.NCY = (P.OUT + NS - 1) / NS;
     P.Tq = (a->Tx + 3) / 4;            // quarter width; the last quarter is ragged when Tx % 4 != 0
-    TACO_CHECK(P.Tq <= 64, "taco_decoder_fwd: Tx/4 = %d > 64", P.Tq);
-    TACO_CHECK(P.OUT / 8 <= MAXT * NWARP, "taco_decoder_fwd: 80r too wide for the fragment pipeline");
-    P.pre_b1 = g_dec_w.pre_b1; P.pre_b2 = g_dec_w.pre_b2; P.in_b = g_dec_w.in_b; P.out_b = g_dec_w.out_b; P.att_v = g_dec_w.att_v;
-    for (int i = 0; i < 3; ++i) { P.gru_bg[i] = g_dec_w.gru_bg[i]; P.gru_bc[i] = g_dec_w.gru_bc[i]; }
-    P.q_bias = a->packed + fused_tail(a->r, tot).b_qF;
+    TACO_CHECK(P.Tq <= 64 && P.NCY <= 16, "taco_decoder_fwd: Tx/4 = %d > 64 or 80r/32 > 16", P.Tq);
+    P.in_b = W.in_b; P.out_b = W.out_b; P.pre_b1 = W.pre_b1; P.pre_b2 = W.pre_b2; P.att_v = W.att_v;
+    for (int i = 0; i < 3; ++i) { P.gru_bg[i] = W.gru_bg[i]; P.gru_bc[i] = W.gru_bc[i]; }
+    const FusedTail ft = fused_tail(a->r, tot);
+    P.b_qF = a->packed + ft.b_qF; P.b_p1F = a->packed + ft.b_p1F; P.b_inS = a->packed + ft.b_inS;
 
-    // shared-memory plan
-    int off = 64 + 2 * NWARP * 128 + 512 + 256 + 1024;
+    // ---- the per-step program ----
+    int n = 0;
+    auto item = [&](int seg, int seg2, int src, int tagd, int stage, int skip0) { P.items[n++] = Item{seg, seg2, src, tagd, stage, skip0}; };
+    item(SG_IN_S, -1, B_S, 0, ST_NONE, 1);                         // off-chain: s(t-1)
+    item(SG_IN_CTX, -1, B_CTX, 0, ST_NONE, 1);
+    item(SG_IN_P2, -1, B_P2, 1, ST_IN, 0);
+    for (int i = 0; i < 3; ++i) {
+        const int x = (i == 0) ? B_Z : B_H0 + (i - 1);
+        item(SG_G_H0 + i, -1, B_H0 + i, 0, ST_NONE, 1);            // off-chain: h_i(t-1)
+        item(SG_G_X0 + i, -1, x, 1, ST_G0 + i, 0);
+        item(SG_C_X0 + i, -1, x, 1, ST_NONE, 0);                   // off-chain: x (already consumed by the gate stage)
+        item(SG_C_RH0 + i, -1, B_RH0 + i, 1, ST_C0 + i, 0);
+    }
+    if (a->mode != TACO_DEC_INFER) item(SG_PM, -1, B_MEL, 0, ST_PM, 0);   // teacher frame t+1 -> p1m(t+1), off-chain
+    item(SG_Y, SG_QP, B_S, 1, ST_OQP, 0);
+    item(-1, -1, 0, 0, ST_AP2, 0);
+    P.n_items = n;
+
+    // ---- residency: off-chain segments in TMEM (256 columns per warp), on-chain segments in shared memory; when the
+    //      keys/values leave too little shared memory (large Tx) further segments move to TMEM ----
+    int off = 16 + 4096 + 256 + 384 + 256 + 704 + 1024 + 64;
     off = (off + 31) / 32 * 32;
     P.smem_kv_off = off;
     off += P.Tq * KV_LD + P.Tq * ENC;
     off = (off + 31) / 32 * 32;
-    P.smem_stream_off = off;
-    off += 2 * STREAM_FLOATS;
     P.smem_res_off = off;
-    const int max_floats = (227 * 1024) / 4;
-    const int budget = max_floats - off;
-    // greedy residency: biggest per-step traffic first (GRU gates, candidates, attention layer, ...)
-    const int order[] = {K_G1, K_G2, K_G3, K_C1, K_C2, K_C3, K_IN, K_OUT, K_Q, K_P2, K_P1};
+    const int budget = (227 * 1024) / 4 - off;
+    const int tm_first[] = {SG_IN_S, SG_G_H0, SG_G_H1, SG_G_H2, SG_C_X0, SG_C_X1, SG_C_X2, SG_PM};
+    const int sm_order[] = {SG_G_X0, SG_C_RH0, SG_G_X1, SG_C_RH1, SG_G_X2, SG_C_RH2, SG_QP, SG_Y, SG_IN_CTX, SG_IN_P2, SG_P2};
+    int tcol8 = 0, tcol4 = 0;            // TMEM columns used in the half of warps 0-3 / 4-7 (8-warp segments use both halves)
+    auto to_tmem = [&](int s) {
+        const int cols = P.seg[s].kpw * P.seg[s].FL;
+        if (P.seg[s].nw == NWARP) {
+            const int c = tcol8 > tcol4 ? tcol8 : tcol4;
+            if (c + cols > 256) return false;
+            P.seg[s].tmem_col = c; tcol8 = tcol4 = c + cols;
+        } else {
+            if (tcol4 + cols > 256) return false;
+            P.seg[s].tmem_col = tcol4; tcol4 += cols;
+        }
+        P.seg[s].smem_off = -1;
+        return true;
+    };
+    for (int s : tm_first) TACO_CHECK(to_tmem(s), "taco_decoder_fwd: TMEM plan overflow");
     int res = 0;
-    for (int i = 0; i < 11; ++i) {
-        StageDesc& d = P.st[order[i]];
-        const int fl = (d.K0 + d.K1) * d.NT * 8;
-        if (fl <= budget - res) { d.res_off = res; res += fl; }
+    for (int s : sm_order) {
+        if (P.seg[s].slice_floats <= budget - res) { P.seg[s].smem_off = res; res += P.seg[s].slice_floats; }
+        else TACO_CHECK(to_tmem(s), "taco_decoder_fwd: weights do not fit in shared + tensor memory (Tx=%d)", a->Tx);
     }
     P.smem_total_floats = off + res;
     const size_t smem_bytes = (size_t)P.smem_total_floats * 4;
@@ -890,9 +984,20 @@ extern "C" int taco_decoder_fwd(const taco_decoder_args* a, void* stream) {
         TACO_CUDA(cudaFuncSetAttribute(decoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
-    TACO_CUDA(cudaMemsetAsync(a->workspace, 0, (size_t)P.ws.total * 8, st));
-    void* args[] = {(void*)&P};
-    TACO_CUDA(cudaLaunchCooperativeKernel((void*)decoder_kernel, dim3(NCTA), dim3(NTHR), args, smem_bytes, st));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(NCTA); cfg.blockDim = dim3(NTHR); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = st;
+    // all 32 clusters (128 CTAs) must be co-resident: the kernel is a dataflow machine without a grid barrier
+    static int max_clusters = -1;
+    if (max_clusters < 0) {
+        cudaLaunchConfig_t q = cfg; q.dynamicSmemBytes = 227 * 1024;
+        int nc = 0;
+        TACO_CUDA(cudaOccupancyMaxActiveClusters(&nc, (void*)decoder_kernel, &q));
+        max_clusters = nc;
+    }
+    TACO_CHECK(max_clusters >= NCTA / 4, "taco_decoder_fwd: only %d clusters of 4 CTAs can be co-resident on this device (need %d)", max_clusters, NCTA / 4);
+    TACO_CUDA(cudaMemsetAsync(a->workspace, 0, (size_t)ws_total * 8, st));
+    TACO_CUDA(cudaLaunchKernelEx(&cfg, decoder_kernel, P));
     ++g_taco_launches;
     return 0;
 }

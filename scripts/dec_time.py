@@ -22,7 +22,7 @@ print("LL mode", os.environ.get("TACO_DEC_LL", "default"), "decoder ms", statist
 if os.environ.get("TACO_TRACE"):
     import numpy as np
     ws = m.runtime.dec_ws.view(torch.int64).cpu().numpy()
-    total = 13 * 32 * 256                       # NBUF exchange buffers of [32][256] words (decoder.cu build_ws_layout)
+    total = (11 * 32 + 48) * 4 * 64             # exchange buffers [4 row groups][nkt][8][8] words (decoder.cu build_ws_layout)
     names = ["IN", "G1", "C1", "G2", "C2", "G3", "C3", "OQP", "A|P2"]
     n = 1 + len(names) * T
     tr = ws[total: total + n]
@@ -31,7 +31,7 @@ if os.environ.get("TACO_TRACE"):
     med = np.median(d, axis=0)
     print("per-slot median ns (CTA 0):", {n_: int(v) for n_, v in zip(names, med)}, "sum", int(med.sum()))
     ck = ws[total + 16 * T + 16: total + 16 * T + 16 + 4 * 20 * 8].reshape(4, 20, 8)
-    inames = ["IN_S", "IN_CTX", "IN_P2*", "G_H0", "G_X0*", "C_X0", "C_RH0*", "G_H1", "G_X1*", "C_X1", "C_RH1*", "G_H2", "G_X2*", "C_X2", "C_RH2*", "OQP*", "AP2"]
+    inames = ["IN_S", "IN_CP*", "G_H0", "G_X0*", "C_X0", "C_RH0*", "G_H1", "G_X1*", "C_X1", "C_RH1*", "G_H2", "G_X2*", "C_X2", "C_RH2*", "OQP*", "AP2"]
     print("item: start->loads-issued | ->weights | ->mma done | (finish) ->partials | ->sync | ->epilogue   [cycles, CTA0 thread0, step 11]")
     st = 1
     for i, nm in enumerate(inames):

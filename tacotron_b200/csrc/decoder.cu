@@ -63,27 +63,33 @@ constexpr int AU = 256;        // attention units
 constexpr int ENC = 256;       // memory depth
 constexpr int MF = 80;
 constexpr int KV_LD = 260;     // padded row stride of e^{2 keys} in smem
-constexpr int LD = 256;        // row stride (words) of every exchange buffer
 
-// ---- weight segments (one K <= 256 slab of one stage, per CTA column slice) -------------------------------------
+// ---- weight segments (one K slab of one stage, per CTA column slice) ---------------------------------------------
 enum SegId {
-    SG_IN_S = 0, SG_IN_CTX, SG_IN_P2,
+    SG_IN_S = 0, SG_IN_CP,
     SG_G_H0, SG_G_H1, SG_G_H2, SG_G_X0, SG_G_X1, SG_G_X2,
     SG_C_X0, SG_C_X1, SG_C_X2, SG_C_RH0, SG_C_RH1, SG_C_RH2,
     SG_Y, SG_QP, SG_PM, SG_P2, NSEG
 };
-// ---- exchange buffers ([32 rows][LD] 64-bit words each) ---------------------------------------------------------
-enum BufId { B_S = 0, B_CTX, B_P2, B_Z, B_H0, B_H1, B_H2, B_RH0, B_RH1, B_RH2, B_Q, B_P1Y, B_P1M, NBUF, B_MEL };
+// ---- exchange buffers: [4 row groups][nkt k-tiles][8 rows][8 words] of 64-bit {value, tag} words.  One k-tile of one
+//      row group (512 B) is written by ONE producer CTA and read by one warp-wide 16-byte load: fully coalesced.
+//      B_CP holds ctx (k-tiles 0..31) and p2 (k-tiles 32..47): the on-chain operand of the input projection.
+enum BufId { B_S = 0, B_CP, B_Z, B_H0, B_H1, B_H2, B_RH0, B_RH1, B_RH2, B_Q, B_P1Y, B_P1M, NBUF };
+__host__ __device__ inline int buf_nkt(int b) { return b == B_CP ? 48 : 32; }
 // ---- stages (what "finish" does) --------------------------------------------------------------------------------
 enum StageId { ST_IN = 0, ST_G0, ST_G1, ST_G2, ST_C0, ST_C1, ST_C2, ST_PM, ST_OQP, ST_AP2, ST_NONE };
 // bias rows in smem ([row][16])
 enum BiasRow { BR_IN = 0, BR_INX, BR_G0, BR_G1, BR_G2, BR_C0, BR_C1, BR_C2, BR_Y, BR_QP, BR_PM, BR_P2, NBR };
+// item kinds: fragment width / tiles / k-tile slots per warp
+enum ItemKind { IK_F2S4 = 0, IK_F4S4, IK_F4S4X2, IK_F2S6, IK_PM, IK_AP2 };
+// output slots of the per-CTA output-offset table
+enum OutId { O_Z = 0, O_RH0, O_RH1, O_RH2, O_H0, O_H1, O_H2, O_S, O_Q, O_P1Y, O_P1M, O_P2, NOUT };
 
 struct SegDesc {
-    int K;             // contraction length (multiple of 8, <= 256)
+    int K;             // contraction length (multiple of 8)
     int FL;            // floats per lane and k-tile: 4 = 16 weight columns, 2 = 8 weight columns
     int nw;            // warps that split K (8, or 4 for the P2 stage)
-    int kpw;           // k-tile slots per warp (4 or 8; padded with zeros)
+    int kpw;           // k-tile slots per warp (4, 6 or 8; padded with zeros)
     int smem_off;      // float offset inside the resident smem region, or -1: lives in TMEM
     int tmem_col;      // column offset inside the warp's 256-column TMEM half
     int slice_floats;  // nw * kpw * 32 * FL
@@ -95,7 +101,9 @@ struct Item {          // one unit of the per-step program: multiply one operand
     int src;           // BufId of the operand
     int tagd;          // operand tag = t + tagd
     int stage;         // StageId finished after this item, or ST_NONE
-    int skip_t0;       // operand does not exist at t == 0 (zero initial state)
+    int skip0;         // leading k-tile slots that do not exist at t == 0 (zero initial state); 99 = the whole item
+    int kind;          // ItemKind
+    int pre;           // operand is known long before the item runs: its loads are issued one finish() early
 };
 
 constexpr int MAX_ITEMS = 20;
@@ -263,51 +271,47 @@ __device__ __forceinline__ void ktile_mma(float (&acc)[3][4], uint32_t bh0, uint
     mma_tf32(acc[2], ah[0], ah[1], ah[2], ah[3], bh0, bh1);
 }
 
-// One operand segment against one (MT = 1) or two (MT = 2) weight tiles.  `widx`/`nw`: this warp's index among the
-// warps that split K; local slot i covers k-tile widx + nw*i.  `koff`: first k-tile slot of the warp's fragment
-// block used by this call (0, or 4 for the second half of an 8-slot segment).  Operand = LL exchange words (polling).
-template <int FL, int MT>
-__device__ __forceinline__ void seg_mma(float (&acc)[2][3][4], const SegDesc& sd, const SegDesc& sd2, const float* res_s, uint32_t tm_lane_col,
-                                        const uint64_t* rowp, bool live, uint32_t tag, int widx, int nw, int koff, int lane, long long* ck = nullptr) {
-    const int nkt = sd.K >> 3;
-    const int tg = lane & 3;
-    ulonglong2 v[4];
-    const uint64_t* p0 = rowp + (size_t)(widx + nw * koff) * 8 + 2 * tg;
+// ---- operand ingest + multiply of one item -------------------------------------------------------------------------
+// Slot i of warp-index `widx` (of `nw` warps splitting K) covers k-tile widx + nw*i; its 8 rows x 8 words sit at
+// p0 + i*nw*64 (p0 already contains this lane's g*8 + 2*tg).  NS = slots per call (4 or 6); s0 = first live slot.
+template <int NS_>
+__device__ __forceinline__ void issue_loads(ulonglong2 (&v)[6], const uint64_t* p0, int nkt, int widx, int nw, int s0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-        if (live && widx + nw * (koff + i) < nkt) v[i] = ll_load2(p0 + (size_t)i * nw * 8);
-    if (ck) ck[0] = clock64();
-    // weight fragments of the (up to) four k-tile slots
-    float w[MT][4 * FL];
+    for (int i = 0; i < NS_; ++i)
+        if (i >= s0 && widx + nw * i < nkt) v[i] = ll_load2(p0 + (size_t)i * nw * 64);
+}
+// weight word: >= 0: float offset in the resident smem region; bit 31 set: TMEM column inside the warp's window.
+// wslot = index of the first fragment slot used by this call in the segment's [warp][slot] block, tcoff = its TMEM column.
+template <int FL, int MT, int NS_>
+__device__ __forceinline__ void consume(float (&acc)[2][3][4], ulonglong2 (&v)[6], const uint64_t* p0, int nkt, int widx, int nw, int s0,
+                                        uint32_t tag, uint32_t w1, uint32_t w2, int wslot, int tcoff, const float* res_s, uint32_t tm_lane_col,
+                                        int lane, long long* ck) {
+    float w[MT][NS_ * FL];
     __syncwarp();
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
-        const SegDesc& d = mt ? sd2 : sd;
-        if (d.smem_off >= 0) {
-            const float* wp = res_s + d.smem_off + ((size_t)(widx * d.kpw + koff) * 32 + lane) * FL;
+        const uint32_t ww = mt ? w2 : w1;
+        if (!(ww & 0x80000000u)) {
+            const float* wp = res_s + ww + ((size_t)wslot * 32 + lane) * FL;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < NS_; ++i) {
                 if constexpr (FL == 4) { const float4 t = *reinterpret_cast<const float4*>(wp + (size_t)i * 32 * FL); w[mt][4 * i] = t.x; w[mt][4 * i + 1] = t.y; w[mt][4 * i + 2] = t.z; w[mt][4 * i + 3] = t.w; }
                 else                   { const float2 t = *reinterpret_cast<const float2*>(wp + (size_t)i * 32 * FL); w[mt][2 * i] = t.x; w[mt][2 * i + 1] = t.y; }
             }
-        } else {
-            const uint32_t ta = tm_lane_col + (uint32_t)(d.tmem_col + koff * FL);
+        } else if constexpr (NS_ == 4) {
+            const uint32_t ta = tm_lane_col + (ww & 0x7fffffffu) + (uint32_t)tcoff;
             if constexpr (FL == 4) tm_ld16(ta, w[mt]);
             else                   tm_ld8(ta, w[mt]);
         }
     }
     if (ck) ck[1] = clock64();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        if (widx + nw * (koff + i) < nkt) {            // warp-uniform
-            float xa = 0.f, xb = 0.f;
-            if (live) {
-                ll_spin(v[i], p0 + (size_t)i * nw * 8, tag);
-                xa = __uint_as_float((uint32_t)v[i].x); xb = __uint_as_float((uint32_t)v[i].y);
-            }
+    for (int i = 0; i < NS_; ++i) {
+        if (i >= s0 && widx + nw * i < nkt) {          // warp-uniform
+            ll_spin(v[i], p0 + (size_t)i * nw * 64, tag);
             uint32_t bh0, bl0, bh1, bl1;
-            split_tf32(xa, bh0, bl0);
-            split_tf32(xb, bh1, bl1);
+            split_tf32(__uint_as_float((uint32_t)v[i].x), bh0, bl0);
+            split_tf32(__uint_as_float((uint32_t)v[i].y), bh1, bl1);
             __syncwarp();                               // lanes arrive from divergent polling loops
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt) ktile_mma<FL>(acc[mt], bh0, bl0, bh1, bl1, &w[mt][i * FL]);
@@ -316,9 +320,11 @@ __device__ __forceinline__ void seg_mma(float (&acc)[2][3][4], const SegDesc& sd
     if (ck) ck[2] = clock64();
 }
 
+struct ItemRec { uint32_t base; int tagd; int nkt; int kind; int stage; int skip0; uint32_t w1, w2; };   // 32 bytes, in smem
+
 __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_kernel(const __grid_constant__ DecParams P) {
     extern __shared__ __align__(16) float smem[];
-    // smem map (floats): [0,16) tmem ptr | part 4096 | part2 256 | loc 384 | bias 256 | att 704 | xbuf 1024 | xstat 64 | kv | resident weights
+    // smem map (floats): [0,16) tmem ptr | part 4096 | part2 256 | loc 384 | bias 256 | att 704 | xbuf 1024 | xstat 64 | itab 192 | kv | weights
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem);
     float* part_s = smem + 16;                                    // [2 parity][8 warps][2 tiles][128]
     float* part2_s = part_s + 4096;                               // [4 warps][64]   (P2, warps 4-7)
@@ -327,6 +333,8 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
     float* att_s = bias_s + 256;                                  // eq[256] | v[256] | e[64] | p[64] | misc[64]
     uint64_t* xbuf = reinterpret_cast<uint64_t*>(att_s + 704);    // [2 parity][4 src][64] words
     uint64_t* xstat = xbuf + 512;                                 // [2 parity][4 src][2] words (+pad)
+    ItemRec* itab = reinterpret_cast<ItemRec*>(att_s + 704 + 1024 + 64);   // [MAX_ITEMS] resolved item records (160 floats)
+    uint32_t* otab = reinterpret_cast<uint32_t*>(itab + MAX_ITEMS);          // [NOUT] output word offsets of this CTA
     float* ek_s = smem + P.smem_kv_off;
     float* vals_s = ek_s + P.Tq * KV_LD;
     float* res_s = smem + P.smem_res_off;
@@ -342,7 +350,9 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, tg = lane & 3;            // MMA fragment coordinates
     const int cta = blockIdx.x;
-    const int rg = cta & 3, cs = cta >> 2;             // dense stages: row group, column slice
+    // dense stages: row group = the 32 consecutive CTAs that also run the attention of those 8 utterances, so the four
+    // row groups are four INDEPENDENT 32-CTA machines on (mostly) neighbouring SMs: no exchange crosses a group
+    const int rg = cta >> 5, cs = cta & 31;
     const int arow = cta >> 2;                          // attention: utterance (the cluster), quarter = cluster rank
     const uint32_t aq = cluster_rank();
     const taco_decoder_args& A = P.a;
@@ -350,6 +360,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
     const int B = A.B, T = A.T, OUT = P.OUT, Tq = P.Tq, Tx = A.Tx, NCY = P.NCY;
     const int row0 = rg * RPG;
     const int myrow = row0 + g;                        // the utterance row this lane's B fragments belong to
+    const int lane_w = g * 8 + 2 * tg;                  // this lane's word offset inside a k-tile block
 
     // ---- tensor memory: the whole 512-column TMEM of the SM (1 CTA/SM) ----
     if (warp == 0) {
@@ -364,8 +375,8 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
         float bv = 0.f;
         int col; const float* bp = nullptr;
         switch (br) {
-            case BR_IN:  col = seg_col(SG_IN_CTX, cs, m, NCY, OUT); bp = P.in_b; break;
-            case BR_INX: col = seg_col(SG_IN_CTX, cs, m, NCY, OUT); bp = P.b_inS; break;
+            case BR_IN:  col = seg_col(SG_IN_CP, cs, m, NCY, OUT); bp = P.in_b; break;
+            case BR_INX: col = seg_col(SG_IN_CP, cs, m, NCY, OUT); bp = P.b_inS; break;
             case BR_G0: case BR_G1: case BR_G2: col = seg_col(SG_G_X0, cs, m, NCY, OUT); bp = P.gru_bg[br - BR_G0]; break;
             case BR_C0: case BR_C1: case BR_C2: col = seg_col(SG_C_X0, cs, m, NCY, OUT); bp = P.gru_bc[br - BR_C0]; break;
             case BR_Y:   col = seg_col(SG_Y, cs, m, NCY, OUT); bp = P.out_b; break;
@@ -375,6 +386,30 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
         }
         if (bp && col >= 0) bv = __ldg(bp + col);
         bias_s[tid] = bv;
+    }
+    // resolved item records / output offsets (everything the per-item code would otherwise fetch through dependent
+    // constant-bank loads: ~300 cycles per item in the first v4 trace)
+    if (tid < P.n_items) {
+        const Item& it = P.items[tid];
+        ItemRec r;
+        r.base = 0; r.nkt = 0; r.w1 = r.w2 = 0;
+        r.tagd = it.tagd; r.kind = it.kind | (it.pre << 8); r.stage = it.stage; r.skip0 = it.skip0;
+        if (it.kind <= IK_F2S6) {
+            const SegDesc& d = P.seg[it.seg];
+            r.base = (uint32_t)(P.buf[it.src] + (int64_t)rg * buf_nkt(it.src) * 64);
+            r.nkt = d.K >> 3;
+            r.w1 = d.smem_off >= 0 ? (uint32_t)d.smem_off : (0x80000000u | (uint32_t)d.tmem_col);
+            if (it.seg2 >= 0) { const SegDesc& d2 = P.seg[it.seg2]; r.w2 = d2.smem_off >= 0 ? (uint32_t)d2.smem_off : (0x80000000u | (uint32_t)d2.tmem_col); }
+        }
+        itab[tid] = r;
+    }
+    if (tid < NOUT) {
+        const int bmap[NOUT] = {B_Z, B_RH0, B_RH1, B_RH2, B_H0, B_H1, B_H2, B_S, B_Q, B_P1Y, B_P1M, B_CP};
+        const int b = bmap[tid];
+        uint32_t o = (uint32_t)(P.buf[b] + (int64_t)rg * buf_nkt(b) * 64);
+        if (tid == O_P2) o += (uint32_t)((32 + (cs >> 1)) * 64 + 0);     // p2 columns 4cs..4cs+3 live in k-tile 32 + cs/2 of B_CP
+        else o += (uint32_t)(cs * 64);                                    // this CTA's 8 columns are k-tile cs
+        otab[tid] = o;
     }
     tc_fence_before();
     __syncthreads();
@@ -413,8 +448,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
             kk = __ldg(reinterpret_cast<const float4*>(A.keys + gi));
             vv = __ldg(reinterpret_cast<const float4*>(A.values + gi));
         }
-        // tanh(k+q) = 1 - 2/(e^{2k} e^{2q} + 1);  2*log2(e) = 2.885390082
-        kk.x = exp2x(kk.x); kk.y = exp2x(kk.y); kk.z = exp2x(kk.z); kk.w = exp2x(kk.w);
+        kk.x = exp2x(kk.x); kk.y = exp2x(kk.y); kk.z = exp2x(kk.z); kk.w = exp2x(kk.w);   // tanh(k+q) = 1 - 2/(e^{2k} e^{2q} + 1)
         *reinterpret_cast<float4*>(ek_s + j * KV_LD + d4) = kk;
         *reinterpret_cast<float4*>(vals_s + j * ENC + d4) = vv;
     }
@@ -422,11 +456,11 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
     const int my_len = (arow < B) ? A.text_length[arow] : 0;
     __syncthreads();
     if (warp == 0) {                                    // V0 = sum_d v_d  (e_j = V0 - 2 sum_d v_d / (E_jd + 1))
-        float s = 0.f;
-        for (int i = lane; i < AU; i += 32) s += v_s[i];
+        float sv = 0.f;
+        for (int i = lane; i < AU; i += 32) sv += v_s[i];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) misc_s[0] = s;
+        for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+        if (lane == 0) misc_s[0] = sv;
     }
     __syncthreads();
     cluster_sync_all();                                 // peers' shared memory is initialised before anyone pushes into it
@@ -438,11 +472,12 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
         for (int a1 = 0; a1 < 3; ++a1)
 #pragma unroll
             for (int a2 = 0; a2 < 4; ++a2) acc[a0][a1][a2] = 0.f;
+    ulonglong2 v[6];                                    // operand words in flight
 
     int par = 0;                                        // parity of the partial-tile buffer
-    long long* cktr = nullptr;                          // per-item clock64 trace (CTA 0, thread 0, steps 10..13)
     const bool tracer = (cta == 0 && tid == 0 && A.step_ns != nullptr);
     int64_t trace_i = 0;
+    long long* cktr = nullptr;                          // per-item clock64 trace (CTA 0, thread 0, steps 10..13)
 
     // =========================================================================================================
     // finish a stage: per-warp partial tiles -> smem, cross-warp sum, epilogue (one thread per output)
@@ -466,49 +501,90 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
 #pragma unroll
                 for (int a2 = 0; a2 < 4; ++a2) acc[a0][a1][a2] = 0.f;
     };
-    auto sum8 = [&](const float* part, int mt, int e) {
-        float v = 0.f;
+    auto sum8 = [&](const float* part, int mt, int pidx) {
+        float sv = 0.f;
 #pragma unroll
-        for (int w = 0; w < NWARP; ++w) v += part[(w * 2 + mt) * 128 + e];
-        return v;
+        for (int w = 0; w < NWARP; ++w) sv += part[(w * 2 + mt) * 128 + pidx];
+        return sv;
     };
+    // epilogue thread mapping: lanes run over the 8 weight columns first (8-byte words of one row are then
+    // contiguous: a warp writes two full 128-byte lines), rows next, the second 8 columns (G: u gates) last.
+    const int e_brow = (tid >> 3) & 7, e_wc = tid & 7, e_hi = (tid >> 6) & 1;
+    const int e_pidx = (e_wc + 8 * e_hi) * 8 + e_brow;       // index into a [16 cols][8 rows] partial tile
+    const int e_loc = e_wc * 8 + e_brow;                     // index into the [8 cols][8 rows] local state arrays
+    const int e_row = row0 + e_brow;
+    const int e_word = e_brow * 8 + perm8(e_wc);             // word inside this CTA's k-tile block of an exchange buffer
 
     // ---- attention of step t on warps 0..3 (128 threads): scores, partial softmax / context, cluster merge ----
     auto attention = [&](int t) {
-        if (arow >= B) return;                          // whole cluster idle for padding utterances
         const uint32_t tag = (uint32_t)t + 1;
         const int xp = t & 1;
+        uint64_t* ctx_out = ws + P.buf[B_CP] + (int64_t)(arow >> 3) * 48 * 64 + (8 * (int)aq + (tid >> 3)) * 64 + (arow & 7) * 8 + perm8(tid & 7);
+        if (arow >= B) {                                // padding utterance: publish a zero context (consumers poll every row)
+            if (tid < 64) ll_store(ctx_out, 0.f, tag + 1);
+            return;
+        }
         {   // q(t) of this utterance -> e^{2q}
-            const float2 qq = ll_wait2(ws + P.buf[B_Q] + (int64_t)arow * LD + 2 * tid, tag);
+            const float2 qq = ll_wait2(ws + P.buf[B_Q] + (int64_t)(arow >> 3) * 2048 + (tid >> 2) * 64 + (arow & 7) * 8 + 2 * (tid & 3), tag);
             const int k0 = ((tid >> 2) << 3) + (tid & 3);        // physical pair (2p, 2p+1) = logical k0, k0+4
             eq_s[k0] = exp2x(qq.x);
             eq_s[k0 + 4] = exp2x(qq.y);
         }
         named_bar(1, 128);
-        const float V0 = misc_s[0];
-        {
-            const int dsl = lane & 7;
-            for (int j0 = warp * 4; j0 < Tq; j0 += 16) {
-                const int j = j0 + (lane >> 3);
-                const bool valid = j < Tq;
-                float a = 0.f;
-                if (valid) {
+        {   // scores: lane owns 8 consecutive depth indices (its e^{2q}, v slices stay in registers), warp w owns
+            // positions j = w, w+4, ...; eight positions are reduced over the warp with one transposing butterfly
+            float eq[8], vv[8];
+            {
+                const float4 q0 = *reinterpret_cast<const float4*>(eq_s + 8 * lane), q1 = *reinterpret_cast<const float4*>(eq_s + 8 * lane + 4);
+                const float4 v0 = *reinterpret_cast<const float4*>(v_s + 8 * lane), v1 = *reinterpret_cast<const float4*>(v_s + 8 * lane + 4);
+                eq[0] = q0.x; eq[1] = q0.y; eq[2] = q0.z; eq[3] = q0.w; eq[4] = q1.x; eq[5] = q1.y; eq[6] = q1.z; eq[7] = q1.w;
+                vv[0] = v0.x; vv[1] = v0.y; vv[2] = v0.z; vv[3] = v0.w; vv[4] = v1.x; vv[5] = v1.y; vv[6] = v1.z; vv[7] = v1.w;
+            }
+            const float V0 = misc_s[0];
+            for (int jb = 0; jb < Tq; jb += 32) {       // 8 positions per warp and round
+                float a8[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int d0 = i * 32 + dsl * 4;
-                        const float4 kk = *reinterpret_cast<const float4*>(ek_s + j * KV_LD + d0);
-                        const float4 qq = *reinterpret_cast<const float4*>(eq_s + d0);
-                        const float4 vv = *reinterpret_cast<const float4*>(v_s + d0);
-                        a = fmaf(vv.x, rcp_fast(fmaf(kk.x, qq.x, 1.0f)), a);
-                        a = fmaf(vv.y, rcp_fast(fmaf(kk.y, qq.y, 1.0f)), a);
-                        a = fmaf(vv.z, rcp_fast(fmaf(kk.z, qq.z, 1.0f)), a);
-                        a = fmaf(vv.w, rcp_fast(fmaf(kk.w, qq.w, 1.0f)), a);
+                for (int jj = 0; jj < 8; ++jj) {
+                    const int j = jb + warp + 4 * jj;
+                    float a = 0.f;
+                    if (j < Tq) {                       // warp-uniform
+                        const float4 k0 = *reinterpret_cast<const float4*>(ek_s + j * KV_LD + 8 * lane);
+                        const float4 k1 = *reinterpret_cast<const float4*>(ek_s + j * KV_LD + 8 * lane + 4);
+                        a = fmaf(vv[0], rcp_fast(fmaf(k0.x, eq[0], 1.0f)), a);
+                        a = fmaf(vv[1], rcp_fast(fmaf(k0.y, eq[1], 1.0f)), a);
+                        a = fmaf(vv[2], rcp_fast(fmaf(k0.z, eq[2], 1.0f)), a);
+                        a = fmaf(vv[3], rcp_fast(fmaf(k0.w, eq[3], 1.0f)), a);
+                        a = fmaf(vv[4], rcp_fast(fmaf(k1.x, eq[4], 1.0f)), a);
+                        a = fmaf(vv[5], rcp_fast(fmaf(k1.y, eq[5], 1.0f)), a);
+                        a = fmaf(vv[6], rcp_fast(fmaf(k1.z, eq[6], 1.0f)), a);
+                        a = fmaf(vv[7], rcp_fast(fmaf(k1.w, eq[7], 1.0f)), a);
                     }
+                    a8[jj] = a;
                 }
-                a += __shfl_xor_sync(0xffffffffu, a, 1);
-                a += __shfl_xor_sync(0xffffffffu, a, 2);
-                a += __shfl_xor_sync(0xffffffffu, a, 4);
-                if (valid && dsl == 0) e_s[j] = ((int)aq * Tq + j < my_len) ? fmaf(-2.0f, a, V0) : -INFINITY;
+                // transposing butterfly: after the three halving steps lane group (lane>>2) holds position jj = lane>>2
+                float b4[4], b2[2], b1;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float send = (lane & 16) ? a8[k] : a8[k + 4];
+                    const float keep = (lane & 16) ? a8[k + 4] : a8[k];
+                    b4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                }
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const float send = (lane & 8) ? b4[k] : b4[k + 2];
+                    const float keep = (lane & 8) ? b4[k + 2] : b4[k];
+                    b2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
+                {
+                    const float send = (lane & 4) ? b2[0] : b2[1];
+                    const float keep = (lane & 4) ? b2[1] : b2[0];
+                    b1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                }
+                b1 += __shfl_xor_sync(0xffffffffu, b1, 2);
+                b1 += __shfl_xor_sync(0xffffffffu, b1, 1);
+                const int jj = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                const int j = jb + warp + 4 * jj;
+                if ((lane & 3) == 0 && j < Tq) e_s[j] = ((int)aq * Tq + j < my_len) ? fmaf(-2.0f, b1, V0) : -INFINITY;
             }
         }
         named_bar(1, 128);
@@ -534,10 +610,11 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
         named_bar(1, 128);
         {   // partial context: columns 2 tid, 2 tid + 1; pushed to the CTA that owns them (64 columns per CTA)
             float c0 = 0.f, c1 = 0.f;
+#pragma unroll 4
             for (int j = 0; j < Tq; ++j) {
                 const float p = p_s[j];
-                const float2 vv = *reinterpret_cast<const float2*>(vals_s + j * ENC + 2 * tid);
-                c0 = fmaf(p, vv.x, c0); c1 = fmaf(p, vv.y, c1);
+                const float2 vv2 = *reinterpret_cast<const float2*>(vals_s + j * ENC + 2 * tid);
+                c0 = fmaf(p, vv2.x, c0); c1 = fmaf(p, vv2.y, c1);
             }
             const uint32_t dst = (uint32_t)tid >> 5;
             const int i0 = (2 * tid) & 63;
@@ -556,11 +633,11 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
             if (qd == (int)aq) w_own = wq[qd];
         }
         const float inv = (S > 0.f) ? 1.0f / S : 0.f;
-        if (tid < 64) {                                  // final context column 64 aq + tid
+        if (tid < 64) {                                  // final context column 64 aq + tid  (tag of the step that consumes it)
             float c = 0.f;
 #pragma unroll
             for (int qd = 0; qd < 4; ++qd) c = fmaf(wq[qd], sm_wait(xbuf + (xp * 4 + qd) * 64 + tid, tag), c);
-            ll_store(ws + P.buf[B_CTX] + (int64_t)arow * LD + perm8(64 * (int)aq + tid), c * inv, tag);
+            ll_store(ctx_out, c * inv, tag + 1);
         } else {                                         // alignments of this quarter (AttentionWrapper alignment_history)
             const int j = tid - 64;
             if (j < Tq && (int)aq * Tq + j < Tx) A.align[((int64_t)arow * T + t) * Tx + aq * Tq + j] = p_s[j] * (w_own * inv);
@@ -574,10 +651,13 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
         bool from_y = (tb > 0);
         if (A.mode == TACO_DEC_TEACHER) from_y = false;
         else if (A.mode == TACO_DEC_SCHED) from_y = (tb > 0) && (myrow < B) && (A.sample_mask[(int64_t)(tb - 1) * B + myrow] != 0);
-        const uint64_t* rowp = ws + P.buf[from_y ? B_P1Y : B_P1M] + (int64_t)myrow * LD;
+        const uint64_t* p0 = ws + P.buf[from_y ? B_P1Y : B_P1M] + (int64_t)rg * 2048 + widx * 64 + lane_w;
         const SegDesc& sd = P.seg[SG_P2];
-        seg_mma<2, 1>(acc, sd, sd, res_s, tm_lane_col, rowp, true, tag, widx, 4, 0, lane);
-        seg_mma<2, 1>(acc, sd, sd, res_s, tm_lane_col, rowp, true, tag, widx, 4, 4, lane);
+        const uint32_t w1 = sd.smem_off >= 0 ? (uint32_t)sd.smem_off : (0x80000000u | (uint32_t)sd.tmem_col);
+        issue_loads<4>(v, p0, 32, widx, 4, 0);
+        consume<2, 1, 4>(acc, v, p0, 32, widx, 4, 0, tag, w1, w1, widx * 8, 0, res_s, tm_lane_col, lane, nullptr);
+        issue_loads<4>(v, p0 + 16 * 64, 32, widx + 16, 4, 0);
+        consume<2, 1, 4>(acc, v, p0 + 16 * 64, 32, widx + 16, 4, 0, tag, w1, w1, widx * 8 + 4, 8, res_s, tm_lane_col, lane, nullptr);
         float* pw = part2_s + widx * 64;
         *reinterpret_cast<float2*>(pw + g * 8 + 2 * tg) =
             make_float2((acc[0][0][0] + acc[0][1][0]) + acc[0][2][0], (acc[0][0][1] + acc[0][1][1]) + acc[0][2][1]);
@@ -587,12 +667,12 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
             for (int a2 = 0; a2 < 4; ++a2) acc[0][a1][a2] = 0.f;
         named_bar(2, 128);
         const int e = tid - 128;
-        if (e < 32) {                                    // 4 columns x 8 rows
-            const int wcol = e >> 3, brow = e & 7, row = row0 + brow, col = 4 * cs + wcol;
-            float v = part2_s[e] + part2_s[64 + e] + part2_s[128 + e] + part2_s[192 + e] + bias_s[BR_P2 * 16 + wcol];
-            v = fmaxf(v, 0.f);
-            if (A.keep2 && row < B && tb < T) v = A.keep2[((int64_t)tb * B + row) * 128 + col] ? v * A.keep_scale : 0.f;
-            ll_store(ws + P.buf[B_P2] + (int64_t)row * LD + perm8(col), v, tag);
+        if (e < 32) {                                    // 8 rows x 4 columns, columns fastest
+            const int wcol = e & 3, brow = e >> 2, row = row0 + brow, col = 4 * cs + wcol, pi = wcol * 8 + brow;
+            float pv = part2_s[pi] + part2_s[64 + pi] + part2_s[128 + pi] + part2_s[192 + pi] + bias_s[BR_P2 * 16 + wcol];
+            pv = fmaxf(pv, 0.f);
+            if (A.keep2 && row < B && tb < T) pv = A.keep2[((int64_t)tb * B + row) * 128 + col] ? pv * A.keep_scale : 0.f;
+            ll_store(ws + otab[O_P2] + brow * 8 + perm8(4 * (cs & 1) + wcol), pv, tag);
         }
         named_bar(2, 128);                               // part2_s may be rewritten
     };
@@ -638,59 +718,57 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
         if (cktr) cktr[4] = clock64();
         __syncthreads();
         if (cktr) cktr[5] = clock64();
-        const int e = tid & 127, wcol = e >> 3, brow = e & 7, row = row0 + brow;
         const uint32_t tag = (uint32_t)t + 1;
         switch (stage) {
             case ST_IN:
                 if (tid < 64) {
-                    float v = sum8(part, 0, e) + bias_s[BR_IN * 16 + wcol];
-                    if (t > 0) v += bias_s[BR_INX * 16 + wcol];
-                    z_loc[e] = v;
-                    ll_store(ws + P.buf[B_Z] + (int64_t)row * LD + 8 * cs + perm8(wcol), v, tag);
+                    float zv = sum8(part, 0, e_pidx) + bias_s[BR_IN * 16 + e_wc];
+                    if (t > 0) zv += bias_s[BR_INX * 16 + e_wc];
+                    z_loc[e_loc] = zv;
+                    ll_store(ws + otab[O_Z] + e_word, zv, tag);
                 }
                 break;
             case ST_G0: case ST_G1: case ST_G2:
                 if (tid < 128) {
                     const int gi = stage - ST_G0;
-                    const float gt = sigmoidf_acc(sum8(part, 0, e) + bias_s[(BR_G0 + gi) * 16 + wcol]);
-                    if (wcol < 8) ll_store(ws + P.buf[B_RH0 + gi] + (int64_t)row * LD + 8 * cs + perm8(wcol), gt * h_loc[gi * 64 + e], tag);   // r * h
-                    else u_loc[e - 64] = gt;                                                                                                  // u stays local
+                    const float gt = sigmoidf_acc(sum8(part, 0, e_pidx) + bias_s[(BR_G0 + gi) * 16 + e_wc + 8 * e_hi]);
+                    if (!e_hi) ll_store(ws + otab[O_RH0 + gi] + e_word, gt * h_loc[gi * 64 + e_loc], tag);   // r * h
+                    else u_loc[e_loc] = gt;                                                                // u stays local
                 }
                 break;
             case ST_C0: case ST_C1: case ST_C2:
                 if (tid < 64) {
                     const int gi = stage - ST_C0;
-                    const float cnd = tanhf_acc(sum8(part, 0, e) + bias_s[(BR_C0 + gi) * 16 + wcol]);
-                    const float uu = u_loc[e];
-                    const float hn = uu * h_loc[gi * 64 + e] + (1.0f - uu) * cnd;
-                    h_loc[gi * 64 + e] = hn;
-                    const int col = 8 * cs + wcol;
-                    ll_store(ws + P.buf[B_H0 + gi] + (int64_t)row * LD + 8 * cs + perm8(wcol), hn, tag);
-                    if (A.h_save && row < B) A.h_save[(((int64_t)gi * T + t) * B + row) * U + col] = hn;   // training: BPTT input
-                    if (gi == 2) ll_store(ws + P.buf[B_S] + (int64_t)row * LD + 8 * cs + perm8(wcol), z_loc[e] + hn, tag);
+                    const float cnd = tanhf_acc(sum8(part, 0, e_pidx) + bias_s[(BR_C0 + gi) * 16 + e_wc]);
+                    const float uu = u_loc[e_loc];
+                    const float hn = uu * h_loc[gi * 64 + e_loc] + (1.0f - uu) * cnd;
+                    h_loc[gi * 64 + e_loc] = hn;
+                    ll_store(ws + otab[O_H0 + gi] + e_word, hn, tag);
+                    if (gi == 2) ll_store(ws + otab[O_S] + e_word, z_loc[e_loc] + hn, tag);
+                    if (A.h_save && e_row < B) A.h_save[(((int64_t)gi * T + t) * B + e_row) * U + 8 * cs + e_wc] = hn;   // training: BPTT input
                 }
                 break;
             case ST_PM:
                 if (tid < 64) {                              // here t = tb, the step the pre-net output belongs to
-                    const int col = 8 * cs + wcol;
-                    float v = fmaxf(sum8(part, 0, e) + bias_s[BR_PM * 16 + wcol], 0.f);
-                    if (A.keep1 && row < B && t < T) v = A.keep1[((int64_t)t * B + row) * 256 + col] ? v * A.keep_scale : 0.f;
-                    ll_store(ws + P.buf[B_P1M] + (int64_t)row * LD + 8 * cs + perm8(wcol), v, tag);
+                    const int col = 8 * cs + e_wc;
+                    float pv = fmaxf(sum8(part, 0, e_pidx) + bias_s[BR_PM * 16 + e_wc], 0.f);
+                    if (A.keep1 && e_row < B && t < T) pv = A.keep1[((int64_t)t * B + e_row) * 256 + col] ? pv * A.keep_scale : 0.f;
+                    ll_store(ws + otab[O_P1M] + e_word, pv, tag);
                 }
                 break;
             case ST_OQP: {
                 const int mt = tid >> 7;
-                const float v0 = sum8(part, mt, e) + bias_s[(BR_Y + mt) * 16 + wcol];
+                const float v0 = sum8(part, mt, e_pidx) + bias_s[(BR_Y + mt) * 16 + e_wc + 8 * e_hi];
                 if (mt == 0) {                               // y(t): the output itself (nothing downstream reads it)
-                    const int col = cs * NCY + wcol;
-                    if (wcol < NCY && col < OUT && row < B) A.y[((int64_t)row * T + t) * OUT + col] = v0;
-                } else if (wcol < 8) {                       // q(t)
-                    ll_store(ws + P.buf[B_Q] + (int64_t)row * LD + 8 * cs + perm8(wcol), v0, tag);
+                    const int wcol = e_wc + 8 * e_hi, col = cs * NCY + wcol;
+                    if (wcol < NCY && col < OUT && e_row < B) A.y[((int64_t)e_row * T + t) * OUT + col] = v0;
+                } else if (!e_hi) {                          // q(t)
+                    ll_store(ws + otab[O_Q] + e_word, v0, tag);
                 } else {                                     // p1(t+1) of free-running rows
-                    const int c8 = wcol - 8, col = 8 * cs + c8, tb = t + 1;
-                    float v = fmaxf(v0, 0.f);
-                    if (A.keep1 && row < B && tb < T) v = A.keep1[((int64_t)tb * B + row) * 256 + col] ? v * A.keep_scale : 0.f;
-                    ll_store(ws + P.buf[B_P1Y] + (int64_t)row * LD + 8 * cs + perm8(c8), v, tag + 1);
+                    const int col = 8 * cs + e_wc, tb = t + 1;
+                    float pv = fmaxf(v0, 0.f);
+                    if (A.keep1 && e_row < B && tb < T) pv = A.keep1[((int64_t)tb * B + e_row) * 256 + col] ? pv * A.keep_scale : 0.f;
+                    ll_store(ws + otab[O_P1Y] + e_word, pv, tag + 1);
                 }
             } break;
             default: break;
@@ -709,33 +787,57 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
     // =========================================================================================================
     // T decoder steps x the item program
     // =========================================================================================================
+    const int n_items = P.n_items;
+    bool pref = false;                                  // v[] already holds the loads of the current item
     for (int t = 0; t < T; ++t) {
         if (tracer) A.step_ns[t] = globaltimer_ns();
-        for (int ii = 0; ii < P.n_items; ++ii) {
-            const Item& it = P.items[ii];
-            if (it.stage == ST_AP2) {
+        for (int ii = 0; ii < n_items; ++ii) {
+            const int4 ra = *reinterpret_cast<const int4*>(&itab[ii]);                 // base, tagd, nkt, kind
+            const int4 rb = *reinterpret_cast<const int4*>(reinterpret_cast<const int*>(&itab[ii]) + 4);   // stage, skip0, w1, w2
+            const int kind = ra.w & 0xff, stage = rb.x;
+            long long* ck = nullptr;
+            if (tracer && t >= 10 && t < 14) { ck = reinterpret_cast<long long*>(ws + P.trace_off + 16 * T + 16 + ((t - 10) * MAX_ITEMS + ii) * 8); ck[3] = clock64(); }
+            cktr = ck;
+            if (kind == IK_AP2) {
                 if (warp < 4) attention(t);
                 else if (t + 1 < T) prenet2(t + 1);
                 if (tracer) ws[P.trace_off + (trace_i++)] = globaltimer_ns();
                 continue;
             }
-            if (it.stage == ST_PM) {
+            if (kind == IK_PM) {
                 if (t + 1 < T) { prenet1_teacher(t + 1); finish(ST_PM, t + 1); }
                 continue;
             }
-            long long* ck = nullptr;
-            if (tracer && t >= 10 && t < 14) { ck = reinterpret_cast<long long*>(ws + P.trace_off + 16 * T + 16 + ((t - 10) * MAX_ITEMS + ii) * 8); ck[3] = clock64(); }
-            cktr = ck;
-            if (!(it.skip_t0 && t == 0)) {
-                const SegDesc& sd = P.seg[it.seg];
-                const uint64_t* rowp = ws + P.buf[it.src] + (int64_t)myrow * LD;
-                const bool live = (it.src != B_CTX) || (myrow < B);       // padding utterances have no attention cluster output
-                const uint32_t tag = (uint32_t)(t + it.tagd);
-                if (it.seg2 >= 0)      seg_mma<4, 2>(acc, sd, P.seg[it.seg2], res_s, tm_lane_col, rowp, live, tag, warp, NWARP, 0, lane, ck);
-                else if (sd.FL == 4)   seg_mma<4, 1>(acc, sd, sd, res_s, tm_lane_col, rowp, live, tag, warp, NWARP, 0, lane, ck);
-                else                   seg_mma<2, 1>(acc, sd, sd, res_s, tm_lane_col, rowp, live, tag, warp, NWARP, 0, lane, ck);
+            const int s0 = (t == 0) ? rb.y : 0;
+            if (s0 < 99) {
+                const uint64_t* p0 = ws + (uint32_t)ra.x + warp * 64 + lane_w;
+                const uint32_t tag = (uint32_t)(t + ra.y);
+                const int nkt = ra.z;
+                if (kind == IK_F2S6) {
+                    issue_loads<6>(v, p0, nkt, warp, NWARP, s0);
+                    if (ck) ck[0] = clock64();
+                    consume<2, 1, 6>(acc, v, p0, nkt, warp, NWARP, s0, tag, (uint32_t)rb.z, 0u, warp * 6, 0, res_s, tm_lane_col, lane, ck);
+                } else {
+                    if (!pref) issue_loads<4>(v, p0, nkt, warp, NWARP, 0);
+                    if (ck) ck[0] = clock64();
+                    if (kind == IK_F4S4X2)    consume<4, 2, 4>(acc, v, p0, nkt, warp, NWARP, 0, tag, (uint32_t)rb.z, (uint32_t)rb.w, warp * 4, 0, res_s, tm_lane_col, lane, ck);
+                    else if (kind == IK_F4S4) consume<4, 1, 4>(acc, v, p0, nkt, warp, NWARP, 0, tag, (uint32_t)rb.z, 0u, warp * 4, 0, res_s, tm_lane_col, lane, ck);
+                    else                      consume<2, 1, 4>(acc, v, p0, nkt, warp, NWARP, 0, tag, (uint32_t)rb.z, 0u, warp * 4, 0, res_s, tm_lane_col, lane, ck);
+                }
             }
-            if (it.stage != ST_NONE) finish(it.stage, t);
+            pref = false;
+            if (stage != ST_NONE) {
+                // the next item's operand is already known (off-chain half of the next stage): put its loads in flight
+                // now, so that they travel while this stage's epilogue runs
+                if (ii + 1 < n_items) {
+                    const int4 na = *reinterpret_cast<const int4*>(&itab[ii + 1]);
+                    if ((na.w >> 8) & 1) {
+                        issue_loads<4>(v, ws + (uint32_t)na.x + warp * 64 + lane_w, na.z, warp, NWARP, 0);
+                        pref = true;
+                    }
+                }
+                finish(stage, t);
+            }
         }
     }
 
@@ -789,15 +891,15 @@ __global__ void matmul_naive_kernel(const float* __restrict__ Amat, int lda, con
 }
 
 // ---- fused linear stages (weight-only algebra; sums are re-associated, ~1e-6 relative) --------------------------
-//   W_ctxF = W_a[80r:80r+256] . W_in[128:384]                       ctx(t-1) -> z(t)
+//   W_cpF  = [ W_a[80r:80r+256] . W_in[128:384] ; W_in[0:128] ]    [ctx(t-1) | p2(t)] -> z(t)
 //   M1     = W_a[0:80r] . W_in[128:384];  W_sF = W_out . M1;  b_inS = b_out . M1        y(t-1) = s(t-1).W_out + b_out -> z(t)
 //   W_qp   = [ W_out . W_q | W_out[:, last 80] . W1 ];  b_qF = b_out . W_q;  b_p1F = b_out[last 80] . W1 + b1
-struct FusedTail { int64_t w_ctxF, m1, w_sF, w_qp, b_qF, b_p1F, b_inS, total; };
+struct FusedTail { int64_t w_cpF, m1, w_sF, w_qp, b_qF, b_p1F, b_inS, total; };
 FusedTail fused_tail(int r, int64_t slices_total) {
     const int OUT = MF * r;
     FusedTail f;
     int64_t o = (slices_total + 63) / 64 * 64;
-    f.w_ctxF = o; o += (int64_t)ENC * U;
+    f.w_cpF = o;  o += (int64_t)(ENC + 128) * U;          // [W_ctxF ; W_in[0:128]]: the on-chain operand [ctx | p2]
     f.m1 = o;     o += (int64_t)OUT * U;
     f.w_sF = o;   o += (int64_t)U * U;
     f.w_qp = o;   o += (int64_t)U * 2 * AU;
@@ -810,7 +912,7 @@ FusedTail fused_tail(int r, int64_t slices_total) {
 
 void build_seg_table(SegDesc* sd, int64_t* total_floats) {
     auto set = [&](int id, int K, int FL, int nw, int kpw) { sd[id].K = K; sd[id].FL = FL; sd[id].nw = nw; sd[id].kpw = kpw; };
-    set(SG_IN_S, 256, 2, 8, 4); set(SG_IN_CTX, 256, 2, 8, 4); set(SG_IN_P2, 128, 2, 8, 4);
+    set(SG_IN_S, 256, 2, 8, 4); set(SG_IN_CP, 384, 2, 8, 6);
     for (int i = 0; i < 3; ++i) {
         set(SG_G_H0 + i, 256, 4, 8, 4); set(SG_G_X0 + i, 256, 4, 8, 4);
         set(SG_C_X0 + i, 256, 2, 8, 4); set(SG_C_RH0 + i, 256, 2, 8, 4);
@@ -827,7 +929,7 @@ void build_seg_table(SegDesc* sd, int64_t* total_floats) {
 
 void build_ws_layout(int64_t* buf, int64_t* total) {
     int64_t o = 0;
-    for (int b = 0; b < NBUF; ++b) { buf[b] = o; o += (int64_t)BPAD * LD; }
+    for (int b = 0; b < NBUF; ++b) { buf[b] = o; o += (int64_t)4 * buf_nkt(b) * 64; }
     *total = o;
 }
 
@@ -859,10 +961,11 @@ extern "C" int taco_decoder_pack(const taco_decoder_weights* w, int r, float* pa
     const int OUT = MF * r;
     const int NCY = (OUT + NS - 1) / NS;
     const FusedTail ft = fused_tail(r, tot);
-    float *w_ctxF = packed + ft.w_ctxF, *m1 = packed + ft.m1, *w_sF = packed + ft.w_sF, *w_qp = packed + ft.w_qp;
+    float *w_cpF = packed + ft.w_cpF, *m1 = packed + ft.m1, *w_sF = packed + ft.w_sF, *w_qp = packed + ft.w_qp;
     const float* w_inA = w->in_W + (int64_t)128 * U;           // W_in[128:384]
-    matmul_naive_kernel<<<256, 256, 0, stm>>>(w->att_Wa + (int64_t)OUT * AU, AU, w_inA, U, w_ctxF, U, ENC, U, AU, nullptr);
+    matmul_naive_kernel<<<256, 256, 0, stm>>>(w->att_Wa + (int64_t)OUT * AU, AU, w_inA, U, w_cpF, U, ENC, U, AU, nullptr);
     TACO_LAUNCH_CHECK();
+    TACO_CUDA(cudaMemcpyAsync(w_cpF + (int64_t)ENC * U, w->in_W, (size_t)128 * U * sizeof(float), cudaMemcpyDeviceToDevice, stm));
     matmul_naive_kernel<<<400, 256, 0, stm>>>(w->att_Wa, AU, w_inA, U, m1, U, OUT, U, AU, nullptr);
     TACO_LAUNCH_CHECK();
     matmul_naive_kernel<<<256, 256, 0, stm>>>(w->out_W, OUT, m1, U, w_sF, U, U, U, OUT, nullptr);
@@ -880,7 +983,7 @@ extern "C" int taco_decoder_pack(const taco_decoder_weights* w, int r, float* pa
 
     struct Src { const float* W; int ld; int k0; };
     Src src[NSEG];
-    src[SG_IN_S] = {w_sF, U, 0}; src[SG_IN_CTX] = {w_ctxF, U, 0}; src[SG_IN_P2] = {w->in_W, U, 0};
+    src[SG_IN_S] = {w_sF, U, 0}; src[SG_IN_CP] = {w_cpF, U, 0};
     for (int i = 0; i < 3; ++i) {
         src[SG_G_X0 + i] = {w->gru_Wg[i], 2 * U, 0};  src[SG_G_H0 + i] = {w->gru_Wg[i], 2 * U, U};     // rows: x then h (TF 1.2 GRUCell)
         src[SG_C_X0 + i] = {w->gru_Wc[i], U, 0};      src[SG_C_RH0 + i] = {w->gru_Wc[i], U, U};
@@ -929,25 +1032,26 @@ extern "C" int taco_decoder_fwd(const taco_decoder_args* a, void* stream) {
 
     // ---- the per-step program ----
     int n = 0;
-    auto item = [&](int seg, int seg2, int src, int tagd, int stage, int skip0) { P.items[n++] = Item{seg, seg2, src, tagd, stage, skip0}; };
-    item(SG_IN_S, -1, B_S, 0, ST_NONE, 1);                         // off-chain: s(t-1)
-    item(SG_IN_CTX, -1, B_CTX, 0, ST_NONE, 1);
-    item(SG_IN_P2, -1, B_P2, 1, ST_IN, 0);
+    auto item = [&](int seg, int seg2, int src, int tagd, int stage, int skip0, int kind, int pre) {
+        P.items[n++] = Item{seg, seg2, src, tagd, stage, skip0, kind, pre};
+    };
+    item(SG_IN_S, -1, B_S, 0, ST_NONE, 99, IK_F2S4, 1);                       // off-chain: s(t-1)
+    item(SG_IN_CP, -1, B_CP, 1, ST_IN, 4, IK_F2S6, 0);                        // [ctx(t-1) | p2(t)] (no context at t = 0)
     for (int i = 0; i < 3; ++i) {
         const int x = (i == 0) ? B_Z : B_H0 + (i - 1);
-        item(SG_G_H0 + i, -1, B_H0 + i, 0, ST_NONE, 1);            // off-chain: h_i(t-1)
-        item(SG_G_X0 + i, -1, x, 1, ST_G0 + i, 0);
-        item(SG_C_X0 + i, -1, x, 1, ST_NONE, 0);                   // off-chain: x (already consumed by the gate stage)
-        item(SG_C_RH0 + i, -1, B_RH0 + i, 1, ST_C0 + i, 0);
+        item(SG_G_H0 + i, -1, B_H0 + i, 0, ST_NONE, 99, IK_F4S4, 1);          // off-chain: h_i(t-1)
+        item(SG_G_X0 + i, -1, x, 1, ST_G0 + i, 0, IK_F4S4, 0);
+        item(SG_C_X0 + i, -1, x, 1, ST_NONE, 0, IK_F2S4, 1);                  // off-chain: x (already consumed by the gate stage)
+        item(SG_C_RH0 + i, -1, B_RH0 + i, 1, ST_C0 + i, 0, IK_F2S4, 0);
     }
-    if (a->mode != TACO_DEC_INFER) item(SG_PM, -1, B_MEL, 0, ST_PM, 0);   // teacher frame t+1 -> p1m(t+1), off-chain
-    item(SG_Y, SG_QP, B_S, 1, ST_OQP, 0);
-    item(-1, -1, 0, 0, ST_AP2, 0);
+    if (a->mode != TACO_DEC_INFER) item(-1, -1, 0, 0, ST_PM, 0, IK_PM, 0);    // teacher frame t+1 -> p1m(t+1), off-chain
+    item(SG_Y, SG_QP, B_S, 1, ST_OQP, 0, IK_F4S4X2, 0);
+    item(-1, -1, 0, 0, ST_AP2, 0, IK_AP2, 0);
     P.n_items = n;
 
     // ---- residency: off-chain segments in TMEM (256 columns per warp), on-chain segments in shared memory; when the
     //      keys/values leave too little shared memory (large Tx) further segments move to TMEM ----
-    int off = 16 + 4096 + 256 + 384 + 256 + 704 + 1024 + 64;
+    int off = 16 + 4096 + 256 + 384 + 256 + 704 + 1024 + 64 + 192;
     off = (off + 31) / 32 * 32;
     P.smem_kv_off = off;
     off += P.Tq * KV_LD + P.Tq * ENC;
@@ -955,7 +1059,7 @@ extern "C" int taco_decoder_fwd(const taco_decoder_args* a, void* stream) {
     P.smem_res_off = off;
     const int budget = (227 * 1024) / 4 - off;
     const int tm_first[] = {SG_IN_S, SG_G_H0, SG_G_H1, SG_G_H2, SG_C_X0, SG_C_X1, SG_C_X2, SG_PM};
-    const int sm_order[] = {SG_G_X0, SG_C_RH0, SG_G_X1, SG_C_RH1, SG_G_X2, SG_C_RH2, SG_QP, SG_Y, SG_IN_CTX, SG_IN_P2, SG_P2};
+    const int sm_order[] = {SG_IN_CP, SG_G_X0, SG_C_RH0, SG_G_X1, SG_C_RH1, SG_G_X2, SG_C_RH2, SG_QP, SG_Y, SG_P2};
     int tcol8 = 0, tcol4 = 0;            // TMEM columns used in the half of warps 0-3 / 4-7 (8-warp segments use both halves)
     auto to_tmem = [&](int s) {
         const int cols = P.seg[s].kpw * P.seg[s].FL;
@@ -974,7 +1078,7 @@ extern "C" int taco_decoder_fwd(const taco_decoder_args* a, void* stream) {
     int res = 0;
     for (int s : sm_order) {
         if (P.seg[s].slice_floats <= budget - res) { P.seg[s].smem_off = res; res += P.seg[s].slice_floats; }
-        else TACO_CHECK(to_tmem(s), "taco_decoder_fwd: weights do not fit in shared + tensor memory (Tx=%d)", a->Tx);
+        else TACO_CHECK(s != SG_IN_CP && to_tmem(s), "taco_decoder_fwd: weights do not fit in shared + tensor memory (Tx=%d)", a->Tx);
     }
     P.smem_total_floats = off + res;
     const size_t smem_bytes = (size_t)P.smem_total_floats * 4;

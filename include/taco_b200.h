@@ -32,7 +32,10 @@ extern "C" {
 
 enum { TACO_ACT_NONE = 0, TACO_ACT_RELU = 1, TACO_ACT_SIGMOID = 2, TACO_ACT_TANH = 3 };
 enum { TACO_IMPL_TC = 0,   /* tcgen05 tensor cores, TF32 multiplies, fp32 accumulate (TMA-fed) */
-       TACO_IMPL_SIMT = 1  /* fp32 FFMA, exact fp32 products                                  */ };
+       TACO_IMPL_SIMT = 1, /* fp32 FFMA, exact fp32 products                                  */
+       TACO_IMPL_TC3 = 2   /* tcgen05 tensor cores, error-compensated 3xTF32 (x = hi + lo; lo.hi + hi.lo + hi.hi,
+                              fp32 accumulate): fp32-grade products (~1e-6 relative).  Wp then holds the
+                              hi rows [0,N) followed by the lo rows [N,2N) (taco_pack_weight_x3)          */ };
 enum { TACO_EPI_NORMAL = 0,
        TACO_EPI_HIGHWAY = 1 /* N = 2U: cols [0,U) = H pre-act, [U,2U) = T pre-act; Y[M][U] =
                                relu(H)*sig(T) + X*(1-sig(T)), X = hx (models/ops.py:32-45)   */ };
@@ -93,6 +96,10 @@ int taco_linear_fwd(const taco_linear_desc* d, void* stream);
  * (dst + (n)*ld_dst) holds, for tap j and channel c, W[j][c][n] at column j*round_up(C,32)+c,
  * rounded to TF32 (round-to-nearest); padding channels are zero.                             */
 int taco_pack_weight(const float* W, int taps, int C, int N, float* dst, int64_t ld_dst, void* stream);
+/* 3xTF32 operand pair for TACO_IMPL_TC3: dst_hi rows = TF32 round-to-nearest heads, dst_lo rows = the remainders
+ * (W - hi, cut to TF32); same layout as taco_pack_weight.  For a bank, call once per filter with the row offsets
+ * of that filter in the hi half and in the lo half (lo half starts at row bank_K*bank_cout).                 */
+int taco_pack_weight_x3(const float* W, int taps, int C, int N, float* dst_hi, float* dst_lo, int64_t ld_dst, void* stream);
 
 /* tf.layers.max_pooling1d(pool 2, stride 1, 'same') over t  (models/ops.py:66-71)            */
 int taco_maxpool_fwd(const float* X, float* Y, int B, int T, int C, void* stream);

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtaco_b200.so")
 
 ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3
-IMPL_TC, IMPL_SIMT = 0, 1
+IMPL_TC, IMPL_SIMT, IMPL_TC3 = 0, 1, 2
 EPI_NORMAL, EPI_HIGHWAY = 0, 1
 DEC_INFER, DEC_TEACHER, DEC_SCHED = 0, 1, 2
 
@@ -91,7 +91,7 @@ _lib = None
 
 # every symbol include/taco_b200.h declares (tests check the .so exports all of them)
 EXPORTS = [
-    "taco_last_error", "taco_version", "taco_device_info", "taco_linear_fwd", "taco_pack_weight",
+    "taco_last_error", "taco_version", "taco_device_info", "taco_linear_fwd", "taco_pack_weight", "taco_pack_weight_x3",
     "taco_maxpool_fwd", "taco_gather_rows", "taco_mask_rows", "taco_bigru_fwd",
     "taco_decoder_packed_bytes", "taco_decoder_workspace_bytes", "taco_decoder_pack", "taco_decoder_fwd",
     "taco_l1_loss_fwd", "taco_l1_partial_count", "taco_launch_count",
@@ -122,6 +122,7 @@ def lib():
     L.taco_device_info.argtypes = [C.POINTER(C.c_int)] * 3
     L.taco_linear_fwd.argtypes = [C.POINTER(LinearDesc), C.c_void_p]
     L.taco_pack_weight.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
+    L.taco_pack_weight_x3.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     L.taco_maxpool_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.taco_gather_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float,
                                    C.c_void_p, C.c_void_p]

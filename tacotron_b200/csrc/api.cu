@@ -16,6 +16,7 @@ void taco_set_error(const char* fmt, ...) {
 int taco_linear_simt(const taco_linear_desc* d, cudaStream_t st);
 int taco_linear_tc(const taco_linear_desc* d, cudaStream_t st);
 int taco_pack_weight_impl(const float* W, int taps, int C, int N, float* dst, int64_t ld_dst, cudaStream_t st);
+int taco_pack_weight_x3_impl(const float* W, int taps, int C, int N, float* dst_hi, float* dst_lo, int64_t ld_dst, cudaStream_t st);
 
 namespace {
 
@@ -128,9 +129,14 @@ int taco_linear_fwd(const taco_linear_desc* d, void* stream) {
     TACO_CHECK(d->bank_K > 0 || d->taps >= 1, "taco_linear_fwd: taps must be >= 1");
     TACO_CHECK(d->ldx >= d->C, "taco_linear_fwd: ldx < C");
     if (d->impl == TACO_IMPL_SIMT) return taco_linear_simt(d, (cudaStream_t)stream);
-    if (d->impl == TACO_IMPL_TC) return taco_linear_tc(d, (cudaStream_t)stream);
+    if (d->impl == TACO_IMPL_TC || d->impl == TACO_IMPL_TC3) return taco_linear_tc(d, (cudaStream_t)stream);
     taco_set_error("taco_linear_fwd: unknown impl %d", d->impl);
     return 1;
+}
+
+int taco_pack_weight_x3(const float* W, int taps, int C, int N, float* dst_hi, float* dst_lo, int64_t ld_dst, void* stream) {
+    TACO_CHECK(W && dst_hi && dst_lo && taps >= 1 && C >= 1 && N >= 1, "taco_pack_weight_x3: bad arguments");
+    return taco_pack_weight_x3_impl(W, taps, C, N, dst_hi, dst_lo, ld_dst, (cudaStream_t)stream);
 }
 
 int taco_pack_weight(const float* W, int taps, int C, int N, float* dst, int64_t ld_dst, void* stream) {

@@ -53,8 +53,8 @@
 namespace {
 
 constexpr int NCTA = 128;
-constexpr int NTHR = 256;
-constexpr int NWARP = 8;
+constexpr int NTHR = 512;      // 16 warps: 4 per SM sub-partition (the step is a chain of short dependent instruction sequences:
+constexpr int NWARP = 16;      // with 2 warps per scheduler every fixed latency was exposed -- 'wait' was the top stall reason)
 constexpr int RPG = 8;         // rows per row group
 constexpr int NS = 32;         // column slices
 constexpr int BPAD = 32;
@@ -81,17 +81,17 @@ enum StageId { ST_IN = 0, ST_G0, ST_G1, ST_G2, ST_C0, ST_C1, ST_C2, ST_PM, ST_OQ
 // bias rows in smem ([row][16])
 enum BiasRow { BR_IN = 0, BR_INX, BR_G0, BR_G1, BR_G2, BR_C0, BR_C1, BR_C2, BR_Y, BR_QP, BR_PM, BR_P2, NBR };
 // item kinds: fragment width / tiles / k-tile slots per warp
-enum ItemKind { IK_F2S4 = 0, IK_F4S4, IK_F4S4X2, IK_F2S6, IK_PM, IK_AP2 };
+enum ItemKind { IK_F2 = 0, IK_F4, IK_F4X2, IK_F2CP, IK_PM, IK_AP2 };   // 8 / 16 / 2x16 columns x 2 k-tile slots; [ctx|p2]: 3 slots
 // output slots of the per-CTA output-offset table
 enum OutId { O_Z = 0, O_RH0, O_RH1, O_RH2, O_H0, O_H1, O_H2, O_S, O_Q, O_P1Y, O_P1M, O_P2, NOUT };
 
 struct SegDesc {
     int K;             // contraction length (multiple of 8)
     int FL;            // floats per lane and k-tile: 4 = 16 weight columns, 2 = 8 weight columns
-    int nw;            // warps that split K (8, or 4 for the P2 stage)
-    int kpw;           // k-tile slots per warp (4, 6 or 8; padded with zeros)
+    int nw;            // warps that split K (16, or 8 for the P2 stage)
+    int kpw;           // k-tile slots per warp (2, 3 or 4; padded with zeros)
     int smem_off;      // float offset inside the resident smem region, or -1: lives in TMEM
-    int tmem_col;      // column offset inside the warp's 256-column TMEM half
+    int tmem_col;      // column offset inside the warp's 128-column TMEM window
     int slice_floats;  // nw * kpw * 32 * FL
     int64_t g_off;     // float offset of slice 0 in the packed buffer
 };
@@ -218,6 +218,13 @@ __device__ __forceinline__ void tm_st4(uint32_t taddr, float a, float b, float c
                  "r"(__float_as_uint(c)), "r"(__float_as_uint(d)) : "memory");
 }
 __device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_ld4(uint32_t taddr, float (&w)[4]) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tm_ld8(uint32_t taddr, float (&w)[8]) {
     uint32_t r[8];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -273,9 +280,9 @@ __device__ __forceinline__ void ktile_mma(float (&acc)[3][4], uint32_t bh0, uint
 
 // ---- operand ingest + multiply of one item -------------------------------------------------------------------------
 // Slot i of warp-index `widx` (of `nw` warps splitting K) covers k-tile widx + nw*i; its 8 rows x 8 words sit at
-// p0 + i*nw*64 (p0 already contains this lane's g*8 + 2*tg).  NS = slots per call (4 or 6); s0 = first live slot.
+// p0 + i*nw*64 (p0 already contains this lane's g*8 + 2*tg).  NS_ = slots per call (2, 3 or 4); s0 = first live slot.
 template <int NS_>
-__device__ __forceinline__ void issue_loads(ulonglong2 (&v)[6], const uint64_t* p0, int nkt, int widx, int nw, int s0) {
+__device__ __forceinline__ void issue_loads(ulonglong2 (&v)[4], const uint64_t* p0, int nkt, int widx, int nw, int s0) {
 #pragma unroll
     for (int i = 0; i < NS_; ++i)
         if (i >= s0 && widx + nw * i < nkt) v[i] = ll_load2(p0 + (size_t)i * nw * 64);
@@ -283,7 +290,7 @@ __device__ __forceinline__ void issue_loads(ulonglong2 (&v)[6], const uint64_t* 
 // weight word: >= 0: float offset in the resident smem region; bit 31 set: TMEM column inside the warp's window.
 // wslot = index of the first fragment slot used by this call in the segment's [warp][slot] block, tcoff = its TMEM column.
 template <int FL, int MT, int NS_>
-__device__ __forceinline__ void consume(float (&acc)[2][3][4], ulonglong2 (&v)[6], const uint64_t* p0, int nkt, int widx, int nw, int s0,
+__device__ __forceinline__ void consume(float (&acc)[2][3][4], ulonglong2 (&v)[4], const uint64_t* p0, int nkt, int widx, int nw, int s0,
                                         uint32_t tag, uint32_t w1, uint32_t w2, int wslot, int tcoff, const float* res_s, uint32_t tm_lane_col,
                                         int lane, long long* ck) {
     float w[MT][NS_ * FL];
@@ -298,10 +305,10 @@ __device__ __forceinline__ void consume(float (&acc)[2][3][4], ulonglong2 (&v)[6
                 if constexpr (FL == 4) { const float4 t = *reinterpret_cast<const float4*>(wp + (size_t)i * 32 * FL); w[mt][4 * i] = t.x; w[mt][4 * i + 1] = t.y; w[mt][4 * i + 2] = t.z; w[mt][4 * i + 3] = t.w; }
                 else                   { const float2 t = *reinterpret_cast<const float2*>(wp + (size_t)i * 32 * FL); w[mt][2 * i] = t.x; w[mt][2 * i + 1] = t.y; }
             }
-        } else if constexpr (NS_ == 4) {
+        } else if constexpr (NS_ * FL == 4 || NS_ * FL == 8) {
             const uint32_t ta = tm_lane_col + (ww & 0x7fffffffu) + (uint32_t)tcoff;
-            if constexpr (FL == 4) tm_ld16(ta, w[mt]);
-            else                   tm_ld8(ta, w[mt]);
+            if constexpr (NS_ * FL == 8) tm_ld8(ta, w[mt]);
+            else                         tm_ld4(ta, w[mt]);
         }
     }
     if (ck) ck[1] = clock64();
@@ -324,11 +331,11 @@ struct ItemRec { uint32_t base; int tagd; int nkt; int kind; int stage; int skip
 
 __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_kernel(const __grid_constant__ DecParams P) {
     extern __shared__ __align__(16) float smem[];
-    // smem map (floats): [0,16) tmem ptr | part 4096 | part2 256 | loc 384 | bias 256 | att 704 | xbuf 1024 | xstat 64 | itab 192 | kv | weights
+    // smem map (floats): [0,16) tmem ptr | part 6144 | part2 512 | loc 384 | bias 256 | att 704 | xbuf 1024 | xstat 64 | itab 192 | kv | weights
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem);
-    float* part_s = smem + 16;                                    // [2 parity][8 warps][2 tiles][128]
-    float* part2_s = part_s + 4096;                               // [4 warps][64]   (P2, warps 4-7)
-    float* loc_s = part2_s + 256;                                 // h_loc[3][64] | u_loc[64] | z_loc[64]
+    float* part_s = smem + 16;                                    // [3 buffers][16 warps][128]: two alternate, the third is OQP's 2nd tile
+    float* part2_s = part_s + 6144;                               // [8 warps][64]   (P2, warps 8-15)
+    float* loc_s = part2_s + 512;                                 // h_loc[3][64] | u_loc[64] | z_loc[64]
     float* bias_s = loc_s + 384;                                  // [NBR][16]
     float* att_s = bias_s + 256;                                  // eq[256] | v[256] | e[64] | p[64] | misc[64]
     uint64_t* xbuf = reinterpret_cast<uint64_t*>(att_s + 704);    // [2 parity][4 src][64] words
@@ -394,7 +401,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
         ItemRec r;
         r.base = 0; r.nkt = 0; r.w1 = r.w2 = 0;
         r.tagd = it.tagd; r.kind = it.kind | (it.pre << 8); r.stage = it.stage; r.skip0 = it.skip0;
-        if (it.kind <= IK_F2S6) {
+        if (it.kind <= IK_F2CP) {
             const SegDesc& d = P.seg[it.seg];
             r.base = (uint32_t)(P.buf[it.src] + (int64_t)rg * buf_nkt(it.src) * 64);
             r.nkt = d.K >> 3;
@@ -415,8 +422,8 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    // this warp's private TMEM window: lanes 32*(warp%4).., columns 256*(warp/4)..
-    const uint32_t tm_lane_col = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * 256u;
+    // this warp's private TMEM window: lanes 32*(warp%4).., columns 128*(warp/4)..
+    const uint32_t tm_lane_col = tmem_base + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * 128u;
 
     // ---- one-time preload of the weight slices: smem segments by coalesced copies, TMEM segments by tcgen05.st ----
     for (int sg = 0; sg < NSEG; ++sg) {
@@ -427,7 +434,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
             float4* d4 = reinterpret_cast<float4*>(res_s + d.smem_off);
             for (int i = tid; i < d.slice_floats / 4; i += NTHR) d4[i] = __ldg(s4 + i);
         } else {
-            const int widx = (d.nw == NWARP) ? warp : warp - 4;
+            const int widx = (d.nw == NWARP) ? warp : warp - 8;
             if (widx >= 0) {                                            // warp-uniform
                 for (int i = 0; i < d.kpw; ++i) {
                     const float* wp = src + ((size_t)(widx * d.kpw + i) * 32 + lane) * d.FL;
@@ -472,7 +479,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
         for (int a1 = 0; a1 < 3; ++a1)
 #pragma unroll
             for (int a2 = 0; a2 < 4; ++a2) acc[a0][a1][a2] = 0.f;
-    ulonglong2 v[6];                                    // operand words in flight
+    ulonglong2 v[4];                                    // operand words in flight
 
     int par = 0;                                        // parity of the partial-tile buffer
     const bool tracer = (cta == 0 && tid == 0 && A.step_ns != nullptr);
@@ -482,11 +489,11 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
     // =========================================================================================================
     // finish a stage: per-warp partial tiles -> smem, cross-warp sum, epilogue (one thread per output)
     // =========================================================================================================
-    auto store_partials = [&](float* part, int MT, bool full16) {
+    auto store_partials = [&](float* part, float* part_b, int MT, bool full16) {
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
             if (mt < MT) {
-                float* pw = part + (warp * 2 + mt) * 128;
+                float* pw = (mt ? part_b : part) + warp * 128;
                 *reinterpret_cast<float2*>(pw + g * 8 + 2 * tg) =
                     make_float2((acc[mt][0][0] + acc[mt][1][0]) + acc[mt][2][0], (acc[mt][0][1] + acc[mt][1][1]) + acc[mt][2][1]);
                 if (full16)
@@ -501,11 +508,11 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
 #pragma unroll
                 for (int a2 = 0; a2 < 4; ++a2) acc[a0][a1][a2] = 0.f;
     };
-    auto sum8 = [&](const float* part, int mt, int pidx) {
-        float sv = 0.f;
+    auto sum16 = [&](const float* part, int pidx) {
+        float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-        for (int w = 0; w < NWARP; ++w) sv += part[(w * 2 + mt) * 128 + pidx];
-        return sv;
+        for (int w = 0; w < NWARP; w += 2) { s0 += part[w * 128 + pidx]; s1 += part[(w + 1) * 128 + pidx]; }
+        return s0 + s1;
     };
     // epilogue thread mapping: lanes run over the 8 weight columns first (8-byte words of one row are then
     // contiguous: a warp writes two full 128-byte lines), rows next, the second 8 columns (G: u gates) last.
@@ -515,24 +522,24 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
     const int e_row = row0 + e_brow;
     const int e_word = e_brow * 8 + perm8(e_wc);             // word inside this CTA's k-tile block of an exchange buffer
 
-    // ---- attention of step t on warps 0..3 (128 threads): scores, partial softmax / context, cluster merge ----
+    // ---- attention of step t on warps 0..7 (256 threads): scores, partial softmax / context, cluster merge ----
     auto attention = [&](int t) {
         const uint32_t tag = (uint32_t)t + 1;
         const int xp = t & 1;
-        uint64_t* ctx_out = ws + P.buf[B_CP] + (int64_t)(arow >> 3) * 48 * 64 + (8 * (int)aq + (tid >> 3)) * 64 + (arow & 7) * 8 + perm8(tid & 7);
+        uint64_t* ctx_out = ws + P.buf[B_CP] + (int64_t)(arow >> 3) * 48 * 64 + (8 * (int)aq + ((tid & 63) >> 3)) * 64 + (arow & 7) * 8 + perm8(tid & 7);
         if (arow >= B) {                                // padding utterance: publish a zero context (consumers poll every row)
             if (tid < 64) ll_store(ctx_out, 0.f, tag + 1);
             return;
         }
-        {   // q(t) of this utterance -> e^{2q}
+        if (tid < 128) {   // q(t) of this utterance -> e^{2q}
             const float2 qq = ll_wait2(ws + P.buf[B_Q] + (int64_t)(arow >> 3) * 2048 + (tid >> 2) * 64 + (arow & 7) * 8 + 2 * (tid & 3), tag);
             const int k0 = ((tid >> 2) << 3) + (tid & 3);        // physical pair (2p, 2p+1) = logical k0, k0+4
             eq_s[k0] = exp2x(qq.x);
             eq_s[k0 + 4] = exp2x(qq.y);
         }
-        named_bar(1, 128);
+        named_bar(1, 256);
         {   // scores: lane owns 8 consecutive depth indices (its e^{2q}, v slices stay in registers), warp w owns
-            // positions j = w, w+4, ...; eight positions are reduced over the warp with one transposing butterfly
+            // positions j = w, w+8, ...; four positions are reduced over the warp with one transposing butterfly
             float eq[8], vv[8];
             {
                 const float4 q0 = *reinterpret_cast<const float4*>(eq_s + 8 * lane), q1 = *reinterpret_cast<const float4*>(eq_s + 8 * lane + 4);
@@ -541,11 +548,11 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
                 vv[0] = v0.x; vv[1] = v0.y; vv[2] = v0.z; vv[3] = v0.w; vv[4] = v1.x; vv[5] = v1.y; vv[6] = v1.z; vv[7] = v1.w;
             }
             const float V0 = misc_s[0];
-            for (int jb = 0; jb < Tq; jb += 32) {       // 8 positions per warp and round
-                float a8[8];
+            for (int jb = 0; jb < Tq; jb += 32) {       // 4 positions per warp and round
+                float a4[4];
 #pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                    const int j = jb + warp + 4 * jj;
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int j = jb + warp + 8 * jj;
                     float a = 0.f;
                     if (j < Tq) {                       // warp-uniform
                         const float4 k0 = *reinterpret_cast<const float4*>(ek_s + j * KV_LD + 8 * lane);
@@ -559,35 +566,30 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
                         a = fmaf(vv[6], rcp_fast(fmaf(k1.z, eq[6], 1.0f)), a);
                         a = fmaf(vv[7], rcp_fast(fmaf(k1.w, eq[7], 1.0f)), a);
                     }
-                    a8[jj] = a;
+                    a4[jj] = a;
                 }
-                // transposing butterfly: after the three halving steps lane group (lane>>2) holds position jj = lane>>2
-                float b4[4], b2[2], b1;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float send = (lane & 16) ? a8[k] : a8[k + 4];
-                    const float keep = (lane & 16) ? a8[k + 4] : a8[k];
-                    b4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-                }
+                // transposing butterfly: after the two halving steps lane group (lane>>3) holds position jj = lane>>3
+                float b2[2], b1;
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
-                    const float send = (lane & 8) ? b4[k] : b4[k + 2];
-                    const float keep = (lane & 8) ? b4[k + 2] : b4[k];
-                    b2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                    const float send = (lane & 16) ? a4[k] : a4[k + 2];
+                    const float keep = (lane & 16) ? a4[k + 2] : a4[k];
+                    b2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
                 }
                 {
-                    const float send = (lane & 4) ? b2[0] : b2[1];
-                    const float keep = (lane & 4) ? b2[1] : b2[0];
-                    b1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                    const float send = (lane & 8) ? b2[0] : b2[1];
+                    const float keep = (lane & 8) ? b2[1] : b2[0];
+                    b1 = keep + __shfl_xor_sync(0xffffffffu, send, 8);
                 }
+                b1 += __shfl_xor_sync(0xffffffffu, b1, 4);
                 b1 += __shfl_xor_sync(0xffffffffu, b1, 2);
                 b1 += __shfl_xor_sync(0xffffffffu, b1, 1);
-                const int jj = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-                const int j = jb + warp + 4 * jj;
-                if ((lane & 3) == 0 && j < Tq) e_s[j] = ((int)aq * Tq + j < my_len) ? fmaf(-2.0f, b1, V0) : -INFINITY;
+                const int jj = ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1);
+                const int j = jb + warp + 8 * jj;
+                if ((lane & 7) == 0 && j < Tq) e_s[j] = ((int)aq * Tq + j < my_len) ? fmaf(-2.0f, b1, V0) : -INFINITY;
             }
         }
-        named_bar(1, 128);
+        named_bar(1, 256);
         // quarter statistics (every warp redundantly; Tq <= 64)
         const float e0 = (lane < Tq) ? e_s[lane] : -INFINITY;
         const float e1 = (lane + 32 < Tq) ? e_s[lane + 32] : -INFINITY;
@@ -607,20 +609,18 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
             dsm_store(xstat + (xp * 4 + aq) * 2, (uint32_t)tid, m, tag);
             dsm_store(xstat + (xp * 4 + aq) * 2 + 1, (uint32_t)tid, ssum, tag);
         }
-        named_bar(1, 128);
-        {   // partial context: columns 2 tid, 2 tid + 1; pushed to the CTA that owns them (64 columns per CTA)
+        named_bar(1, 256);
+        {   // partial context: column tid; pushed to the CTA that owns it (64 columns per CTA)
             float c0 = 0.f, c1 = 0.f;
 #pragma unroll 4
-            for (int j = 0; j < Tq; ++j) {
-                const float p = p_s[j];
-                const float2 vv2 = *reinterpret_cast<const float2*>(vals_s + j * ENC + 2 * tid);
-                c0 = fmaf(p, vv2.x, c0); c1 = fmaf(p, vv2.y, c1);
+            for (int j = 0; j + 1 < Tq; j += 2) {
+                c0 = fmaf(p_s[j], vals_s[j * ENC + tid], c0);
+                c1 = fmaf(p_s[j + 1], vals_s[(j + 1) * ENC + tid], c1);
             }
-            const uint32_t dst = (uint32_t)tid >> 5;
-            const int i0 = (2 * tid) & 63;
-            dsm_store(xbuf + (xp * 4 + aq) * 64 + i0, dst, c0, tag);
-            dsm_store(xbuf + (xp * 4 + aq) * 64 + i0 + 1, dst, c1, tag);
+            if (Tq & 1) c0 = fmaf(p_s[Tq - 1], vals_s[(Tq - 1) * ENC + tid], c0);
+            dsm_store(xbuf + (xp * 4 + aq) * 64 + (tid & 63), (uint32_t)tid >> 6, c0 + c1, tag);
         }
+        if (tid >= 128) return;
         // merge: global max / sum from the four quarter statistics
         float mq[4], wq[4], M = -INFINITY, S = 0.f, w_own = 0.f;
 #pragma unroll
@@ -644,20 +644,18 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
         }
     };
 
-    // ---- second pre-net layer of step tb on warps 4..7: p2(tb) = relu(p1(tb) . W2 + b2) ----
+    // ---- second pre-net layer of step tb on warps 8..15: p2(tb) = relu(p1(tb) . W2 + b2) ----
     auto prenet2 = [&](int tb) {
         const uint32_t tag = (uint32_t)tb + 1;
-        const int widx = warp - 4;
+        const int widx = warp - 8;
         bool from_y = (tb > 0);
         if (A.mode == TACO_DEC_TEACHER) from_y = false;
         else if (A.mode == TACO_DEC_SCHED) from_y = (tb > 0) && (myrow < B) && (A.sample_mask[(int64_t)(tb - 1) * B + myrow] != 0);
         const uint64_t* p0 = ws + P.buf[from_y ? B_P1Y : B_P1M] + (int64_t)rg * 2048 + widx * 64 + lane_w;
         const SegDesc& sd = P.seg[SG_P2];
         const uint32_t w1 = sd.smem_off >= 0 ? (uint32_t)sd.smem_off : (0x80000000u | (uint32_t)sd.tmem_col);
-        issue_loads<4>(v, p0, 32, widx, 4, 0);
-        consume<2, 1, 4>(acc, v, p0, 32, widx, 4, 0, tag, w1, w1, widx * 8, 0, res_s, tm_lane_col, lane, nullptr);
-        issue_loads<4>(v, p0 + 16 * 64, 32, widx + 16, 4, 0);
-        consume<2, 1, 4>(acc, v, p0 + 16 * 64, 32, widx + 16, 4, 0, tag, w1, w1, widx * 8 + 4, 8, res_s, tm_lane_col, lane, nullptr);
+        issue_loads<4>(v, p0, 32, widx, 8, 0);
+        consume<2, 1, 4>(acc, v, p0, 32, widx, 8, 0, tag, w1, w1, widx * 4, 0, res_s, tm_lane_col, lane, nullptr);
         float* pw = part2_s + widx * 64;
         *reinterpret_cast<float2*>(pw + g * 8 + 2 * tg) =
             make_float2((acc[0][0][0] + acc[0][1][0]) + acc[0][2][0], (acc[0][0][1] + acc[0][1][1]) + acc[0][2][1]);
@@ -665,56 +663,52 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
         for (int a1 = 0; a1 < 3; ++a1)
 #pragma unroll
             for (int a2 = 0; a2 < 4; ++a2) acc[0][a1][a2] = 0.f;
-        named_bar(2, 128);
-        const int e = tid - 128;
+        named_bar(2, 256);
+        const int e = tid - 256;
         if (e < 32) {                                    // 8 rows x 4 columns, columns fastest
             const int wcol = e & 3, brow = e >> 2, row = row0 + brow, col = 4 * cs + wcol, pi = wcol * 8 + brow;
-            float pv = part2_s[pi] + part2_s[64 + pi] + part2_s[128 + pi] + part2_s[192 + pi] + bias_s[BR_P2 * 16 + wcol];
+            float pv = bias_s[BR_P2 * 16 + wcol];
+#pragma unroll
+            for (int w = 0; w < 8; ++w) pv += part2_s[w * 64 + pi];
             pv = fmaxf(pv, 0.f);
             if (A.keep2 && row < B && tb < T) pv = A.keep2[((int64_t)tb * B + row) * 128 + col] ? pv * A.keep_scale : 0.f;
             ll_store(ws + otab[O_P2] + brow * 8 + perm8(4 * (cs & 1) + wcol), pv, tag);
         }
-        named_bar(2, 128);                               // part2_s may be rewritten
+        named_bar(2, 256);                               // part2_s may be rewritten
     };
 
     // ---- first pre-net layer of step tb from the teacher frame (or zeros): p1m(tb) = relu(x . W1 + b1) ----
     auto prenet1_teacher = [&](int tb) {
         const bool have = (A.mode != TACO_DEC_INFER) && (myrow < B) && (tb < T);
         const SegDesc& sd = P.seg[SG_PM];
-        float w[8];
+        float w[4];
         if (sd.smem_off >= 0) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 t2 = *reinterpret_cast<const float2*>(res_s + sd.smem_off + ((size_t)(warp * sd.kpw + i) * 32 + lane) * 2);
-                w[2 * i] = t2.x; w[2 * i + 1] = t2.y;
-            }
+            const float2 t2 = *reinterpret_cast<const float2*>(res_s + sd.smem_off + ((size_t)(warp * sd.kpw) * 32 + lane) * 2);
+            w[0] = t2.x; w[1] = t2.y; w[2] = w[3] = 0.f;
         } else {
             __syncwarp();
-            tm_ld8(tm_lane_col + (uint32_t)sd.tmem_col, w);
+            tm_ld4(tm_lane_col + (uint32_t)sd.tmem_col, w);
         }
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int kt = warp + 8 * i;
-            if (kt < MF / 8) {                           // warp-uniform
-                float xa = 0.f, xb = 0.f;
-                if (have) {
-                    const float* mp = A.mel + ((int64_t)myrow * T + tb) * OUT + (OUT - MF) + kt * 8 + tg;
-                    xa = __ldg(mp); xb = __ldg(mp + 4);
-                }
-                uint32_t bh0, bl0, bh1, bl1;
-                split_tf32(xa, bh0, bl0);
-                split_tf32(xb, bh1, bl1);
-                __syncwarp();
-                ktile_mma<2>(acc[0], bh0, bl0, bh1, bl1, &w[2 * i]);
+        if (warp < MF / 8) {                             // k-tile = warp (10 k-tiles); warp-uniform
+            float xa = 0.f, xb = 0.f;
+            if (have) {
+                const float* mp = A.mel + ((int64_t)myrow * T + tb) * OUT + (OUT - MF) + warp * 8 + tg;
+                xa = __ldg(mp); xb = __ldg(mp + 4);
             }
+            uint32_t bh0, bl0, bh1, bl1;
+            split_tf32(xa, bh0, bl0);
+            split_tf32(xb, bh1, bl1);
+            __syncwarp();
+            ktile_mma<2>(acc[0], bh0, bl0, bh1, bl1, &w[0]);
         }
     };
 
     auto finish = [&](int stage, int t) {
         float* part = part_s + par * 2048;
+        float* part_b = part_s + 2 * 2048;               // second tile of OQP (its previous readers are a full step behind)
         par ^= 1;
         const bool full16 = (stage >= ST_G0 && stage <= ST_G2) || stage == ST_OQP;
-        store_partials(part, stage == ST_OQP ? 2 : 1, full16);
+        store_partials(part, part_b, stage == ST_OQP ? 2 : 1, full16);
         if (cktr) cktr[4] = clock64();
         __syncthreads();
         if (cktr) cktr[5] = clock64();
@@ -722,7 +716,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
         switch (stage) {
             case ST_IN:
                 if (tid < 64) {
-                    float zv = sum8(part, 0, e_pidx) + bias_s[BR_IN * 16 + e_wc];
+                    float zv = sum16(part, e_pidx) + bias_s[BR_IN * 16 + e_wc];
                     if (t > 0) zv += bias_s[BR_INX * 16 + e_wc];
                     z_loc[e_loc] = zv;
                     ll_store(ws + otab[O_Z] + e_word, zv, tag);
@@ -731,7 +725,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
             case ST_G0: case ST_G1: case ST_G2:
                 if (tid < 128) {
                     const int gi = stage - ST_G0;
-                    const float gt = sigmoidf_acc(sum8(part, 0, e_pidx) + bias_s[(BR_G0 + gi) * 16 + e_wc + 8 * e_hi]);
+                    const float gt = sigmoidf_acc(sum16(part, e_pidx) + bias_s[(BR_G0 + gi) * 16 + e_wc + 8 * e_hi]);
                     if (!e_hi) ll_store(ws + otab[O_RH0 + gi] + e_word, gt * h_loc[gi * 64 + e_loc], tag);   // r * h
                     else u_loc[e_loc] = gt;                                                                // u stays local
                 }
@@ -739,7 +733,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
             case ST_C0: case ST_C1: case ST_C2:
                 if (tid < 64) {
                     const int gi = stage - ST_C0;
-                    const float cnd = tanhf_acc(sum8(part, 0, e_pidx) + bias_s[(BR_C0 + gi) * 16 + e_wc]);
+                    const float cnd = tanhf_acc(sum16(part, e_pidx) + bias_s[(BR_C0 + gi) * 16 + e_wc]);
                     const float uu = u_loc[e_loc];
                     const float hn = uu * h_loc[gi * 64 + e_loc] + (1.0f - uu) * cnd;
                     h_loc[gi * 64 + e_loc] = hn;
@@ -751,14 +745,14 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
             case ST_PM:
                 if (tid < 64) {                              // here t = tb, the step the pre-net output belongs to
                     const int col = 8 * cs + e_wc;
-                    float pv = fmaxf(sum8(part, 0, e_pidx) + bias_s[BR_PM * 16 + e_wc], 0.f);
+                    float pv = fmaxf(sum16(part, e_pidx) + bias_s[BR_PM * 16 + e_wc], 0.f);
                     if (A.keep1 && e_row < B && t < T) pv = A.keep1[((int64_t)t * B + e_row) * 256 + col] ? pv * A.keep_scale : 0.f;
                     ll_store(ws + otab[O_P1M] + e_word, pv, tag);
                 }
                 break;
-            case ST_OQP: {
+            case ST_OQP: if (tid < 256) {
                 const int mt = tid >> 7;
-                const float v0 = sum8(part, mt, e_pidx) + bias_s[(BR_Y + mt) * 16 + e_wc + 8 * e_hi];
+                const float v0 = sum16(mt ? part_b : part, e_pidx) + bias_s[(BR_Y + mt) * 16 + e_wc + 8 * e_hi];
                 if (mt == 0) {                               // y(t): the output itself (nothing downstream reads it)
                     const int wcol = e_wc + 8 * e_hi, col = cs * NCY + wcol;
                     if (wcol < NCY && col < OUT && e_row < B) A.y[((int64_t)e_row * T + t) * OUT + col] = v0;
@@ -782,7 +776,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
     // =========================================================================================================
     prenet1_teacher(0);
     finish(ST_PM, 0);
-    if (warp >= 4) prenet2(0);
+    if (warp >= 8) prenet2(0);
 
     // =========================================================================================================
     // T decoder steps x the item program
@@ -799,7 +793,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
             if (tracer && t >= 10 && t < 14) { ck = reinterpret_cast<long long*>(ws + P.trace_off + 16 * T + 16 + ((t - 10) * MAX_ITEMS + ii) * 8); ck[3] = clock64(); }
             cktr = ck;
             if (kind == IK_AP2) {
-                if (warp < 4) attention(t);
+                if (warp < 8) attention(t);
                 else if (t + 1 < T) prenet2(t + 1);
                 if (tracer) ws[P.trace_off + (trace_i++)] = globaltimer_ns();
                 continue;
@@ -813,16 +807,16 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
                 const uint64_t* p0 = ws + (uint32_t)ra.x + warp * 64 + lane_w;
                 const uint32_t tag = (uint32_t)(t + ra.y);
                 const int nkt = ra.z;
-                if (kind == IK_F2S6) {
-                    issue_loads<6>(v, p0, nkt, warp, NWARP, s0);
+                if (kind == IK_F2CP) {
+                    issue_loads<3>(v, p0, nkt, warp, NWARP, s0);
                     if (ck) ck[0] = clock64();
-                    consume<2, 1, 6>(acc, v, p0, nkt, warp, NWARP, s0, tag, (uint32_t)rb.z, 0u, warp * 6, 0, res_s, tm_lane_col, lane, ck);
+                    consume<2, 1, 3>(acc, v, p0, nkt, warp, NWARP, s0, tag, (uint32_t)rb.z, 0u, warp * 3, 0, res_s, tm_lane_col, lane, ck);
                 } else {
-                    if (!pref) issue_loads<4>(v, p0, nkt, warp, NWARP, 0);
+                    if (!pref) issue_loads<2>(v, p0, nkt, warp, NWARP, 0);
                     if (ck) ck[0] = clock64();
-                    if (kind == IK_F4S4X2)    consume<4, 2, 4>(acc, v, p0, nkt, warp, NWARP, 0, tag, (uint32_t)rb.z, (uint32_t)rb.w, warp * 4, 0, res_s, tm_lane_col, lane, ck);
-                    else if (kind == IK_F4S4) consume<4, 1, 4>(acc, v, p0, nkt, warp, NWARP, 0, tag, (uint32_t)rb.z, 0u, warp * 4, 0, res_s, tm_lane_col, lane, ck);
-                    else                      consume<2, 1, 4>(acc, v, p0, nkt, warp, NWARP, 0, tag, (uint32_t)rb.z, 0u, warp * 4, 0, res_s, tm_lane_col, lane, ck);
+                    if (kind == IK_F4X2)    consume<4, 2, 2>(acc, v, p0, nkt, warp, NWARP, 0, tag, (uint32_t)rb.z, (uint32_t)rb.w, warp * 2, 0, res_s, tm_lane_col, lane, ck);
+                    else if (kind == IK_F4) consume<4, 1, 2>(acc, v, p0, nkt, warp, NWARP, 0, tag, (uint32_t)rb.z, 0u, warp * 2, 0, res_s, tm_lane_col, lane, ck);
+                    else                    consume<2, 1, 2>(acc, v, p0, nkt, warp, NWARP, 0, tag, (uint32_t)rb.z, 0u, warp * 2, 0, res_s, tm_lane_col, lane, ck);
                 }
             }
             pref = false;
@@ -832,7 +826,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
                 if (ii + 1 < n_items) {
                     const int4 na = *reinterpret_cast<const int4*>(&itab[ii + 1]);
                     if ((na.w >> 8) & 1) {
-                        issue_loads<4>(v, ws + (uint32_t)na.x + warp * 64 + lane_w, na.z, warp, NWARP, 0);
+                        issue_loads<2>(v, ws + (uint32_t)na.x + warp * 64 + lane_w, na.z, warp, NWARP, 0);
                         pref = true;
                     }
                 }
@@ -912,12 +906,12 @@ FusedTail fused_tail(int r, int64_t slices_total) {
 
 void build_seg_table(SegDesc* sd, int64_t* total_floats) {
     auto set = [&](int id, int K, int FL, int nw, int kpw) { sd[id].K = K; sd[id].FL = FL; sd[id].nw = nw; sd[id].kpw = kpw; };
-    set(SG_IN_S, 256, 2, 8, 4); set(SG_IN_CP, 384, 2, 8, 6);
+    set(SG_IN_S, 256, 2, 16, 2); set(SG_IN_CP, 384, 2, 16, 3);
     for (int i = 0; i < 3; ++i) {
-        set(SG_G_H0 + i, 256, 4, 8, 4); set(SG_G_X0 + i, 256, 4, 8, 4);
-        set(SG_C_X0 + i, 256, 2, 8, 4); set(SG_C_RH0 + i, 256, 2, 8, 4);
+        set(SG_G_H0 + i, 256, 4, 16, 2); set(SG_G_X0 + i, 256, 4, 16, 2);
+        set(SG_C_X0 + i, 256, 2, 16, 2); set(SG_C_RH0 + i, 256, 2, 16, 2);
     }
-    set(SG_Y, 256, 4, 8, 4); set(SG_QP, 256, 4, 8, 4); set(SG_PM, MF, 2, 8, 4); set(SG_P2, 256, 2, 4, 8);
+    set(SG_Y, 256, 4, 16, 2); set(SG_QP, 256, 4, 16, 2); set(SG_PM, MF, 2, 16, 2); set(SG_P2, 256, 2, 8, 4);
     int64_t off = 0;
     for (int s = 0; s < NSEG; ++s) {
         sd[s].slice_floats = sd[s].nw * sd[s].kpw * 32 * sd[s].FL;
@@ -1035,23 +1029,23 @@ extern "C" int taco_decoder_fwd(const taco_decoder_args* a, void* stream) {
     auto item = [&](int seg, int seg2, int src, int tagd, int stage, int skip0, int kind, int pre) {
         P.items[n++] = Item{seg, seg2, src, tagd, stage, skip0, kind, pre};
     };
-    item(SG_IN_S, -1, B_S, 0, ST_NONE, 99, IK_F2S4, 1);                       // off-chain: s(t-1)
-    item(SG_IN_CP, -1, B_CP, 1, ST_IN, 4, IK_F2S6, 0);                        // [ctx(t-1) | p2(t)] (no context at t = 0)
+    item(SG_IN_S, -1, B_S, 0, ST_NONE, 99, IK_F2, 1);                         // off-chain: s(t-1)
+    item(SG_IN_CP, -1, B_CP, 1, ST_IN, 2, IK_F2CP, 0);                        // [ctx(t-1) | p2(t)] (no context at t = 0)
     for (int i = 0; i < 3; ++i) {
         const int x = (i == 0) ? B_Z : B_H0 + (i - 1);
-        item(SG_G_H0 + i, -1, B_H0 + i, 0, ST_NONE, 99, IK_F4S4, 1);          // off-chain: h_i(t-1)
-        item(SG_G_X0 + i, -1, x, 1, ST_G0 + i, 0, IK_F4S4, 0);
-        item(SG_C_X0 + i, -1, x, 1, ST_NONE, 0, IK_F2S4, 1);                  // off-chain: x (already consumed by the gate stage)
-        item(SG_C_RH0 + i, -1, B_RH0 + i, 1, ST_C0 + i, 0, IK_F2S4, 0);
+        item(SG_G_H0 + i, -1, B_H0 + i, 0, ST_NONE, 99, IK_F4, 1);          // off-chain: h_i(t-1)
+        item(SG_G_X0 + i, -1, x, 1, ST_G0 + i, 0, IK_F4, 0);
+        item(SG_C_X0 + i, -1, x, 1, ST_NONE, 0, IK_F2, 1);                  // off-chain: x (already consumed by the gate stage)
+        item(SG_C_RH0 + i, -1, B_RH0 + i, 1, ST_C0 + i, 0, IK_F2, 0);
     }
     if (a->mode != TACO_DEC_INFER) item(-1, -1, 0, 0, ST_PM, 0, IK_PM, 0);    // teacher frame t+1 -> p1m(t+1), off-chain
-    item(SG_Y, SG_QP, B_S, 1, ST_OQP, 0, IK_F4S4X2, 0);
+    item(SG_Y, SG_QP, B_S, 1, ST_OQP, 0, IK_F4X2, 0);
     item(-1, -1, 0, 0, ST_AP2, 0, IK_AP2, 0);
     P.n_items = n;
 
     // ---- residency: off-chain segments in TMEM (256 columns per warp), on-chain segments in shared memory; when the
     //      keys/values leave too little shared memory (large Tx) further segments move to TMEM ----
-    int off = 16 + 4096 + 256 + 384 + 256 + 704 + 1024 + 64 + 192;
+    int off = 16 + 6144 + 512 + 384 + 256 + 704 + 1024 + 64 + 192;
     off = (off + 31) / 32 * 32;
     P.smem_kv_off = off;
     off += P.Tq * KV_LD + P.Tq * ENC;
@@ -1060,16 +1054,16 @@ extern "C" int taco_decoder_fwd(const taco_decoder_args* a, void* stream) {
     const int budget = (227 * 1024) / 4 - off;
     const int tm_first[] = {SG_IN_S, SG_G_H0, SG_G_H1, SG_G_H2, SG_C_X0, SG_C_X1, SG_C_X2, SG_PM};
     const int sm_order[] = {SG_IN_CP, SG_G_X0, SG_C_RH0, SG_G_X1, SG_C_RH1, SG_G_X2, SG_C_RH2, SG_QP, SG_Y, SG_P2};
-    int tcol8 = 0, tcol4 = 0;            // TMEM columns used in the half of warps 0-3 / 4-7 (8-warp segments use both halves)
+    int tcol_all = 0, tcol_hi = 0;       // TMEM columns used in every warp's 128-column window / in the windows of warps 8-15 only
     auto to_tmem = [&](int s) {
         const int cols = P.seg[s].kpw * P.seg[s].FL;
         if (P.seg[s].nw == NWARP) {
-            const int c = tcol8 > tcol4 ? tcol8 : tcol4;
-            if (c + cols > 256) return false;
-            P.seg[s].tmem_col = c; tcol8 = tcol4 = c + cols;
+            const int c = tcol_all > tcol_hi ? tcol_all : tcol_hi;
+            if (c + cols > 128) return false;
+            P.seg[s].tmem_col = c; tcol_all = tcol_hi = c + cols;
         } else {
-            if (tcol4 + cols > 256) return false;
-            P.seg[s].tmem_col = tcol4; tcol4 += cols;
+            if (tcol_hi + cols > 128) return false;
+            P.seg[s].tmem_col = tcol_hi; tcol_hi += cols;
         }
         P.seg[s].smem_off = -1;
         return true;

@@ -17,6 +17,11 @@
 //    (tcgen05.ld 32x32b -> smem transpose -> fused epilogue -> coalesced 128B row stores).
 //  * 96 KB of pipeline smem per CTA -> 2 CTAs/SM, so one CTA's epilogue overlaps the other's
 //    main loop without a persistent scheduler.
+//  * X3 = true (TACO_IMPL_TC3, precision 'fp32x3'): error-compensated 3xTF32 -- fp32-grade products on
+//    the tensor cores.  Weights arrive pre-split (hi = TF32 head, lo = remainder: taco_pack_weight_x3),
+//    the activation tile is split IN SHARED MEMORY by the four otherwise idle epilogue warps (hi
+//    overwrites the tile, lo goes to a twin tile with the same swizzle), and every k-step issues
+//    lo.hi + hi.lo + hi.hi into the same TMEM accumulator.
 #include <cuda.h>
 #include "epilogue.cuh"
 
@@ -36,13 +41,14 @@ struct TcArgs {
     int tiles_per_seq; // M tiles per utterance
     int tile_stride;   // 128, or 127 when pooling
     int pool;
+    int lo_row0;       // X3: first row of the lo half in the packed weight buffer (= rows of the hi half)
     EpiParams e;
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool X3 = false>
 struct SmemLayout {
     static constexpr int B_STAGE_BYTES = BN * TC_BK * 4;
-    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int STAGE_BYTES = (X3 ? 2 : 1) * (A_STAGE_BYTES + B_STAGE_BYTES);   // X3: A | A_lo | B_hi | B_lo
     static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
     static constexpr int BAR_OFFSET = PIPE_BYTES;
     static constexpr int TOTAL = PIPE_BYTES + 128 + 1024;   // barriers + alignment slack
@@ -70,21 +76,25 @@ __device__ __forceinline__ uint32_t make_idesc() {
     return d;
 }
 
+// fp32 -> nearest TF32-representable value (ties away from zero), two integer instructions
+__device__ __forceinline__ float rn_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // MODE 0: normal epilogue (optional fused max-pool), MODE 1: highway (BN = 2U = 256)
-template <int BN, int STAGES, int MODE>
+template <int BN, int STAGES, int MODE, bool X3>
 __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                       const __grid_constant__ CUtensorMap tmB, TcArgs a) {
-    using L = SmemLayout<BN, STAGES>;
+    using L = SmemLayout<BN, STAGES, X3>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full = empty_bar + STAGES;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* conv_bar = tmem_full + 1;                  // X3: stage split into hi / lo by the converter warps
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(conv_bar + STAGES);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -102,7 +112,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&conv_bar[s], 128); }
         mbar_init(tmem_full, 1);
         mbar_fence_init();
     }
@@ -125,12 +135,13 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t* As = smem + s * L::STAGE_BYTES;
-                uint8_t* Bs = As + A_STAGE_BYTES;
+                uint8_t* Bs = As + (X3 ? 2 : 1) * A_STAGE_BYTES;
                 const int j = it / a.cchunks;
                 const int c0 = (it - j * a.cchunks) * TC_BK;
-                mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
+                mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + (X3 ? 2 : 1) * L::B_STAGE_BYTES);
                 tma_load_3d(As, &tmA, &full_bar[s], c0, t0 + tap0 + j, b);
                 tma_load_2d(Bs, &tmB, &full_bar[s], j * a.Cpad + c0, n0);
+                if (X3) tma_load_2d(Bs + L::B_STAGE_BYTES, &tmB, &full_bar[s], j * a.Cpad + c0, a.lo_row0 + n0);
             }
         }
     } else if (warp == 1) {
@@ -140,16 +151,24 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
             for (int it = 0; it < n_iters; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
-                mbar_wait(&full_bar[s], ph);
+                mbar_wait(X3 ? &conv_bar[s] : &full_bar[s], ph);
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
                 const uint64_t adesc = make_smem_desc(a_addr);
-                const uint64_t bdesc = make_smem_desc(a_addr + A_STAGE_BYTES);
+                const uint64_t bdesc = make_smem_desc(a_addr + (X3 ? 2 : 1) * A_STAGE_BYTES);
 #pragma unroll
                 for (int k = 0; k < TC_BK / 8; ++k) {
                     // advance 8 tf32 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
-                    tc_mma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
-                                (it > 0 || k > 0) ? 1u : 0u);
+                    if (X3) {
+                        const uint64_t alo = make_smem_desc(a_addr + A_STAGE_BYTES) + (uint64_t)(2 * k);
+                        const uint64_t blo = make_smem_desc(a_addr + 2 * A_STAGE_BYTES + L::B_STAGE_BYTES) + (uint64_t)(2 * k);
+                        tc_mma_tf32(tmem_base, alo, bdesc + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);     // lo . hi
+                        tc_mma_tf32(tmem_base, adesc + (uint64_t)(2 * k), blo, idesc, 1u);                               // hi . lo
+                        tc_mma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);         // hi . hi
+                    } else {
+                        tc_mma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
+                                    (it > 0 || k > 0) ? 1u : 0u);
+                    }
                 }
                 tc_commit(&empty_bar[s]);      // frees the stage once these MMAs have read it
             }
@@ -158,6 +177,34 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     } else {
         // ================= epilogue warps (2..5) =================
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        if (X3) {
+            // ---- during the main loop these 128 threads split each landed activation tile: x = hi + lo with hi = the
+            //      nearest TF32 value (written back in place so that the result does not depend on how the tensor core
+            //      narrows fp32) and lo = the exact remainder, itself rounded to TF32 ----
+            const int ct = threadIdx.x - 64;
+            for (int it = 0; it < n_iters; ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                float4* A4 = reinterpret_cast<float4*>(smem + s * L::STAGE_BYTES);
+                float4* L4 = reinterpret_cast<float4*>(smem + s * L::STAGE_BYTES + A_STAGE_BYTES);
+#pragma unroll
+                for (int c = 0; c < A_STAGE_BYTES / 16 / 128; ++c) {
+                    const float4 x = A4[ct + c * 128];
+                    float4 h, l;
+                    // round to nearest (ties away) by integer arithmetic on the bit pattern: truncation would bias every
+                    // term the same way and the bias grows linearly with K (1.6e-5 of max|ref| at K = 3072, measured)
+                    h.x = rn_tf32(x.x); l.x = rn_tf32(x.x - h.x);
+                    h.y = rn_tf32(x.y); l.y = rn_tf32(x.y - h.y);
+                    h.z = rn_tf32(x.z); l.z = rn_tf32(x.z - h.z);
+                    h.w = rn_tf32(x.w); l.w = rn_tf32(x.w - h.w);
+                    A4[ct + c * 128] = h;
+                    L4[ct + c * 128] = l;
+                }
+                fence_proxy_async();                   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                mbar_arrive(&conv_bar[s]);
+            }
+        }
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         // scratch aliases the (now idle) pipeline buffers: [4 quarters][MODE?2:1][32][33] floats
@@ -287,6 +334,29 @@ __global__ void pack_weight_kernel(const float* __restrict__ W, int taps, int C,
     }
 }
 
+// X3: hi = TF32 round-to-nearest head, lo = (W - hi) cut to TF32 (the remainder has <= 13 significant bits; the cut drops
+// at most 2^-22 |W|) -- both exactly representable, so the tensor core's own fp32 -> tf32 narrowing cannot change them
+__global__ void pack_weight_x3_kernel(const float* __restrict__ W, int taps, int C, int N, int Cpad,
+                                      float* __restrict__ dst_hi, float* __restrict__ dst_lo, int64_t ld) {
+    int64_t total = (int64_t)N * taps * Cpad;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int c = (int)(i % Cpad);
+        int64_t r = i / Cpad;
+        int j = (int)(r % taps);
+        int n = (int)(r / taps);
+        float hi = 0.0f, lo = 0.0f;
+        if (c < C) {
+            const float v = W[((int64_t)j * C + c) * N + n];
+            uint32_t u;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+            hi = __uint_as_float(u & 0xffffe000u);
+            lo = __uint_as_float((__float_as_uint(v - hi) + 0x1000u) & 0xffffe000u);    // nearest, not cut: no systematic bias
+        }
+        dst_hi[(int64_t)n * ld + (int64_t)j * Cpad + c] = hi;
+        dst_lo[(int64_t)n * ld + (int64_t)j * Cpad + c] = lo;
+    }
+}
+
 // ---- driver entry point for cuTensorMapEncodeTiled (no link-time libcuda dependency) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -303,15 +373,15 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-template <int BN, int STAGES, int MODE>
+template <int BN, int STAGES, int MODE, bool X3 = false>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, dim3 grid, cudaStream_t st) {
-    using L = SmemLayout<BN, STAGES>;
+    using L = SmemLayout<BN, STAGES, X3>;
     static bool configured = false;
     if (!configured) {
-        TACO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        TACO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, MODE, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         configured = true;
     }
-    gemm_tc_kernel<BN, STAGES, MODE><<<grid, 192, L::TOTAL, st>>>(tmA, tmB, a);
+    gemm_tc_kernel<BN, STAGES, MODE, X3><<<grid, 192, L::TOTAL, st>>>(tmA, tmB, a);
     TACO_LAUNCH_CHECK();
     return 0;
 }
@@ -326,6 +396,18 @@ int taco_pack_weight_impl(const float* W, int taps, int C, int N, float* dst, in
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
     pack_weight_kernel<<<blocks, 256, 0, st>>>(W, taps, C, N, Cpad, dst, ld_dst);
+    TACO_LAUNCH_CHECK();
+    return 0;
+}
+
+int taco_pack_weight_x3_impl(const float* W, int taps, int C, int N, float* dst_hi, float* dst_lo, int64_t ld_dst, cudaStream_t st) {
+    const int Cpad = (C + 31) / 32 * 32;
+    TACO_CHECK(ld_dst >= (int64_t)taps * Cpad, "taco_pack_weight_x3: ld_dst %lld < taps*Cpad %d", (long long)ld_dst, taps * Cpad);
+    int64_t total = (int64_t)N * taps * Cpad;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    pack_weight_x3_kernel<<<blocks, 256, 0, st>>>(W, taps, C, N, Cpad, dst_hi, dst_lo, ld_dst);
     TACO_LAUNCH_CHECK();
     return 0;
 }
@@ -352,6 +434,8 @@ int taco_linear_tc(const taco_linear_desc* d, cudaStream_t st) {
     a.taps = d->taps; a.tap0 = d->tap0; a.bank = d->bank_K > 0 ? 1 : 0;
     a.N = d->N;
     a.pool = d->pool ? 1 : 0;
+    const bool x3 = d->impl == TACO_IMPL_TC3;
+    a.lo_row0 = d->N;                                    // packed buffer = [hi rows 0..N) | lo rows N..2N)
     a.tile_stride = a.pool ? (TC_BM - 1) : TC_BM;
     a.tiles_per_seq = a.pool ? ((d->T - 1 + a.tile_stride - 1) / a.tile_stride) : ((d->T + TC_BM - 1) / TC_BM);
     if (a.tiles_per_seq < 1) a.tiles_per_seq = 1;
@@ -374,7 +458,7 @@ int taco_linear_tc(const taco_linear_desc* d, cudaStream_t st) {
         TACO_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(A) failed: %d (C=%d T=%d B=%d ldx=%lld)", (int)r, d->C, d->T, d->B, (long long)d->ldx);
     }
     {
-        cuuint64_t dims[2] = {(cuuint64_t)d->ldwp, (cuuint64_t)d->N};
+        cuuint64_t dims[2] = {(cuuint64_t)d->ldwp, (cuuint64_t)d->N * (x3 ? 2u : 1u)};
         cuuint64_t strides[1] = {(cuuint64_t)d->ldwp * 4};
         cuuint32_t box[2] = {TC_BK, (cuuint32_t)BN};
         cuuint32_t es[2] = {1, 1};
@@ -384,6 +468,10 @@ int taco_linear_tc(const taco_linear_desc* d, cudaStream_t st) {
         TACO_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed: %d (N=%d ldwp=%lld)", (int)r, d->N, (long long)d->ldwp);
     }
     dim3 grid((d->N + BN - 1) / BN, (unsigned)(a.tiles_per_seq * d->B));
+    if (x3) {
+        if (highway) return launch_tc<256, 2, 1, true>(tmA, tmB, a, grid, st);
+        return launch_tc<128, 3, 0, true>(tmA, tmB, a, grid, st);
+    }
     if (highway) return launch_tc<256, 2, 1>(tmA, tmB, a, grid, st);
     // short K loops (<= 8 k-iterations: dense 128/256-wide inputs) are epilogue/latency bound: a 2-stage ring (64 KB)
     // lets three CTAs share an SM instead of two

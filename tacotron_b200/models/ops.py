@@ -89,10 +89,12 @@ class Runtime:
     """Per-store kernel-side state: precision mode, derived operand buffers, scratch buffers."""
 
     def __init__(self, store, precision="tf32"):
-        assert precision in ("tf32", "fp32")
+        assert precision in ("tf32", "fp32", "fp32x3")
         self.store = store
         self.precision = precision
-        self.impl = L.IMPL_TC if precision == "tf32" else L.IMPL_SIMT
+        # 'fp32x3': tcgen05 tensor cores with the error-compensated 3xTF32 split (fp32-grade products, ~1e-6);
+        # 'tf32': single-pass TF32 products; 'fp32': exact-product FFMA kernel (cross-check path)
+        self.impl = {"tf32": L.IMPL_TC, "fp32": L.IMPL_SIMT, "fp32x3": L.IMPL_TC3}[precision]
         self.derived = {}
         self.derived_version = {}
         self.scratch = {}
@@ -125,18 +127,26 @@ def _cpad(c):
     return (c + 31) // 32 * 32
 
 
-def _pack(rt, key, W, taps, Cin, N, ld=None, row0=0, dst=None):
-    """TF [taps][C][N] -> K-major TF32 operand rows [row0, row0+N) of dst (tensor-core path)."""
+def _pack(rt, key, W, taps, Cin, N, ld=None, row0=0, dst=None, n_total=None):
+    """TF [taps][C][N] -> K-major TF32 operand rows [row0, row0+N) of dst (tensor-core path).  For the 3xTF32 path
+    dst has 2*n_total rows: the hi heads in rows [0, n_total), the lo remainders in rows [n_total, 2 n_total)."""
     ld = ld or taps * _cpad(Cin)
+    n_total = n_total or N
+    x3 = rt.impl == L.IMPL_TC3
     if dst is None:
-        dst = torch.zeros((N, ld), dtype=torch.float32, device=W.device)
-    L.check(L.lib().taco_pack_weight(L.ptr(W), taps, Cin, N, C.c_void_p(dst.data_ptr() + row0 * ld * 4), ld,
-                                     L.current_stream()), "taco_pack_weight")
+        dst = torch.zeros(((2 if x3 else 1) * n_total, ld), dtype=torch.float32, device=W.device)
+    if x3:
+        L.check(L.lib().taco_pack_weight_x3(L.ptr(W), taps, Cin, N, C.c_void_p(dst.data_ptr() + row0 * ld * 4),
+                                            C.c_void_p(dst.data_ptr() + (n_total + row0) * ld * 4), ld, L.current_stream()),
+                "taco_pack_weight_x3")
+    else:
+        L.check(L.lib().taco_pack_weight(L.ptr(W), taps, Cin, N, C.c_void_p(dst.data_ptr() + row0 * ld * 4), ld,
+                                         L.current_stream()), "taco_pack_weight")
     return dst
 
 
 def packed_weight(rt, name, W, taps, Cin, N):
-    if rt.impl != L.IMPL_TC:
+    if rt.impl == L.IMPL_SIMT:
         return None
     return rt.get(("pack", name), lambda old: _pack(rt, name, W.contiguous(), taps, Cin, N, dst=old))
 
@@ -247,12 +257,13 @@ def conv1d_banks(inputs, K=16, cout=128, scope=None):
     ball = sc.store.span(sc.name("b1"), sc.name(f"b{K}"))
     scale, shift = bn_affine(rt, sc)
     Wp = None
-    if rt.impl == L.IMPL_TC:
+    if rt.impl != L.IMPL_SIMT:
         def build(old):
             ld = K * _cpad(Cin)
-            dst = old if old is not None else torch.zeros((K * cout, ld), dtype=torch.float32, device=inputs.device)
+            rows = K * cout * (2 if rt.impl == L.IMPL_TC3 else 1)
+            dst = old if old is not None else torch.zeros((rows, ld), dtype=torch.float32, device=inputs.device)
             for k in range(1, K + 1):
-                _pack(rt, None, sc.p(f"W{k}"), k, Cin, cout, ld=ld, row0=(k - 1) * cout, dst=dst)
+                _pack(rt, None, sc.p(f"W{k}"), k, Cin, cout, ld=ld, row0=(k - 1) * cout, dst=dst, n_total=K * cout)
             return dst
         Wp = rt.get(("pack", sc.name("bank")), build)
         if _save is None:

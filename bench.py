@@ -614,7 +614,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--precision", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--precision", default="fp32x3", choices=["fp32x3", "tf32", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fp32-mode", action="store_true", help="skip the side measurement of the exact-fp32 precision mode")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying CUDA graphs")

@@ -8,7 +8,7 @@ import torch
 from tacotron_b200 import Config, Tacotron
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
-precision = sys.argv[2] if len(sys.argv) > 2 else "tf32"
+precision = sys.argv[2] if len(sys.argv) > 2 else "fp32x3"
 B, TX, T, R = 32, 128, 200, 5
 m = Tacotron(Config(r=R, vocab_size=64, max_decode_iter=T, precision=precision), None, train=False, seed=1)
 g = torch.Generator().manual_seed(0)

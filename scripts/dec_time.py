@@ -31,8 +31,8 @@ if os.environ.get("TACO_TRACE"):
     med = np.median(d, axis=0)
     print("per-slot median ns (CTA 0):", {n_: int(v) for n_, v in zip(names, med)}, "sum", int(med.sum()))
     ck = ws[total + 16 * T + 16: total + 16 * T + 16 + 4 * 20 * 8].reshape(4, 20, 8)
-    inames = ["IN_S", "IN_CP*", "G_H0", "G_X0*", "C_X0", "C_RH0*", "G_H1", "G_X1*", "C_X1", "C_RH1*", "G_H2", "G_X2*", "C_X2", "C_RH2*", "OQP*", "AP2"]
-    print("item: start->loads-issued | ->weights | ->mma done | (finish) ->partials | ->sync | ->epilogue   [cycles, CTA0 thread0, step 11]")
+    inames = ["IN", "G1", "C1", "G2", "C2", "G3", "C3", "OQP", "AP2"]
+    print("stage: start->on-chain loads issued | (off-chain half) ->on-chain weights | ->mma done | (finish) ->partials | ->sync | ->epilogue   [cycles, CTA0 thread0, step 11]")
     st = 1
     for i, nm in enumerate(inames):
         c = ck[st, i]

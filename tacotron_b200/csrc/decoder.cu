@@ -63,6 +63,7 @@ constexpr int AU = 256;        // attention units
 constexpr int ENC = 256;       // memory depth
 constexpr int MF = 80;
 constexpr int KV_LD = 260;     // padded row stride of e^{2 keys} in smem
+constexpr int PPITCH = 132;    // floats between the partial tiles of consecutive warps (128 + 4: cross-warp sums hit different banks)
 
 // ---- weight segments (one K slab of one stage, per CTA column slice) ---------------------------------------------
 enum SegId {
@@ -96,14 +97,13 @@ struct SegDesc {
     int64_t g_off;     // float offset of slice 0 in the packed buffer
 };
 
-struct Item {          // one unit of the per-step program: multiply one operand segment into the accumulators
-    int seg, seg2;     // weight segment(s); seg2 >= 0: second 16-column tile sharing the operand (OQP)
-    int src;           // BufId of the operand
-    int tagd;          // operand tag = t + tagd
-    int stage;         // StageId finished after this item, or ST_NONE
-    int skip0;         // leading k-tile slots that do not exist at t == 0 (zero initial state); 99 = the whole item
+struct Item {          // one stage of the per-step program: [off-chain half] + on-chain half of one contraction, then finish
     int kind;          // ItemKind
-    int pre;           // operand is known long before the item runs: its loads are issued one finish() early
+    int stage;         // StageId finished after the on-chain half
+    int pre_seg, pre_src, pre_tagd, pre_skip0;   // off-chain half: weight segment (-1: none), operand buffer, tag = t + tagd,
+                                                 // 1 = operand does not exist at t == 0 (zero initial state)
+    int on_seg, on_seg2, on_src, on_tagd, on_s0; // on-chain half; seg2 >= 0: second 16-column tile sharing the operand (OQP);
+                                                 // on_s0 = leading k-tile slots that do not exist at t == 0
 };
 
 constexpr int MAX_ITEMS = 20;
@@ -289,7 +289,7 @@ __device__ __forceinline__ void issue_loads(ulonglong2 (&v)[4], const uint64_t* 
 }
 // weight word: >= 0: float offset in the resident smem region; bit 31 set: TMEM column inside the warp's window.
 // wslot = index of the first fragment slot used by this call in the segment's [warp][slot] block, tcoff = its TMEM column.
-template <int FL, int MT, int NS_>
+template <int FL, int MT, int NS_, bool TR>
 __device__ __forceinline__ void consume(float (&acc)[2][3][4], ulonglong2 (&v)[4], const uint64_t* p0, int nkt, int widx, int nw, int s0,
                                         uint32_t tag, uint32_t w1, uint32_t w2, int wslot, int tcoff, const float* res_s, uint32_t tm_lane_col,
                                         int lane, long long* ck) {
@@ -311,7 +311,7 @@ __device__ __forceinline__ void consume(float (&acc)[2][3][4], ulonglong2 (&v)[4
             else                         tm_ld4(ta, w[mt]);
         }
     }
-    if (ck) ck[1] = clock64();
+    if (TR && ck) ck[1] = clock64();
 #pragma unroll
     for (int i = 0; i < NS_; ++i) {
         if (i >= s0 && widx + nw * i < nkt) {          // warp-uniform
@@ -324,23 +324,25 @@ __device__ __forceinline__ void consume(float (&acc)[2][3][4], ulonglong2 (&v)[4
             for (int mt = 0; mt < MT; ++mt) ktile_mma<FL>(acc[mt], bh0, bl0, bh1, bl1, &w[mt][i * FL]);
         }
     }
-    if (ck) ck[2] = clock64();
+    if (TR && ck) ck[2] = clock64();
 }
 
-struct ItemRec { uint32_t base; int tagd; int nkt; int kind; int stage; int skip0; uint32_t w1, w2; };   // 32 bytes, in smem
+struct ItemRec { uint32_t flags, pre_base; int pre_tagd; uint32_t pre_w; uint32_t on_base; int on_tagd; uint32_t on_w1, on_w2; int on_nkt, pad0, pad1, pad2; };   // 48 bytes, in smem
+// flags: kind | stage << 8 | has_pre << 16 | pre_skip0 << 17 | on_s0 << 20
 
+template <bool TR>     // TR: per-stage clock64 trace of CTA 0 (scripts/dec_time.py); the production instantiation has none of it
 __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_kernel(const __grid_constant__ DecParams P) {
     extern __shared__ __align__(16) float smem[];
-    // smem map (floats): [0,16) tmem ptr | part 6144 | part2 512 | loc 384 | bias 256 | att 704 | xbuf 1024 | xstat 64 | itab 192 | kv | weights
+    // smem map (floats): [0,16) tmem ptr | part 6400 | part2 512 | loc 384 | bias 256 | att 704 | xbuf 1024 | xstat 64 | itab 256 | kv | weights
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem);
-    float* part_s = smem + 16;                                    // [3 buffers][16 warps][128]: two alternate, the third is OQP's 2nd tile
-    float* part2_s = part_s + 6144;                               // [8 warps][64]   (P2, warps 8-15)
+    float* part_s = smem + 16;                                    // [3 buffers][16 warps][PPITCH]: two alternate, the third is OQP's 2nd tile
+    float* part2_s = part_s + 6400;                               // [8 warps][64]   (P2, warps 8-15)
     float* loc_s = part2_s + 512;                                 // h_loc[3][64] | u_loc[64] | z_loc[64]
     float* bias_s = loc_s + 384;                                  // [NBR][16]
     float* att_s = bias_s + 256;                                  // eq[256] | v[256] | e[64] | p[64] | misc[64]
     uint64_t* xbuf = reinterpret_cast<uint64_t*>(att_s + 704);    // [2 parity][4 src][64] words
     uint64_t* xstat = xbuf + 512;                                 // [2 parity][4 src][2] words (+pad)
-    ItemRec* itab = reinterpret_cast<ItemRec*>(att_s + 704 + 1024 + 64);   // [MAX_ITEMS] resolved item records (160 floats)
+    ItemRec* itab = reinterpret_cast<ItemRec*>(att_s + 704 + 1024 + 64);   // [MAX_ITEMS] resolved stage records (20 x 12 words)
     uint32_t* otab = reinterpret_cast<uint32_t*>(itab + MAX_ITEMS);          // [NOUT] output word offsets of this CTA
     float* ek_s = smem + P.smem_kv_off;
     float* vals_s = ek_s + P.Tq * KV_LD;
@@ -399,14 +401,17 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
     if (tid < P.n_items) {
         const Item& it = P.items[tid];
         ItemRec r;
-        r.base = 0; r.nkt = 0; r.w1 = r.w2 = 0;
-        r.tagd = it.tagd; r.kind = it.kind | (it.pre << 8); r.stage = it.stage; r.skip0 = it.skip0;
-        if (it.kind <= IK_F2CP) {
-            const SegDesc& d = P.seg[it.seg];
-            r.base = (uint32_t)(P.buf[it.src] + (int64_t)rg * buf_nkt(it.src) * 64);
-            r.nkt = d.K >> 3;
-            r.w1 = d.smem_off >= 0 ? (uint32_t)d.smem_off : (0x80000000u | (uint32_t)d.tmem_col);
-            if (it.seg2 >= 0) { const SegDesc& d2 = P.seg[it.seg2]; r.w2 = d2.smem_off >= 0 ? (uint32_t)d2.smem_off : (0x80000000u | (uint32_t)d2.tmem_col); }
+        memset(&r, 0, sizeof(r));
+        auto wword = [&](int sg) { const SegDesc& d = P.seg[sg]; return d.smem_off >= 0 ? (uint32_t)d.smem_off : (0x80000000u | (uint32_t)d.tmem_col); };
+        r.flags = (uint32_t)it.kind | ((uint32_t)it.stage << 8) | ((it.pre_seg >= 0 ? 1u : 0u) << 16) | ((uint32_t)it.pre_skip0 << 17) | ((uint32_t)it.on_s0 << 20);
+        if (it.pre_seg >= 0) {
+            r.pre_base = (uint32_t)(P.buf[it.pre_src] + (int64_t)rg * buf_nkt(it.pre_src) * 64);
+            r.pre_tagd = it.pre_tagd; r.pre_w = wword(it.pre_seg);
+        }
+        if (it.on_seg >= 0) {
+            r.on_base = (uint32_t)(P.buf[it.on_src] + (int64_t)rg * buf_nkt(it.on_src) * 64);
+            r.on_tagd = it.on_tagd; r.on_w1 = wword(it.on_seg); r.on_w2 = it.on_seg2 >= 0 ? wword(it.on_seg2) : 0u;
+            r.on_nkt = P.seg[it.on_seg].K >> 3;
         }
         itab[tid] = r;
     }
@@ -493,7 +498,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
             if (mt < MT) {
-                float* pw = (mt ? part_b : part) + warp * 128;
+                float* pw = (mt ? part_b : part) + warp * PPITCH;
                 *reinterpret_cast<float2*>(pw + g * 8 + 2 * tg) =
                     make_float2((acc[mt][0][0] + acc[mt][1][0]) + acc[mt][2][0], (acc[mt][0][1] + acc[mt][1][1]) + acc[mt][2][1]);
                 if (full16)
@@ -508,10 +513,12 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
 #pragma unroll
                 for (int a2 = 0; a2 < 4; ++a2) acc[a0][a1][a2] = 0.f;
     };
+    // cross-warp sum of one output by one thread.  (Spreading each sum over 2-4 lanes + shuffles so that all 16 warps share
+    // the epilogue was tried: 16.0 instead of 15.3 us/step -- the extra shuffles cost more than the shorter chains save.)
     auto sum16 = [&](const float* part, int pidx) {
         float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-        for (int w = 0; w < NWARP; w += 2) { s0 += part[w * 128 + pidx]; s1 += part[(w + 1) * 128 + pidx]; }
+        for (int w = 0; w < NWARP; w += 2) { s0 += part[w * PPITCH + pidx]; s1 += part[(w + 1) * PPITCH + pidx]; }
         return s0 + s1;
     };
     // epilogue thread mapping: lanes run over the 8 weight columns first (8-byte words of one row are then
@@ -655,7 +662,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
         const SegDesc& sd = P.seg[SG_P2];
         const uint32_t w1 = sd.smem_off >= 0 ? (uint32_t)sd.smem_off : (0x80000000u | (uint32_t)sd.tmem_col);
         issue_loads<4>(v, p0, 32, widx, 8, 0);
-        consume<2, 1, 4>(acc, v, p0, 32, widx, 8, 0, tag, w1, w1, widx * 4, 0, res_s, tm_lane_col, lane, nullptr);
+        consume<2, 1, 4, false>(acc, v, p0, 32, widx, 8, 0, tag, w1, w1, widx * 4, 0, res_s, tm_lane_col, lane, nullptr);
         float* pw = part2_s + widx * 64;
         *reinterpret_cast<float2*>(pw + g * 8 + 2 * tg) =
             make_float2((acc[0][0][0] + acc[0][1][0]) + acc[0][2][0], (acc[0][0][1] + acc[0][1][1]) + acc[0][2][1]);
@@ -704,14 +711,14 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
     };
 
     auto finish = [&](int stage, int t) {
-        float* part = part_s + par * 2048;
-        float* part_b = part_s + 2 * 2048;               // second tile of OQP (its previous readers are a full step behind)
+        float* part = part_s + par * (NWARP * PPITCH);
+        float* part_b = part_s + 2 * (NWARP * PPITCH);               // second tile of OQP (its previous readers are a full step behind)
         par ^= 1;
         const bool full16 = (stage >= ST_G0 && stage <= ST_G2) || stage == ST_OQP;
         store_partials(part, part_b, stage == ST_OQP ? 2 : 1, full16);
-        if (cktr) cktr[4] = clock64();
+        if (TR && cktr) cktr[4] = clock64();
         __syncthreads();
-        if (cktr) cktr[5] = clock64();
+        if (TR && cktr) cktr[5] = clock64();
         const uint32_t tag = (uint32_t)t + 1;
         switch (stage) {
             case ST_IN:
@@ -767,8 +774,8 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
             } break;
             default: break;
         }
-        if (cktr) cktr[6] = clock64();
-        if (tracer) ws[P.trace_off + (trace_i++)] = globaltimer_ns();
+        if (TR && cktr) cktr[6] = clock64();
+        if (TR && tracer) ws[P.trace_off + (trace_i++)] = globaltimer_ns();
     };
 
     // =========================================================================================================
@@ -782,56 +789,66 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
     // T decoder steps x the item program
     // =========================================================================================================
     const int n_items = P.n_items;
-    bool pref = false;                                  // v[] already holds the loads of the current item
+    const uint32_t itab_a = smem_u32(itab);
+    ulonglong2 vp[4];                                   // operand words of the off-chain half (prefetched one finish() early)
+    bool pref = false;                                  // vp[] already holds the loads of the current stage's off-chain half
+    auto ld_rec = [&](int ii, uint4& r0, uint4& r1, uint32_t& nkt) {
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r0.x), "=r"(r0.y), "=r"(r0.z), "=r"(r0.w) : "r"(itab_a + ii * 48));
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r1.x), "=r"(r1.y), "=r"(r1.z), "=r"(r1.w) : "r"(itab_a + ii * 48 + 16));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(nkt) : "r"(itab_a + ii * 48 + 32));
+    };
+    uint4 nr0, nr1; uint32_t nnkt;
+    ld_rec(0, nr0, nr1, nnkt);
     for (int t = 0; t < T; ++t) {
         if (tracer) A.step_ns[t] = globaltimer_ns();
         for (int ii = 0; ii < n_items; ++ii) {
-            const int4 ra = *reinterpret_cast<const int4*>(&itab[ii]);                 // base, tagd, nkt, kind
-            const int4 rb = *reinterpret_cast<const int4*>(reinterpret_cast<const int*>(&itab[ii]) + 4);   // stage, skip0, w1, w2
-            const int kind = ra.w & 0xff, stage = rb.x;
+            // r0 = flags, pre_base, pre_tagd, pre_w;  r1 = on_base, on_tagd, on_w1, on_w2 -- fetched one stage ahead
+            const uint4 r0 = nr0, r1 = nr1; const uint32_t on_nkt = nnkt;
+            ld_rec(ii + 1 < n_items ? ii + 1 : 0, nr0, nr1, nnkt);
+            const int kind = r0.x & 0xff, stage = (r0.x >> 8) & 0xff;
             long long* ck = nullptr;
-            if (tracer && t >= 10 && t < 14) { ck = reinterpret_cast<long long*>(ws + P.trace_off + 16 * T + 16 + ((t - 10) * MAX_ITEMS + ii) * 8); ck[3] = clock64(); }
+            if (TR && tracer && t >= 10 && t < 14) { ck = reinterpret_cast<long long*>(ws + P.trace_off + 16 * T + 16 + ((t - 10) * MAX_ITEMS + ii) * 8); ck[3] = clock64(); }
             cktr = ck;
             if (kind == IK_AP2) {
                 if (warp < 8) attention(t);
                 else if (t + 1 < T) prenet2(t + 1);
-                if (tracer) ws[P.trace_off + (trace_i++)] = globaltimer_ns();
+                if (TR && tracer) ws[P.trace_off + (trace_i++)] = globaltimer_ns();
                 continue;
             }
             if (kind == IK_PM) {
                 if (t + 1 < T) { prenet1_teacher(t + 1); finish(ST_PM, t + 1); }
                 continue;
             }
-            const int s0 = (t == 0) ? rb.y : 0;
-            if (s0 < 99) {
-                const uint64_t* p0 = ws + (uint32_t)ra.x + warp * 64 + lane_w;
-                const uint32_t tag = (uint32_t)(t + ra.y);
-                const int nkt = ra.z;
-                if (kind == IK_F2CP) {
-                    issue_loads<3>(v, p0, nkt, warp, NWARP, s0);
-                    if (ck) ck[0] = clock64();
-                    consume<2, 1, 3>(acc, v, p0, nkt, warp, NWARP, s0, tag, (uint32_t)rb.z, 0u, warp * 3, 0, res_s, tm_lane_col, lane, ck);
-                } else {
-                    if (!pref) issue_loads<2>(v, p0, nkt, warp, NWARP, 0);
-                    if (ck) ck[0] = clock64();
-                    if (kind == IK_F4X2)    consume<4, 2, 2>(acc, v, p0, nkt, warp, NWARP, 0, tag, (uint32_t)rb.z, (uint32_t)rb.w, warp * 2, 0, res_s, tm_lane_col, lane, ck);
-                    else if (kind == IK_F4) consume<4, 1, 2>(acc, v, p0, nkt, warp, NWARP, 0, tag, (uint32_t)rb.z, 0u, warp * 2, 0, res_s, tm_lane_col, lane, ck);
-                    else                    consume<2, 1, 2>(acc, v, p0, nkt, warp, NWARP, 0, tag, (uint32_t)rb.z, 0u, warp * 2, 0, res_s, tm_lane_col, lane, ck);
-                }
+            // ---- on-chain operand: loads in flight first, they travel while the off-chain half is multiplied ----
+            const uint64_t* pon = ws + r1.x + warp * 64 + lane_w;
+            const int s0 = (t == 0) ? (int)((r0.x >> 20) & 0xf) : 0;
+            if (kind == IK_F2CP) issue_loads<3>(v, pon, (int)on_nkt, warp, NWARP, s0);
+            else                 issue_loads<2>(v, pon, (int)on_nkt, warp, NWARP, 0);
+            if (TR && ck) ck[0] = clock64();
+            const bool has_pre = ((r0.x >> 16) & 1) && !(t == 0 && ((r0.x >> 17) & 1));
+            const uint64_t* ppre = ws + r0.y + warp * 64 + lane_w;
+            const uint32_t ptag = (uint32_t)(t + (int)r0.z), otag = (uint32_t)(t + (int)r1.y);
+            if (has_pre && !pref) issue_loads<2>(vp, ppre, 32, warp, NWARP, 0);
+            if (kind == IK_F4) {
+                if (has_pre) consume<4, 1, 2, false>(acc, vp, ppre, 32, warp, NWARP, 0, ptag, r0.w, 0u, warp * 2, 0, res_s, tm_lane_col, lane, nullptr);
+                consume<4, 1, 2, TR>(acc, v, pon, 32, warp, NWARP, 0, otag, r1.z, 0u, warp * 2, 0, res_s, tm_lane_col, lane, ck);
+            } else if (kind == IK_F2) {
+                if (has_pre) consume<2, 1, 2, false>(acc, vp, ppre, 32, warp, NWARP, 0, ptag, r0.w, 0u, warp * 2, 0, res_s, tm_lane_col, lane, nullptr);
+                consume<2, 1, 2, TR>(acc, v, pon, 32, warp, NWARP, 0, otag, r1.z, 0u, warp * 2, 0, res_s, tm_lane_col, lane, ck);
+            } else if (kind == IK_F2CP) {
+                if (has_pre) consume<2, 1, 2, false>(acc, vp, ppre, 32, warp, NWARP, 0, ptag, r0.w, 0u, warp * 2, 0, res_s, tm_lane_col, lane, nullptr);
+                consume<2, 1, 3, TR>(acc, v, pon, 48, warp, NWARP, s0, otag, r1.z, 0u, warp * 3, 0, res_s, tm_lane_col, lane, ck);
+            } else {
+                consume<4, 2, 2, TR>(acc, v, pon, 32, warp, NWARP, 0, otag, r1.z, r1.w, warp * 2, 0, res_s, tm_lane_col, lane, ck);
             }
             pref = false;
-            if (stage != ST_NONE) {
-                // the next item's operand is already known (off-chain half of the next stage): put its loads in flight
-                // now, so that they travel while this stage's epilogue runs
-                if (ii + 1 < n_items) {
-                    const int4 na = *reinterpret_cast<const int4*>(&itab[ii + 1]);
-                    if ((na.w >> 8) & 1) {
-                        issue_loads<2>(v, ws + (uint32_t)na.x + warp * 64 + lane_w, na.z, warp, NWARP, 0);
-                        pref = true;
-                    }
-                }
-                finish(stage, t);
+            // the next stage's off-chain operand is already known: put its loads in flight now, they travel while this
+            // stage's epilogue runs
+            if (ii + 1 < n_items && ((nr0.x >> 16) & 1)) {
+                issue_loads<2>(vp, ws + nr0.y + warp * 64 + lane_w, 32, warp, NWARP, 0);
+                pref = true;
             }
+            finish(stage, t);
         }
     }
 
@@ -1024,28 +1041,25 @@ extern "C" int taco_decoder_fwd(const taco_decoder_args* a, void* stream) {
     const FusedTail ft = fused_tail(a->r, tot);
     P.b_qF = a->packed + ft.b_qF; P.b_p1F = a->packed + ft.b_p1F; P.b_inS = a->packed + ft.b_inS;
 
-    // ---- the per-step program ----
+    // ---- the per-step program: one record per stage ----
     int n = 0;
-    auto item = [&](int seg, int seg2, int src, int tagd, int stage, int skip0, int kind, int pre) {
-        P.items[n++] = Item{seg, seg2, src, tagd, stage, skip0, kind, pre};
+    auto stage = [&](int kind, int st_id, int pre_seg, int pre_src, int pre_tagd, int pre_skip0, int on_seg, int on_seg2, int on_src, int on_tagd, int on_s0) {
+        P.items[n++] = Item{kind, st_id, pre_seg, pre_src, pre_tagd, pre_skip0, on_seg, on_seg2, on_src, on_tagd, on_s0};
     };
-    item(SG_IN_S, -1, B_S, 0, ST_NONE, 99, IK_F2, 1);                         // off-chain: s(t-1)
-    item(SG_IN_CP, -1, B_CP, 1, ST_IN, 2, IK_F2CP, 0);                        // [ctx(t-1) | p2(t)] (no context at t = 0)
+    stage(IK_F2CP, ST_IN, SG_IN_S, B_S, 0, 1, SG_IN_CP, -1, B_CP, 1, 2);         // s(t-1) | [ctx(t-1) | p2(t)] (no s, no context at t = 0)
     for (int i = 0; i < 3; ++i) {
         const int x = (i == 0) ? B_Z : B_H0 + (i - 1);
-        item(SG_G_H0 + i, -1, B_H0 + i, 0, ST_NONE, 99, IK_F4, 1);          // off-chain: h_i(t-1)
-        item(SG_G_X0 + i, -1, x, 1, ST_G0 + i, 0, IK_F4, 0);
-        item(SG_C_X0 + i, -1, x, 1, ST_NONE, 0, IK_F2, 1);                  // off-chain: x (already consumed by the gate stage)
-        item(SG_C_RH0 + i, -1, B_RH0 + i, 1, ST_C0 + i, 0, IK_F2, 0);
+        stage(IK_F4, ST_G0 + i, SG_G_H0 + i, B_H0 + i, 0, 1, SG_G_X0 + i, -1, x, 1, 0);           // h_i(t-1) | x
+        stage(IK_F2, ST_C0 + i, SG_C_X0 + i, x, 1, 0, SG_C_RH0 + i, -1, B_RH0 + i, 1, 0);         // x (already consumed by the gates) | r*h
     }
-    if (a->mode != TACO_DEC_INFER) item(-1, -1, 0, 0, ST_PM, 0, IK_PM, 0);    // teacher frame t+1 -> p1m(t+1), off-chain
-    item(SG_Y, SG_QP, B_S, 1, ST_OQP, 0, IK_F4X2, 0);
-    item(-1, -1, 0, 0, ST_AP2, 0, IK_AP2, 0);
+    if (a->mode != TACO_DEC_INFER) stage(IK_PM, ST_PM, -1, 0, 0, 0, -1, -1, 0, 0, 0);             // teacher frame t+1 -> p1m(t+1), off-chain
+    stage(IK_F4X2, ST_OQP, -1, 0, 0, 0, SG_Y, SG_QP, B_S, 1, 0);
+    stage(IK_AP2, ST_AP2, -1, 0, 0, 0, -1, -1, 0, 0, 0);
     P.n_items = n;
 
     // ---- residency: off-chain segments in TMEM (256 columns per warp), on-chain segments in shared memory; when the
     //      keys/values leave too little shared memory (large Tx) further segments move to TMEM ----
-    int off = 16 + 6144 + 512 + 384 + 256 + 704 + 1024 + 64 + 192;
+    int off = 16 + 6400 + 512 + 384 + 256 + 704 + 1024 + 64 + 256;
     off = (off + 31) / 32 * 32;
     P.smem_kv_off = off;
     off += P.Tq * KV_LD + P.Tq * ENC;
@@ -1079,7 +1093,8 @@ extern "C" int taco_decoder_fwd(const taco_decoder_args* a, void* stream) {
 
     static bool configured = false;
     if (!configured) {
-        TACO_CUDA(cudaFuncSetAttribute(decoder_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        TACO_CUDA(cudaFuncSetAttribute(decoder_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        TACO_CUDA(cudaFuncSetAttribute(decoder_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
     cudaLaunchConfig_t cfg;
@@ -1090,12 +1105,14 @@ extern "C" int taco_decoder_fwd(const taco_decoder_args* a, void* stream) {
     if (max_clusters < 0) {
         cudaLaunchConfig_t q = cfg; q.dynamicSmemBytes = 227 * 1024;
         int nc = 0;
-        TACO_CUDA(cudaOccupancyMaxActiveClusters(&nc, (void*)decoder_kernel, &q));
+        TACO_CUDA(cudaOccupancyMaxActiveClusters(&nc, (void*)decoder_kernel<false>, &q));
         max_clusters = nc;
     }
     TACO_CHECK(max_clusters >= NCTA / 4, "taco_decoder_fwd: only %d clusters of 4 CTAs can be co-resident on this device (need %d)", max_clusters, NCTA / 4);
     TACO_CUDA(cudaMemsetAsync(a->workspace, 0, (size_t)ws_total * 8, st));
-    TACO_CUDA(cudaLaunchKernelEx(&cfg, decoder_kernel, P));
+    static const bool trace_build = getenv("TACO_TRACE") != nullptr;     // per-stage clock trace (scripts/dec_time.py)
+    if (trace_build && a->step_ns) TACO_CUDA(cudaLaunchKernelEx(&cfg, decoder_kernel<true>, P));
+    else                           TACO_CUDA(cudaLaunchKernelEx(&cfg, decoder_kernel<false>, P));
     ++g_taco_launches;
     return 0;
 }

@@ -11,18 +11,21 @@
 // communication at all.  The recurrent weights (128x256 + 128x128 fp32 = 192 KB) live in the
 // REGISTER FILE of the CTA's 512 threads (96 floats each) for the whole sequence.
 //
-// Thread mapping (v2): shared-memory -> register bandwidth (128 B/clk/SM) was the bottleneck of
-// the first version, where every thread re-read half of h each step (131 KB/step).  Now the 32
-// lanes of a warp split K: lane l owns k = 4l..4l+3 (ONE 16-byte LDS of h per mat-vec), warp w
-// owns 16 gate columns (8 candidate columns), and the per-column partial sums are combined with a
-// halving butterfly (16 -> 8 -> 4 -> 2 -> 1 values over shfl_xor 16, 8, 4, 2, 1: 16 shuffles).
+// Thread mapping (v4).  History (post-net, 1000 steps, us per step): v1 one thread per column, every thread re-reading
+// all of h: 2.0, shared-memory -> register bandwidth bound (128 B/clk/SM); v2 lanes split K 32 ways, 16 columns per warp,
+// 16-to-1 halving butterfly: 0.94, issue bound (~200 instructions per warp-step, half of them butterfly); v3 4 lanes per
+// hidden unit: 0.92, bandwidth bound again (every thread pulls 128 B of h per mat-vec = 64 KB per phase; ncu: 54%
+// short-scoreboard stalls, 1150 shared wavefronts per step).  v4 sits between: a GROUP OF 8 LANES owns two hidden units
+// (their r, u gate columns and candidate columns: 6 columns), the 8 lanes split K (16 rows each: 64 B of h per mat-vec and
+// thread = 32 KB per phase), products are packed two-k-per-instruction (FFMA2 on the h pair as it comes out of a 16-byte
+// shared load) and the 8-lane reduction is a transposing butterfly (4 -> 2 -> 1 values): 7 shuffles per step.
 #include "common.cuh"
 
 namespace {
 
 constexpr int H = 128;
 
-// d += a * b on two packed fp32 lanes (Blackwell FFMA2: one issue slot for two FMAs)
+// d.x += a.x * b.x ; d.y += a.y * b.y  (Blackwell FFMA2: one issue slot for two FMAs)
 __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b) {
     unsigned long long dd = *reinterpret_cast<unsigned long long*>(&d);
     const unsigned long long aa = *reinterpret_cast<const unsigned long long*>(&a);
@@ -31,136 +34,140 @@ __device__ __forceinline__ void ffma2(float2& d, const float2 a, const float2 b)
     d = *reinterpret_cast<float2*>(&dd);
 }
 
-// Reduce N per-lane partial sums (N = 16 or 8) across the 32 lanes.  Each round halves the number of
-// live values: a lane keeps the half selected by its lane bit and receives the partner's
-// contribution for that half.  On return p[0] holds the full sum of column
-//   N=16: c = 8*b4 + 4*b3 + 2*b2 + b1      N=8: c = 4*b4 + 2*b3 + b2      (b_i = bit i of lane)
-template <int N>
-__device__ __forceinline__ float butterfly(float (&p)[N], int lane) {
-    int n = N;
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-        if (n > 1) {
-            const bool hi = (lane & off) != 0;
-            n >>= 1;
-#pragma unroll
-            for (int j = 0; j < N / 2; ++j) {
-                if (j < n) {
-                    const float send = hi ? p[j] : p[j + n];
-                    const float keep = hi ? p[j + n] : p[j];
-                    p[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                }
-            }
-        } else {
-            p[0] += __shfl_xor_sync(0xffffffffu, p[0], off);
-        }
-    }
-    return p[0];
-}
-
 __global__ void __launch_bounds__(512, 1)
 bigru_kernel(const float* __restrict__ xp, const float* __restrict__ Wg_fw, const float* __restrict__ Wc_fw,
              const float* __restrict__ Wg_bw, const float* __restrict__ Wc_bw, float* __restrict__ out, int T) {
     const int b = blockIdx.x;
     const int dir = blockIdx.y;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const float* Wg = dir ? Wg_bw : Wg_fw;     // [128][256]  h-side rows of the gates kernel
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int grp = tid >> 3;                  // 8-lane group: hidden units 2*grp, 2*grp + 1
+    const int l3 = tid & 7;                    // K slice: the 16-byte chunks 8i + l3, i = 0..3 (a group reads 128 contiguous bytes)
+    const float* Wg = dir ? Wg_bw : Wg_fw;     // [128][256]  h-side rows of the gates kernel (columns: r then u)
     const float* Wc = dir ? Wc_bw : Wc_fw;     // [128][128]  (r*h)-side rows of the candidate kernel
 
     __shared__ __align__(16) float h_s[H];
     __shared__ __align__(16) float rh_s[H];
     __shared__ float u_s[H];
 
-    // weights: lane owns k = 4*lane + i; warp owns gate columns [16w,16w+16) and candidate columns [8w,8w+8)
-    float wg[4][16], wc[4][8];
+    // weights as k-pairs: wg[c][2i+p] = (W[k][col_c], W[k+1][col_c]), k = 4*(8i + l3) + 2p;
+    // gate columns c = 0..3: r(j0), u(j0), r(j1), u(j1); candidate columns c = 0..1: j0, j1
+    const int j0 = 2 * grp;
+    float2 wg[4][8], wc[2][8];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) wg[i][c] = __ldg(Wg + (int64_t)(4 * lane + i) * 256 + warp * 16 + c);
+        for (int p = 0; p < 2; ++p) {
+            const int k = 4 * (8 * i + l3) + 2 * p;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) wc[i][c] = __ldg(Wc + (int64_t)(4 * lane + i) * 128 + warp * 8 + c);
+            for (int c = 0; c < 4; ++c) {
+                const int col = (c & 1) * H + j0 + (c >> 1);
+                wg[c][2 * i + p] = make_float2(__ldg(Wg + (int64_t)k * 256 + col), __ldg(Wg + (int64_t)(k + 1) * 256 + col));
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+                wc[c][2 * i + p] = make_float2(__ldg(Wc + (int64_t)k * 128 + j0 + c), __ldg(Wc + (int64_t)(k + 1) * 128 + j0 + c));
+        }
     }
-    // after the butterflies: which column this lane finalises
-    const int gcol = warp * 16 + (((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1));
-    const bool g_owner = (lane & 1) == 0;
-    const int ccol = warp * 8 + (((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1));
-    const bool c_owner = (lane & 3) == 0;
+    // after the butterflies: lane pair (l3 >> 1) of the group holds gate column gc = 2*bit2 + bit1 -> unit j0 + bit2, gate bit1;
+    // lane quad (l3 >> 2) holds the candidate column of unit j0 + bit2
+    const int gj = j0 + ((l3 >> 2) & 1);
+    const bool g_is_u = (l3 >> 1) & 1;
+    const bool g_owner = (l3 & 1) == 0;
+    const bool c_owner = (l3 & 3) == 0;
 
     if (tid < H) h_s[tid] = 0.0f;               // zero initial state (ops.py:112-115, s is None)
     __syncthreads();
 
-    const int64_t seq = (int64_t)b * T;
-    auto xrow = [&](int step) { int t = dir ? (T - 1 - step) : step; return xp + (seq + t) * 768 + dir * 384; };
+    // pointers advance by one time step per iteration (no per-step index arithmetic); the input products are prefetched
+    // three steps ahead (they do not depend on h and stream from HBM), rotating through three named registers
+    // (32-bit element offsets: the host checks B*T*768 < 2^31)
+    const int seq = b * T;
+    const int t_first = dir ? (T - 1) : 0;
+    const int xs = dir ? -768 : 768, os = dir ? -256 : 256;
+    int xgp = (seq + t_first) * 768 + dir * 384 + (g_is_u ? H : 0) + gj;     // this lane's hoisted gate product
+    int outp = (seq + t_first) * 256 + dir * H + gj;
+    const int xc_off = 256 + gj - ((g_is_u ? H : 0) + gj);                  // candidate product relative to xgp
 
-    // input products are prefetched two steps ahead (they do not depend on h)
-    float xg0 = 0.f, xc0 = 0.f, xg1 = 0.f, xc1 = 0.f;
-    if (T > 0) { const float* x = xrow(0); if (g_owner) xg0 = __ldg(x + gcol); if (c_owner) xc0 = __ldg(x + 256 + ccol); }
-    if (T > 1) { const float* x = xrow(1); if (g_owner) xg1 = __ldg(x + gcol); if (c_owner) xc1 = __ldg(x + 256 + ccol); }
+    float xg0 = 0.f, xg1 = 0.f, xg2 = 0.f, xc0 = 0.f, xc1 = 0.f, xc2 = 0.f;
+    if (T > 0) { if (g_owner) xg0 = __ldg(xp + xgp); if (c_owner) xc0 = __ldg(xp + xgp + xc_off); }
+    if (T > 1) { if (g_owner) xg1 = __ldg(xp + xgp + xs); if (c_owner) xc1 = __ldg(xp + xgp + xs + xc_off); }
+    if (T > 2) { if (g_owner) xg2 = __ldg(xp + xgp + 2 * xs); if (c_owner) xc2 = __ldg(xp + xgp + 2 * xs + xc_off); }
+    xgp += 3 * xs;                             // -> the row of step + 3
 
-    for (int step = 0; step < T; ++step) {
-        const int t = dir ? (T - 1 - step) : step;
-        const float xg = xg0, xc = xc0;
-        xg0 = xg1; xc0 = xc1;
-        if (step + 2 < T) {
-            const float* xn = xrow(step + 2);
-            if (g_owner) xg1 = __ldg(xn + gcol);
-            if (c_owner) xc1 = __ldg(xn + 256 + ccol);
+    const float4* h4 = reinterpret_cast<const float4*>(h_s) + l3;
+    const float4* rh4 = reinterpret_cast<const float4*>(rh_s) + l3;
+    const bool b2 = (l3 & 4) != 0, b1 = (l3 & 2) != 0;
+
+    // one time step: consumes (xg, xc), refills them with the products of step + 3 when `more`
+    auto one_step = [&](float& xg, float& xc, bool more) {
+        const float xgv = xg, xcv = xc;
+        if (more) {
+            if (g_owner) xg = __ldg(xp + xgp);
+            if (c_owner) xc = __ldg(xp + xgp + xc_off);
         }
-        // ---- gates: h . Wg_h ----
+        xgp += xs;
+        // ---- gates: h . Wg_h (this lane: 16 rows x 4 columns) ----
         {
-            const float4 hv = *reinterpret_cast<const float4*>(h_s + 4 * lane);
-            float2 p2[8];
-            const float2 hx = make_float2(hv.x, hv.x), hy = make_float2(hv.y, hv.y), hz = make_float2(hv.z, hv.z), hw = make_float2(hv.w, hv.w);
+            float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+            float4 hv[4];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) p2[c] = make_float2(0.f, 0.f);
+            for (int i = 0; i < 4; ++i) hv[i] = h4[8 * i];
 #pragma unroll
-            for (int c = 0; c < 8; ++c) ffma2(p2[c], hx, make_float2(wg[0][2 * c], wg[0][2 * c + 1]));
-#pragma unroll
-            for (int c = 0; c < 8; ++c) ffma2(p2[c], hy, make_float2(wg[1][2 * c], wg[1][2 * c + 1]));
-#pragma unroll
-            for (int c = 0; c < 8; ++c) ffma2(p2[c], hz, make_float2(wg[2][2 * c], wg[2][2 * c + 1]));
-#pragma unroll
-            for (int c = 0; c < 8; ++c) ffma2(p2[c], hw, make_float2(wg[3][2 * c], wg[3][2 * c + 1]));
-            float p[16];
-#pragma unroll
-            for (int c = 0; c < 8; ++c) { p[2 * c] = p2[c].x; p[2 * c + 1] = p2[c].y; }
-            const float acc = butterfly<16>(p, lane);
+            for (int i = 0; i < 4; ++i) {
+                const float2 lo = make_float2(hv[i].x, hv[i].y), hi = make_float2(hv[i].z, hv[i].w);
+                ffma2(a0, lo, wg[0][2 * i]); ffma2(a1, lo, wg[1][2 * i]); ffma2(a2, lo, wg[2][2 * i]); ffma2(a3, lo, wg[3][2 * i]);
+                ffma2(a0, hi, wg[0][2 * i + 1]); ffma2(a1, hi, wg[1][2 * i + 1]); ffma2(a2, hi, wg[2][2 * i + 1]); ffma2(a3, hi, wg[3][2 * i + 1]);
+            }
+            const float p0 = a0.x + a0.y, p1 = a1.x + a1.y, p2 = a2.x + a2.y, p3 = a3.x + a3.y;
+            // transposing butterfly over the 8 lanes: xor 4 keeps the unit (bit2), xor 2 keeps the gate (bit1), xor 1 sums
+            const float q0 = (b2 ? p2 : p0) + __shfl_xor_sync(0xffffffffu, b2 ? p0 : p2, 4);   // r of the kept unit
+            const float q1 = (b2 ? p3 : p1) + __shfl_xor_sync(0xffffffffu, b2 ? p1 : p3, 4);   // u of the kept unit
+            float g = (b1 ? q1 : q0) + __shfl_xor_sync(0xffffffffu, b1 ? q0 : q1, 2);
+            g += __shfl_xor_sync(0xffffffffu, g, 1);
             if (g_owner) {
-                const float g = sigmoidf_acc(acc + xg);
-                if (gcol < H) rh_s[gcol] = g * h_s[gcol];   // r * h
-                else u_s[gcol - H] = g;                      // u
+                const float gt = sigmoidf_acc(g + xgv);
+                if (g_is_u) u_s[gj] = gt;
+                else rh_s[gj] = gt * h_s[gj];   // r * h
             }
         }
         __syncthreads();
-        // ---- candidate: (r*h) . Wc_h ----
+        // ---- candidate: (r*h) . Wc_h (16 rows x 2 columns) ----
         {
-            const float4 rv = *reinterpret_cast<const float4*>(rh_s + 4 * lane);
-            float2 p2[4];
-            const float2 rx = make_float2(rv.x, rv.x), ry = make_float2(rv.y, rv.y), rz = make_float2(rv.z, rv.z), rw = make_float2(rv.w, rv.w);
+            float2 c0 = make_float2(0.f, 0.f), c1 = c0;
+            float4 rvv[4];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) p2[c] = make_float2(0.f, 0.f);
+            for (int i = 0; i < 4; ++i) rvv[i] = rh4[8 * i];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) ffma2(p2[c], rx, make_float2(wc[0][2 * c], wc[0][2 * c + 1]));
-#pragma unroll
-            for (int c = 0; c < 4; ++c) ffma2(p2[c], ry, make_float2(wc[1][2 * c], wc[1][2 * c + 1]));
-#pragma unroll
-            for (int c = 0; c < 4; ++c) ffma2(p2[c], rz, make_float2(wc[2][2 * c], wc[2][2 * c + 1]));
-#pragma unroll
-            for (int c = 0; c < 4; ++c) ffma2(p2[c], rw, make_float2(wc[3][2 * c], wc[3][2 * c + 1]));
-            float p[8];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) { p[2 * c] = p2[c].x; p[2 * c + 1] = p2[c].y; }
-            const float cacc = butterfly<8>(p, lane);
-            if (c_owner) {
-                const float c = tanhf_acc(cacc + xc);
-                const float u = u_s[ccol];
-                const float hn = u * h_s[ccol] + (1.0f - u) * c;
-                h_s[ccol] = hn;
-                out[(seq + t) * 256 + dir * H + ccol] = hn;
+            for (int i = 0; i < 4; ++i) {
+                const float2 lo = make_float2(rvv[i].x, rvv[i].y), hi = make_float2(rvv[i].z, rvv[i].w);
+                ffma2(c0, lo, wc[0][2 * i]); ffma2(c1, lo, wc[1][2 * i]);
+                ffma2(c0, hi, wc[0][2 * i + 1]); ffma2(c1, hi, wc[1][2 * i + 1]);
             }
+            const float p0 = c0.x + c0.y, p1 = c1.x + c1.y;
+            float cc = (b2 ? p1 : p0) + __shfl_xor_sync(0xffffffffu, b2 ? p0 : p1, 4);
+            cc += __shfl_xor_sync(0xffffffffu, cc, 2);
+            cc += __shfl_xor_sync(0xffffffffu, cc, 1);
+            if (c_owner) {
+                const float cn = tanhf_acc(cc + xcv);
+                const float u = u_s[gj];
+                const float hn = u * h_s[gj] + (1.0f - u) * cn;
+                h_s[gj] = hn;
+                out[outp] = hn;
+            }
+            outp += os;
         }
         __syncthreads();
+    };
+
+    int step = 0;
+    for (; step + 3 <= T; step += 3) {
+        one_step(xg0, xc0, step + 3 < T);
+        one_step(xg1, xc1, step + 4 < T);
+        one_step(xg2, xc2, step + 5 < T);
     }
+    if (step < T) { one_step(xg0, xc0, false); ++step; }
+    if (step < T) { one_step(xg1, xc1, false); ++step; }
+    (void)lane;
 }
 
 }  // namespace
@@ -169,6 +176,7 @@ extern "C" int taco_bigru_fwd(const float* xp, const float* Wg_h_fw, const float
                               const float* Wc_h_bw, float* out, int B, int T, void* stream) {
     TACO_CHECK(xp && Wg_h_fw && Wc_h_fw && Wg_h_bw && Wc_h_bw && out, "taco_bigru_fwd: NULL pointer");
     TACO_CHECK(B >= 0 && T >= 0, "taco_bigru_fwd: negative size");
+    TACO_CHECK((int64_t)B * T * 768 < (int64_t)1 << 31, "taco_bigru_fwd: B*T = %lld too large for 32-bit offsets", (long long)B * T);
     if (B == 0 || T == 0) return 0;
     dim3 grid(B, 2);
     bigru_kernel<<<grid, 512, 0, (cudaStream_t)stream>>>(xp, Wg_h_fw, Wc_h_fw, Wg_h_bw, Wc_h_bw, out, T);

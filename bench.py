@@ -35,6 +35,17 @@ FRAMES = B * T * R
 FWD_GFLOP = 168.05
 DECODER_GFLOP = 22.649 + 0.537          # decoder loop + attention memory layer (per launch at C2)
 METRIC = "mel frames/sec at batch 32 r=5; decoder-step p50 latency"
+WORKLOAD = "C2 synthetic: B=32, char 128, 200 decoder steps, r=5, inference forward (free-running)"
+
+
+def config_dict(world, **extra):
+    """the `config` object of the JSON line -- IDENTICAL (keys and values) in our arm and in the reference arm for the
+    same N; what differs between the arms (precision mode, CUDA graphs) is reported under `run`"""
+    c = {"workload": WORKLOAD, "frames_per_step": FRAMES, "batch": B, "char_len": TX, "decoder_steps": T, "r": R,
+         "l2": "GPU arm: 256 MB flush write between timed steps; CPU reference arm: not applicable",
+         "parallelism": f"replicas x{world}, no collective on the data path (the CPU reference arm runs on rank 0 only)"}
+    c.update(extra)
+    return c
 
 
 def peaks():
@@ -94,23 +105,66 @@ def cpu_oracle_step(params, inp, cfg):
         return O.inference(params, inp, cfg, train=False)
 
 
-CPU_THREADS_CAP = 16
+CPU_THREADS_DEFAULT = 16
+_cpu_threads = None            # chosen once per process (see pick_cpu_threads)
 
 
-def time_cpu_oracle(iters):
-    """The reference's CPU path stand-in: PyTorch-CPU fp32 oracle on the host cores, C2 forward.
-    Threads = min(16, cores): the graph is ~3000 small ops and more threads are SLOWER on this pool's hosts
-    (measured: 16 threads 37 K frames/s, 64 threads 3.9 K frames/s); the count used is reported as `cores`.
-    (Probing several thread counts inside the run was tried and removed: re-sizing the OpenMP pool repeatedly
-    cost minutes on the 64-core box.)"""
+def _oracle_setup():
     import torch
     from oracle import tacotron_oracle as O
-    threads = max(1, min(CPU_THREADS_CAP, os.cpu_count() or 1))
-    torch.set_num_threads(threads)
     cfg = O.OracleConfig(r=R, max_decode_iter=T)
     params = O.init_params(cfg, seed=1)
     inp = O.synthetic_inputs(cfg, B, TX, T, seed=0, with_targets=False)
-    cpu_oracle_step(params, inp, cfg)                        # warm-up
+    return cfg, params, inp
+
+
+def probe_worker(threads):
+    """child process of pick_cpu_threads: one warm-up + one timed C2 forward of the oracle at `threads` threads"""
+    import torch
+    torch.set_num_threads(threads)
+    cfg, params, inp = _oracle_setup()
+    cpu_oracle_step(params, inp, cfg)
+    t0 = time.perf_counter()
+    cpu_oracle_step(params, inp, cfg)
+    print(json.dumps({"threads": threads, "sec": time.perf_counter() - t0}), flush=True)
+
+
+def pick_cpu_threads(probe):
+    """Thread count for the CPU arm.  The oracle is ~3000 small ops per forward and more threads are often SLOWER on
+    this pool's hosts (round 1: 16 threads 37 K frames/s, 64 threads 3.9 K).  With `probe` (the --impl reference arm)
+    16 / 32 / 64 threads are each tried once in a CHILD process (re-sizing the OpenMP pool inside one process cost
+    minutes on the 64-core box) and the fastest is kept; otherwise 16."""
+    global _cpu_threads
+    if _cpu_threads is not None:
+        return _cpu_threads
+    ncpu = os.cpu_count() or 1
+    best, tried = min(CPU_THREADS_DEFAULT, ncpu), {}
+    if probe:
+        best_sec = None
+        for th in (16, 32, 64):
+            if th > ncpu:
+                continue
+            try:
+                out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference-probe", "--threads", str(th)],
+                                     capture_output=True, text=True, timeout=150, cwd=ROOT)
+                sec = json.loads(out.stdout.strip().splitlines()[-1])["sec"]
+                tried[th] = sec
+                if best_sec is None or sec < best_sec:
+                    best, best_sec = th, sec
+            except Exception as ex:                         # a probe that fails or times out is simply not chosen
+                tried[th] = f"failed: {type(ex).__name__}"
+    _cpu_threads = (best, tried, ncpu)
+    return _cpu_threads
+
+
+def time_cpu_oracle(iters, warmup=1, probe=False):
+    """The reference's CPU path stand-in: PyTorch-CPU fp32 oracle on the host cores, C2 forward."""
+    import torch
+    threads, tried, ncpu = pick_cpu_threads(probe)
+    torch.set_num_threads(threads)
+    cfg, params, inp = _oracle_setup()
+    for _ in range(max(1, warmup)):
+        cpu_oracle_step(params, inp, cfg)                    # warm-up
     ts = []
     for _ in range(iters):
         t0 = time.perf_counter()
@@ -124,7 +178,7 @@ def time_cpu_oracle_train():
     host cores (clip + Adam omitted: <1 % of the step).  One warm-up + one timed step (~5-15 s each)."""
     import torch
     from oracle import tacotron_oracle as O
-    threads = max(1, min(CPU_THREADS_CAP, os.cpu_count() or 1))
+    threads = pick_cpu_threads(False)[0]
     torch.set_num_threads(threads)
     cfg = O.OracleConfig(r=R)
     params = O.init_params(cfg, seed=1)
@@ -140,21 +194,28 @@ def time_cpu_oracle_train():
 
 
 def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  TensorFlow 1.2 cannot be installed here
+    (Python 3.12, no network), so this is the oracle port (`kind: "port"`), all host threads it can
+    use (probed), same metric / config keys / steps / warm-up as our arm; each step = one full C2 forward (about 1 s)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 20))
-    ts, threads = time_cpu_oracle(steps)
-    sec = statistics.median(ts)
+    steps = max(1, args.steps)
+    warmup = max(args.warmup, 1)
+    ts, threads = time_cpu_oracle(steps, warmup=warmup, probe=True)
+    _, tried, ncpu = pick_cpu_threads(True)
+    sec = statistics.mean(ts)
     val = FRAMES / sec
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "mel frames/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C2 synthetic: B=32, char 128, 200 decoder steps, r=5, inference forward (free-running)",
-                   "note": "reference arm = CPU oracle port of the TF-1.2 graph (TF 1.2 not installable: py3.12, no network)"},
-        "cpu_baseline": {"value": val, "unit": "mel frames/s", "cores": threads, "kind": "port",
-                         "sample": f"{steps} full C2 forward passes (32000 frames each), median"},
+        "config": config_dict(args.gpus),
+        "run": {"precision": "fp32 (PyTorch CPU, MKL/oneDNN)", "cuda_graph": False},
+        "note": "reference arm = CPU oracle port of the TF-1.2 graph (TF 1.2 not installable: py3.12, no network)",
+        "cpu_baseline": {"value": val, "unit": "mel frames/s", "cores": threads, "kind": "port", "host_cpus": ncpu,
+                         "threads_probed_sec_per_step": tried,
+                         "sample": f"{steps} full C2 forward passes (32000 frames each) after {warmup} warm-up, mean"},
         "e2e": {"value": val, "unit": "mel frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -169,7 +230,7 @@ def _log(msg):
     sys.stderr.flush()
 
 
-def measure_train(args, world, rank):
+def measure_train(args, world, rank, n=5, warm=2):
     """Side measurement: the TRAINING step on the same C2 batch per rank -- train-mode
     forward (dropout, scheduled sampling 0.5), L1 losses, hand-written backward, one SUM all-reduce of the flat
     28.4 MB gradient bucket over NCCL when N > 1 (config C4 = N x C2), global-norm clip, Adam.  Never allowed to break
@@ -205,10 +266,9 @@ def measure_train(args, world, rank):
         return {"error": err or "another rank failed its local training step"}
     try:
         m.dp = True
-        for _ in range(2):
+        for _ in range(max(warm, 2)):
             m.train_step(gi, lr=1e-4)
         D.barrier()
-        n = 5
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
         ev[0].record()
         for i in range(n):
@@ -218,6 +278,23 @@ def measure_train(args, world, rank):
         D.barrier()
         ms = D.max_over_ranks(ev[0].elapsed_time(ev[n]) / n)
         loss = float(m.loss)
+        # exposed communication: the same steps without the collective (every rank keeps stepping on its own gradients;
+        # the parameters diverge across ranks from here on, nothing after this point exchanges them)
+        exposed = None
+        if world > 1:
+            m.dp = False
+            m.train_step(gi, lr=1e-4)
+            D.barrier()
+            ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            nl = min(n, 10)
+            ev2[0].record()
+            for i in range(nl):
+                m.train_step(gi, lr=1e-4)
+            ev2[1].record()
+            torch.cuda.synchronize()
+            D.barrier()
+            ms_local = D.max_over_ranks(ev2[0].elapsed_time(ev2[1]) / nl)
+            exposed = {"ms_per_step_without_allreduce": ms_local, "exposed_comm_ms": ms - ms_local}
         # one more step with events between its phases (this rank only; the phases overlap host work differently than
         # in the free-running loop above, so they need not add up to ms_per_step exactly)
         sections = None
@@ -244,13 +321,13 @@ def measure_train(args, world, rank):
                         "sumsq_clip_adam": e[2].elapsed_time(e[3])}
         except Exception as ex:
             sections = {"error": f"{type(ex).__name__}: {str(ex)[:120]}"}
-        return {"value": D.aggregate_throughput(FRAMES, world, ms), "unit": "mel frames/s", "ms_per_step": ms, "steps": n, "warmup": 3,
+        return {"value": D.aggregate_throughput(FRAMES, world, ms), "unit": "mel frames/s", "ms_per_step": ms, "steps": n, "warmup": max(warm, 2) + 1,
                 "n_gpus": world, "scaling": "weak",
                 "config": f"training step on C2 per rank (B=32, char 128, T=200, r=5; global batch {32 * world}): dropout 0.5, scheduled "
                           "sampling 0.5, L1 losses, backward, clip 5, Adam; targets (2 x 141 MB) + activations exceed L2",
-                "allreduce": ({"op": "SUM", "bytes_per_step": int(m.store.flat.numel() * 4), "backend": "nccl"} if world > 1 else None),
+                "allreduce": ({"op": "SUM", "bytes_per_step": int(m.store.flat.numel() * 4), "backend": "nccl", **(exposed or {})} if world > 1 else None),
                 "precision": (f"{args.precision} forward; backward fp32-grade: " +
-                              ("3xTF32 mma.sync tensor-core GEMMs" if args.precision == "tf32" else "exact-product FFMA GEMMs")),
+                              ("exact-product FFMA GEMMs" if args.precision == "fp32" else "3xTF32 tensor-core GEMMs")),
                 "loss_last_step": loss,
                 "sections_ms": sections}
     except Exception as ex:
@@ -530,31 +607,40 @@ def run_ours(args):
         dms = statistics.mean(dec_ms)
         ach = DECODER_GFLOP / dms                      # GFLOP / ms = TFLOP/s
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r01_decoder_traffic.json")
-        if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("dram_bytes")
-        # the same step with every contraction in exact fp32 (precision='fp32': SIMT FFMA GEMMs instead of TF32
-        # tensor cores) -- reported beside the headline so that both precision modes are measured in the same run
-        exact = None
-        if args.precision == "tf32" and not args.no_fp32_mode:
+        for tp in ("r02_decoder_traffic.json", "r01_decoder_traffic.json"):     # ncu --set full capture of the same kernel (per launch)
+            tp = os.path.join(ROOT, "profiles", tp)
+            if os.path.exists(tp):
+                traffic = json.load(open(tp)).get("dram_bytes")
+                break
+        # the same step in the other precision modes, measured in the same run (5 steps each, this rank only):
+        #   tf32 = single-pass TF32 tensor-core products (10-bit mantissa: NARROWER than the reference's fp32 arithmetic,
+        #          stated tolerance 5e-3) -- a side result, never the headline;
+        #   fp32 = exact-product FFMA kernel (the on-GPU cross-check path)
+        def side_mode(prec, note):
             try:
-                cfg32 = Config(r=R, vocab_size=64, max_decode_iter=T, precision="fp32", cuda_graph=not args.no_graph)
-                m32 = Tacotron(cfg32, None, train=False, seed=1)
+                cfgp = Config(r=R, vocab_size=64, max_decode_iter=T, precision=prec, cuda_graph=not args.no_graph)
+                mp = Tacotron(cfgp, None, train=False, seed=1)
                 for _ in range(3):
-                    m32.inference(inp, train=False)
+                    mp.inference(inp, train=False)
                 torch.cuda.synchronize()
-                s32 = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
-                e32 = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+                sp = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+                ep = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
                 for i in range(5):
                     flush.zero_()
-                    s32[i].record(); m32.inference(inp, train=False); e32[i].record()
+                    sp[i].record(); mp.inference(inp, train=False); ep[i].record()
                 torch.cuda.synchronize()
-                ms32 = sum(a.elapsed_time(b) for a, b in zip(s32, e32)) / 5
-                exact = {"value": FRAMES / (ms32 / 1e3), "unit": "mel frames/s", "ms_per_step": ms32, "steps": 5,
-                         "note": "precision='fp32': exact fp32 products everywhere (parity tolerance 2e-4), this rank only"}
-                del m32
-            except Exception as ex:           # never let the side measurement break the headline line
-                exact = {"error": str(ex)[:200]}
+                msp = sum(a.elapsed_time(b) for a, b in zip(sp, ep)) / 5
+                del mp
+                return {"value": FRAMES / (msp / 1e3), "unit": "mel frames/s", "ms_per_step": msp, "steps": 5, "note": note}
+            except Exception as ex:           # never let a side measurement break the headline line
+                return {"error": str(ex)[:200]}
+        exact, tf32_mode = None, None
+        if not args.no_fp32_mode:
+            if args.precision != "tf32":
+                tf32_mode = side_mode("tf32", "precision='tf32': single-pass TF32 products in the feed-forward contractions (parity "
+                                              "tolerance 5e-3 of max|ref|, measured ~1e-3): narrower than the reference's fp32 -- side result only")
+            if args.precision != "fp32":
+                exact = side_mode("fp32", "precision='fp32': exact-product FFMA kernel for every feed-forward contraction (parity tolerance 2e-4)")
         _log("fp32-mode side measurement done")
         c5 = None if (args.no_c5 or world > 1) else measure_c5_isolated(args)     # single-GPU latency: N=1 runs only
         _log("C5 (single utterance + Griffin-Lim) side measurement done")
@@ -563,9 +649,9 @@ def run_ours(args):
             _log("training step with each GEMM kernel (child process) done")
         cpu = None
         if not args.no_cpu_baseline:
-            ts, threads = time_cpu_oracle(3)
+            ts, threads = time_cpu_oracle(3, warmup=1, probe=False)
             sec = statistics.median(ts)
-            cpu = {"value": FRAMES / sec, "unit": "mel frames/s", "cores": threads, "kind": "port",
+            cpu = {"value": FRAMES / sec, "unit": "mel frames/s", "cores": threads, "kind": "port", "host_cpus": os.cpu_count(),
                    "sample": "3 full C2 forward passes of the PyTorch-CPU oracle (32000 frames each), median"}
             if train is not None and "error" not in train:
                 try:
@@ -578,13 +664,15 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": "mel frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32" if args.precision == "tf32" else "f32",
-            "dtype_note": ("feed-forward contractions: TF32 tensor-core multiplies, fp32 accumulate; bi-GRU fp32 FFMA; decoder 3xTF32 "
-                           "(fp32-grade); end-to-end within 5e-3 of the fp32 oracle (measured 8e-4)") if args.precision == "tf32" else "exact fp32 products",
+            "dtype": {"fp32x3": "f32", "tf32": "tf32", "fp32": "f32"}[args.precision],
+            "dtype_note": {"fp32x3": "fp32-grade everywhere: feed-forward contractions = error-compensated 3xTF32 on tcgen05 (x = hi + lo; lo.hi + hi.lo + "
+                                     "hi.hi, fp32 accumulate in TMEM; ~1e-6 relative), decoder = 3xTF32 mma.sync, bi-GRU = fp32 FFMA; passes the SAME "
+                                     "tolerances as the exact-product FFMA mode (2e-5 per op, 2e-4 end to end vs the fp32 oracle)",
+                           "tf32": "feed-forward contractions: single-pass TF32 tensor-core products, fp32 accumulate (tolerance 5e-3); recurrent kernels fp32-grade",
+                           "fp32": "exact fp32 products (FFMA) in every feed-forward contraction"}[args.precision],
             "data": "synthetic",
-            "config": {"workload": "C2 synthetic: B=32, char 128, 200 decoder steps, r=5, inference forward (free-running)",
-                       "frames_per_step": FRAMES, "l2": "256 MB flush write between timed steps", "parallelism": f"replicas x{world}",
-                       "precision": args.precision, "cuda_graph": not args.no_graph},
+            "config": config_dict(world),
+            "run": {"precision": args.precision, "cuda_graph": not args.no_graph},
             "decoder_step_p50_us": statistics.median(step_lat) if step_lat else None,
             "sections_ms": {"encoder": statistics.mean(enc_ms), "decoder": dms, "postnet": statistics.mean(post_ms)},
             "clocks": clocks,
@@ -595,6 +683,7 @@ def run_ours(args):
                          "unit": "TFLOP/s", "frac": ach / pk["bf16_tflops"], "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu dram__bytes_read+write.sum)", "peak_source": pk["source"],
                          "algorithmic_gflop_per_launch": DECODER_GFLOP,
                          "whole_step": {"achieved": FWD_GFLOP / ms_per_step, "frac": FWD_GFLOP / ms_per_step / pk["bf16_tflops"]}},
+            "tf32_mode": tf32_mode,
             "exact_fp32_mode": exact,
             "train": train,
             "c5_latency": c5,
@@ -608,12 +697,55 @@ def run_ours(args):
             _log(f"destroy_process_group: {ex}")
 
 
+def run_train(args):
+    """--mode train: the line's value is the C4 training step (N ranks x C2 per rank, global batch 32 N): train-mode
+    forward, L1 losses, hand-written backward, ONE NCCL all-reduce (SUM) of the flat 28.4 MB gradient bucket, global-norm
+    clip, Adam -- SURVEY.md section 8e.  Per-rank seeds; device-timed, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from tacotron_b200 import _lib
+    from tacotron_b200.utils import dist as D
+    world, rank, local = D.world()
+    torch.cuda.set_device(local)
+    D.init("nccl")
+    lib = _lib.lib()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = lib.taco_launch_count()
+    tr = measure_train(args, world, rank, n=max(args.steps, 1), warm=max(args.warmup, 3))
+    launches = lib.taco_launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        ok = "error" not in tr
+        line = {"metric": METRIC, "mode": "train", "value": tr.get("value"), "unit": "mel frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": tr.get("ms_per_step"), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if args.precision != "tf32" else "tf32", "data": "synthetic",
+                "config": config_dict(world, workload=f"C4 synthetic: {world} x (B=32, char 128, 200 decoder steps, r=5) data-parallel TRAINING step "
+                                                       "(dropout 0.5, scheduled sampling 0.5, L1 losses, backward, all-reduce, clip 5, Adam)",
+                                      parallelism=f"dp{world}: one NCCL all-reduce (SUM) of the 28.4 MB gradient bucket per step",
+                                      l2="targets (2 x 141 MB) + saved activations exceed L2 every step"),
+                "run": {"precision": args.precision, "cuda_graph": False},
+                "clocks": clocks, "gpu_launches": int(launches), "train": tr,
+                "e2e": None}
+        if not ok:
+            line["error"] = tr["error"]
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        try:
+            dist.destroy_process_group()
+        except Exception:
+            pass
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
+    ap.add_argument("--threads", type=int, default=16, help="(internal: --impl reference-probe)")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="infer (default, the BASELINE metric's configuration) or train: time the C4 data-parallel training step "
+                         "(N x C2, one NCCL all-reduce of the 28.4 MB gradient bucket per step) as the line's value")
     ap.add_argument("--precision", default="fp32x3", choices=["fp32x3", "tf32", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fp32-mode", action="store_true", help="skip the side measurement of the exact-fp32 precision mode")
@@ -623,6 +755,10 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "reference-probe":                 # internal: child process of pick_cpu_threads
+        probe_worker(args.threads)
+    elif args.mode == "train":
+        run_train(args)
     elif args.impl == "c5-worker":                       # internal: child process of measure_c5_isolated
         print(json.dumps(measure_c5(args)), flush=True)
     elif args.impl == "train-variant-worker":            # internal: child process, opt-in GEMM kernel

@@ -447,18 +447,6 @@ def measure_train_variant(args):
                "mma_3xtf32": {"ms_per_step": ms_mma, "value": FRAMES / (ms_mma / 1e3), "unit": "mel frames/s"},
                "ffma_exact": {"ms_per_step": ms_ffma, "value": FRAMES / (ms_ffma / 1e3), "unit": "mel frames/s"}}
         print(json.dumps(res), flush=True)                 # keep this result even if the experimental route below faults
-        try:                                               # opt-in, no hardware run yet: data gradients on the tcgen05 forward kernel
-            m.gemm_impl = 1
-            m.config.grad_dx_tc = True
-            m.backward(S)
-            torch.cuda.synchronize()
-            rel_tc = float((m._opt.g - g0).norm() / g0.norm())
-            ms_tc = timed()
-            res["tcgen05_data_gradients"] = {"grad_rel_l2_vs_ffma": rel_tc, "consistent": bool(rel_tc < 5e-2), "ms_per_step": ms_tc,
-                                             "value": FRAMES / (ms_tc / 1e3), "unit": "mel frames/s",
-                                             "note": "single-pass TF32 data gradients (Config.grad_dx_tc), weight gradients 3xTF32 mma.sync"}
-        except Exception as ex:
-            res["tcgen05_data_gradients"] = {"error": f"{type(ex).__name__}: {str(ex)[:160]}"}
         return res
     except Exception as ex:
         return {"error": f"{type(ex).__name__}: {str(ex)[:160]}"}

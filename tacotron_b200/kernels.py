@@ -68,10 +68,12 @@ def gemm(Cm, A, B, *, ta=False, tb=False, beta=0.0, shift=0, period=0, taps=1, d
     L.check(L.lib().taco_gemm(C.byref(d), _st()), "taco_gemm")
 
 
-# Data gradient of conv1d('same') / dense.  Default: taco_gemm (K-segmented, row-shifted form).  DX_TC = True routes it
-# through the tcgen05 forward kernel instead (taco_linear_fwd on dZ with the taps reversed and the weights transposed:
-# a conv data gradient IS a convolution) -- single-pass TF32 like the forward, opt-in until it has had a hardware run.
+# Data gradient of conv1d('same') / dense.  DX_TC = False: taco_gemm (K-segmented, row-shifted form on the mma.sync / FFMA
+# GEMM).  DX_TC = True routes it through the tcgen05 forward kernel instead (taco_linear_fwd on dZ with the taps reversed and
+# the weights transposed: a conv data gradient IS a convolution).  DX_TC_IMPL picks the arithmetic of that route:
+# TACO_IMPL_TC3 (3xTF32, fp32-grade -- what Tacotron.backward uses in 'fp32x3' mode) or TACO_IMPL_TC (single-pass TF32).
 DX_TC = False
+DX_TC_IMPL = L.IMPL_TC3
 
 
 def _cpad(c):
@@ -86,8 +88,13 @@ def conv_dx(dX, dZ, W, T, beta=0.0):
     if DX_TC and tma_ok:
         Wt = W.flip(0).transpose(1, 2).contiguous()                    # [taps, Cout, Cin]: taps reversed, weights transposed
         ld = taps * _cpad(Cout)
-        Wp = torch.zeros((Cin, ld), dtype=torch.float32, device=W.device)
-        L.check(L.lib().taco_pack_weight(_p(Wt), taps, Cout, Cin, _p(Wp), ld, _st()), "taco_pack_weight")
+        x3 = DX_TC_IMPL == L.IMPL_TC3
+        Wp = torch.zeros(((2 if x3 else 1) * Cin, ld), dtype=torch.float32, device=W.device)
+        if x3:
+            L.check(L.lib().taco_pack_weight_x3(_p(Wt), taps, Cout, Cin, _p(Wp), C.c_void_p(Wp.data_ptr() + Cin * ld * 4), ld, _st()),
+                    "taco_pack_weight_x3")
+        else:
+            L.check(L.lib().taco_pack_weight(_p(Wt), taps, Cout, Cin, _p(Wp), ld, _st()), "taco_pack_weight")
         d = L.LinearDesc()
         d.X = dZ.data_ptr(); d.ldx = dZ.stride(0); d.B = M // T; d.T = T; d.C = Cout
         d.taps = taps; d.tap0 = -(tap0 + taps - 1); d.N = Cin
@@ -97,7 +104,7 @@ def conv_dx(dX, dZ, W, T, beta=0.0):
         if beta != 0.0:
             assert beta == 1.0
             d.residual = dX.data_ptr(); d.ldr = dX.stride(0)             # accumulate: each element is read then written by one thread
-        d.impl = L.IMPL_TC
+        d.impl = DX_TC_IMPL
         L.check(L.lib().taco_linear_fwd(C.byref(d), _st()), "taco_linear_fwd[conv_dx]")
         return
     gemm(dX, dZ, W.reshape(taps * Cin, Cout)[:Cin], tb=True, beta=beta, shift=-tap0, dshift=-1, kper=Cout, taps=taps,

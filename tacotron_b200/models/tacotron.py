@@ -274,12 +274,20 @@ class Tacotron(object):
         if impl is None:
             impl = 0 if self.config.precision == "fp32" else 1
         prev = K.set_gemm_impl(impl)
-        prev_dx, K.DX_TC = K.DX_TC, bool(getattr(self.config, "grad_dx_tc", False))    # opt-in: data gradients on tcgen05
+        # data gradients of the dense / conv layers run on the tcgen05 forward kernel (a conv data gradient IS a conv):
+        # 3xTF32 (fp32-grade) in 'fp32x3' mode, single-pass TF32 in 'tf32' mode; 'fp32' mode keeps the exact-product GEMM.
+        # Config.grad_dx_tc overrides (True / False).
+        dx_tc = getattr(self.config, "grad_dx_tc", None)
+        if dx_tc is None:
+            dx_tc = self.config.precision != "fp32"
+        prev_dx, K.DX_TC = K.DX_TC, bool(dx_tc)
+        prev_impl, K.DX_TC_IMPL = K.DX_TC_IMPL, (L.IMPL_TC if self.config.precision == "tf32" else L.IMPL_TC3)
         try:
             grad.model_bwd(K, self.store, self._gviews, S, self.config)
         finally:
             K.set_gemm_impl(prev)
             K.DX_TC = prev_dx
+            K.DX_TC_IMPL = prev_impl
         return self._gviews
 
     def train_step(self, inputs, lr=None, **kw):

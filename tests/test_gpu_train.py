@@ -45,7 +45,8 @@ def test_decoder_bwd_kernel_full_batch():
     _assert(TC.check_decoder_bwd(5, True, B=32, Tx=32, T=6), 2e-4)
 
 
-@pytest.mark.parametrize("r,sched,precision,tol", [(2, True, "fp32", 2e-4), (5, False, "fp32", 2e-4), (2, True, "tf32", 2e-2)])
+@pytest.mark.parametrize("r,sched,precision,tol", [(2, True, "fp32", 2e-4), (5, False, "fp32", 2e-4), (2, True, "tf32", 2e-2),
+                                                   (2, True, "fp32x3", 2e-4)])
 def test_train_forward_saves(r, sched, precision, tol):
     res = TC.check_train_forward(r, sched, precision)
     assert res["_missing"][0] == 0, [k for k in res if k.startswith("_missing_names")]
@@ -59,13 +60,23 @@ def test_model_backward_matches_autograd(r, sched):
     assert res["_rel_l2"][0] <= 1e-4 and res["_cosine"][0] >= 0.9999
 
 
+@pytest.mark.parametrize("r,sched", [(2, True), (5, False)])
+def test_model_backward_fp32x3_matches_autograd(r, sched):
+    """the default precision mode: 3xTF32 tcgen05 forward, data gradients on the same tcgen05 kernel (3xTF32), weight gradients on
+    the 3xTF32 mma.sync GEMM -- held to the SAME bars as the exact-product fp32 mode"""
+    res = TC.check_model_bwd(r, sched, "fp32x3")
+    _assert(res, 2e-3, floor=1e-3)
+    assert res["_rel_l2"][0] <= 1e-4 and res["_cosine"][0] >= 0.9999
+
+
 def test_model_backward_tf32_forward():
     res = TC.check_model_bwd(5, True, "tf32")
     assert res["_rel_l2"][0] <= 0.15 and res["_cosine"][0] >= 0.98, (res["_rel_l2"], res["_cosine"])
 
 
-def test_train_step_matches_oracle():
-    res = TC.check_train_step(2, True, "fp32", steps=2)
+@pytest.mark.parametrize("precision", ["fp32", "fp32x3"])
+def test_train_step_matches_oracle(precision):
+    res = TC.check_train_step(2, True, precision, steps=2)
     params = {k: v for k, v in res.items() if k.startswith("param_worst")}
     _assert({k: v for k, v in res.items() if k not in params}, 1e-4, floor=1e-3)      # losses and global gradient norms
     # parameters after 2 Adam steps of lr 1e-3 (each moves a parameter by ~1e-3): 5e-4 catches a missing or

@@ -17,9 +17,14 @@
 //
 // One cooperative kernel runs all T steps; stages are separated by grid.sync().  Every stage is a skinny GEMM
 // out[32 x N] = in[32 x K] . W^T with W rows contiguous (TF [in,out] layouts make every data-gradient a "NT"
-// product): one warp per output column, lane = batch row, the 32 x K input staged once per CTA in shared memory.
-// Inter-stage data lives in L2 (ld.global.cg; never the non-coherent path).  This is a first, simple schedule --
-// the same dataflow treatment as the forward kernel (decoder.cu) is the planned optimisation.
+// product).  v2 schedule (v1: one warp per output column, the whole 32 x K input staged in shared memory by every CTA
+// and re-read from there once per column -- 137 us per step, bound by shared-memory traffic and by L2 weight-row loads):
+//   * a CTA owns C = ceil(N / grid) CONSECUTIVE output columns of every GEMM; their weight rows (C x K floats, 55 KB in
+//     total per CTA at r = 5) are copied into shared memory ONCE and stay there for all T steps;
+//   * the 8 warps split K; lane = batch row reads its K/8 slice of the input straight from L2 into registers (every
+//     input element is read once per CTA and reused for all C columns), weights are shared-memory broadcasts;
+//   * per-warp partial sums are combined through shared memory, one thread per (row, column) runs the stage epilogue.
+// Inter-stage data lives in L2 (ld.global.cg; never the non-coherent path).
 // Semantics pinned by tests/mirror_kernels.py::decoder_bwd.
 #ifndef TACO_HOST_EMU
 #include <cooperative_groups.h>
@@ -36,6 +41,8 @@ constexpr int U = 256;        // decoder / attention units
 constexpr int RB = 32;        // rows (utterances) per launch
 constexpr int NW = 8;         // warps per CTA
 constexpr int MAXK = 512;
+constexpr int CB = 8;         // output columns processed per pass (register accumulators per lane)
+constexpr int NGEMM = 12;     // GEMMs per step (weight-row cache slots)
 
 struct DecBwdP {
     int B, T, Tx, OUT, MF;
@@ -45,6 +52,8 @@ struct DecBwdP {
     const uint8_t* sel;
     float *DATT, *DY, *DPQ, *DSCORE, *DCTX, *DG[3], *DC[3], *DZ, *DPN2, *DPN1, *DX;
     float* ws;
+    unsigned int* bar;       // grid-barrier counter (zeroed by the host before the launch)
+    int cache_weights;       // 1: this CTA's weight rows fit in shared memory (the normal case); 0: read them from L2
 };
 
 // scratch layout (floats): every buffer is [32][ld]
@@ -54,72 +63,97 @@ constexpr int WS_DINC = WS_DRES + RB * U;         // [32][256]
 constexpr int WS_DHR = WS_DINC + RB * U;          // [32][256]
 constexpr int WS_DHU = WS_DHR + RB * U;           // [3][32][256]
 constexpr int WS_DHC = WS_DHU + 3 * RB * U;       // [3][32][256]   carries, zeroed by the host
-constexpr int WS_TOTAL = WS_DHC + 3 * RB * U;
+constexpr int WS_BAR = WS_DHC + 3 * RB * U;       // grid-barrier counter (1 word, padded)
+constexpr int WS_TOTAL = WS_BAR + 32;
 
-// out[row][n] = sum_k in[row][k] * W[n][k]   (row = lane).  Columns are dealt to the warps of the whole grid; with
-// `reverse` they are dealt from the last warp backwards so that two GEMMs of one stage land on different CTAs.
-template <class Epi>
-__device__ __forceinline__ void skinny_gemm(float* in_s, const float* in, int ldi, int rows, int K, const float* __restrict__ W, int ldw,
-                                            int N, bool reverse, Epi epi) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int TW = gridDim.x * NW;
-    const int first = reverse ? (TW - 1 - (int)(blockIdx.x * NW + NW - 1)) : (int)(blockIdx.x * NW);   // smallest column index of this CTA
-    if (first >= N) return;                              // CTA-uniform: no column for any warp of this CTA
-    const int lds = K + 1;
-    const int K4 = K >> 2;
-    // stage in[32][K] -> in_s: four independent 16-byte L2 loads per thread are issued before the first store (the
-    // straightforward one-load-one-store loop serialised on the load latency: ~16 round trips per stage at K = 512)
-    const int total = RB * K4;
-    for (int base = tid; base < total; base += 4 * blockDim.x) {
-        float4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int idx = base + u * blockDim.x;
-            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (idx < total) {
-                const int row = idx / K4, k4 = idx - row * K4;
-                if (row < rows) v[u] = __ldcg(reinterpret_cast<const float4*>(in + (int64_t)row * ldi) + k4);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int idx = base + u * blockDim.x;
-            if (idx < total) {
-                const int row = idx / K4, k4 = idx - row * K4;
-                float* d = in_s + row * lds + 4 * k4;
-                d[0] = v[u].x; d[1] = v[u].y; d[2] = v[u].z; d[3] = v[u].w;
-            }
-        }
-    }
-    __syncthreads();
-    const int gw = blockIdx.x * NW + warp;
-    for (int n = reverse ? (TW - 1 - gw) : gw; n < N; n += TW) {
-        const float4* wrow = reinterpret_cast<const float4*>(W + (int64_t)n * ldw);
-        const float* a = in_s + lane * lds;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-        // weight rows come from L2 (~300+ cycles per dependent load): keep 16 independent 16-byte loads in flight per
-        // warp.  (First hardware run had unroll 4: 12.5 us per stage, latency-bound on exactly these loads.)  The four
-        // accumulators see the same addends in the same order whatever the unroll factor, so results are bit-identical.
-#pragma unroll 16
-        for (int k4 = 0; k4 < K4; ++k4) {
-            const float4 w = __ldg(wrow + k4);
-            a0 = fmaf(a[4 * k4 + 0], w.x, a0);
-            a1 = fmaf(a[4 * k4 + 1], w.y, a1);
-            a2 = fmaf(a[4 * k4 + 2], w.z, a2);
-            a3 = fmaf(a[4 * k4 + 3], w.w, a3);
-        }
-        epi(lane, n, (a0 + a1) + (a2 + a3));
-    }
-    __syncthreads();                                     // in_s is reused by the next GEMM
+// columns of GEMM `N` owned by this CTA: C = ceil(N / grid) consecutive columns; `reverse` deals them from the last CTA
+// backwards so that the two GEMMs of one stage land on different CTAs
+__host__ __device__ inline void cta_columns(int N, int G, int cta, bool reverse, int& n0, int& n1) {
+    const int C = (N + G - 1) / G;
+    const int c = reverse ? (G - 1 - cta) : cta;
+    n0 = c * C;
+    n1 = n0 + C < N ? n0 + C : N;
+    if (n0 > N) n0 = N;
 }
 
-__global__ void __launch_bounds__(256, 1) decoder_bwd_kernel(const DecBwdP p) {
-    cg::grid_group grid = cg::this_grid();
+// out[row][n] = sum_k in[row][k] * W[n][k]   (row = lane).  wc: this CTA's weight rows [n1-n0][K] in shared memory, or
+// nullptr (rows are then read from global memory).  part_s: [NW][CB][32] floats.
+template <class Epi>
+__device__ __forceinline__ void skinny_gemm(float* part_s, const float* in, int ldi, int rows, int K, const float* __restrict__ W, int ldw,
+                                            int N, bool reverse, const float* wc, Epi epi) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    int n0, n1;
+    cta_columns(N, (int)gridDim.x, (int)blockIdx.x, reverse, n0, n1);
+    if (n0 >= n1) return;                                // CTA-uniform: no column for this CTA
+    const int K4 = K >> 2;
+    const int cpw = (K4 + NW - 1) / NW;                  // 16-byte chunks of K per warp
+    const int c_lo = warp * cpw, c_hi = (c_lo + cpw < K4) ? c_lo + cpw : K4;
+    const float4* arow = reinterpret_cast<const float4*>(in + (int64_t)lane * ldi);
+    const bool live = lane < rows;
+    for (int nb = n0; nb < n1; nb += CB) {
+        const int nc = (n1 - nb < CB) ? n1 - nb : CB;
+        float acc[CB];
+#pragma unroll
+        for (int c = 0; c < CB; ++c) acc[c] = 0.f;
+        // this lane's slice of its input row: independent 16-byte L2 loads, four in flight ahead of the products
+#pragma unroll 4
+        for (int k4 = c_lo; k4 < c_hi; ++k4) {
+            const float4 a = live ? __ldcg(arow + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int c = 0; c < CB; ++c) {
+                if (c < nc) {                            // warp-uniform
+                    const float4 w = wc ? *reinterpret_cast<const float4*>(wc + (size_t)(nb - n0 + c) * K + 4 * k4)
+                                        : __ldg(reinterpret_cast<const float4*>(W + (int64_t)(nb + c) * ldw) + k4);
+                    acc[c] = fmaf(a.x, w.x, acc[c]); acc[c] = fmaf(a.y, w.y, acc[c]);
+                    acc[c] = fmaf(a.z, w.z, acc[c]); acc[c] = fmaf(a.w, w.w, acc[c]);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < CB; ++c)
+            if (c < nc) part_s[(warp * CB + c) * 32 + lane] = acc[c];
+        __syncthreads();
+        if (tid < nc * 32) {                             // one thread per (column, row)
+            const int c = tid >> 5;
+            float v = 0.f;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) v += part_s[(w * CB + c) * 32 + lane];
+            epi(lane, nb + c, v);
+        }
+        __syncthreads();                                 // part_s is reused
+    }
+}
+
+// Grid barrier on a monotonically increasing counter (all CTAs are co-resident: cooperative launch).  One release-add and
+// an acquire-poll per CTA: the cooperative-groups grid.sync() this replaces cost ~10 us per call here, 13 calls per step.
+struct GridBar {
+    unsigned int* ctr;
+    unsigned int target;
+    unsigned int G;
 #ifdef TACO_HOST_EMU
-    float* in_s = emu::dynamic_smem();                   // [32][MAXK+1]
+    __device__ void sync() { __syncthreads(); }
 #else
-    extern __shared__ __align__(16) float in_s[];        // [32][MAXK+1]
+    __device__ __forceinline__ void sync() {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            target += G;
+            red_release_add(ctr, 1u);
+            unsigned int spins = 0;
+            while (ld_acquire(ctr) < target) { if (++spins > (1u << 26)) __trap(); }
+        }
+        __syncthreads();
+    }
 #endif
+};
+
+__global__ void __launch_bounds__(256, 1) decoder_bwd_kernel(const DecBwdP p) {
+    GridBar grid{p.bar, 0u, gridDim.x};
+#ifdef TACO_HOST_EMU
+    float* dyn_s = emu::dynamic_smem();
+#else
+    extern __shared__ __align__(16) float dyn_s[];       // [NW][CB][32] partial sums | cached weight rows of this CTA
+#endif
+    float* in_s = dyn_s;                                 // (partial-sum scratch of skinny_gemm)
     __shared__ float dctx_s[U], dal_s[256], ds_s[256], red_s[NW];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int B = p.B, T = p.T, Tx = p.Tx, OUT = p.OUT, MF = p.MF;
@@ -130,6 +164,29 @@ __global__ void __launch_bounds__(256, 1) decoder_bwd_kernel(const DecBwdP p) {
     float* dhr = p.ws + WS_DHR;
     float* dhu = p.ws + WS_DHU;
     float* dhc = p.ws + WS_DHC;
+
+    // ---- weight-row cache: for each of the 12 GEMMs of a step, the rows of this CTA's columns, copied once ----
+    const float* wcp[NGEMM];
+    {
+        const float* Wm[NGEMM] = {p.W_a, p.W2, p.W1, p.W_q, p.W_out, p.Wc[2], p.Wg[2], p.Wc[1], p.Wg[1], p.Wc[0], p.Wg[0], p.W_in};
+        const int Nn[NGEMM] = {OUT + U, 256, MF, OUT, U, 2 * U, 2 * U, 2 * U, 2 * U, 2 * U, 2 * U, 128 + U};
+        const int Kk[NGEMM] = {U, 128, 256, U, OUT, U, 2 * U, U, 2 * U, U, 2 * U, U};
+        const bool rev[NGEMM] = {false, true, false, false, false, false, false, false, false, false, false, false};
+        float* cur = dyn_s + NW * CB * 32;
+        for (int g = 0; g < NGEMM; ++g) {
+            int n0, n1;
+            cta_columns(Nn[g], (int)gridDim.x, (int)blockIdx.x, rev[g], n0, n1);
+            wcp[g] = nullptr;
+            if (p.cache_weights && n1 > n0) {
+                wcp[g] = cur;
+                const int cnt = (n1 - n0) * Kk[g];       // rows are contiguous in W (ldw == K for every GEMM here)
+                const float* src = Wm[g] + (int64_t)n0 * Kk[g];
+                for (int i = tid; i < cnt; i += blockDim.x) cur[i] = __ldg(src + i);
+                cur += (cnt + 3) & ~3;
+            }
+        }
+        __syncthreads();
+    }
 
     // element-wise head of GRU layer i at step t for (row, unit n): consumes the gradient arriving at h_i(t)
     auto gru_head = [&](int i, int t, int row, int n, float dh_in) {
@@ -148,7 +205,7 @@ __global__ void __launch_bounds__(256, 1) decoder_bwd_kernel(const DecBwdP p) {
         // ================= stage 1: attention layer backward  |  pre-net layer 2 backward of step t+1 =================
         if (t >= 0) {
             const float* in = p.DATT + (int64_t)t * B * U;
-            skinny_gemm(in_s, in, U, B, U, p.W_a, U, OUT + U, false, [&](int row, int n, float v) {
+            skinny_gemm(in_s, in, U, B, U, p.W_a, U, OUT + U, false, wcp[0], [&](int row, int n, float v) {
                 if (row >= B) return;
                 if (n < OUT) dyatt[row * 512 + n] = v;
                 else p.DCTX[((int64_t)t * B + row) * U + (n - OUT)] = v;
@@ -156,7 +213,7 @@ __global__ void __launch_bounds__(256, 1) decoder_bwd_kernel(const DecBwdP p) {
         }
         if (tt < T) {
             const float* in = p.DPN2 + (int64_t)tt * B * 128;
-            skinny_gemm(in_s, in, 128, B, 128, p.W2, 128, 256, true, [&](int row, int n, float v) {
+            skinny_gemm(in_s, in, 128, B, 128, p.W2, 128, 256, true, wcp[1], [&](int row, int n, float v) {
                 if (row >= B) return;
                 const int64_t o = ((int64_t)tt * B + row) * 256 + n;
                 p.DPN1[o] = (__ldg(p.PN1 + o) > 0.f) ? v * p.ks : 0.f;
@@ -168,14 +225,34 @@ __global__ void __launch_bounds__(256, 1) decoder_bwd_kernel(const DecBwdP p) {
             for (int b = (int)gridDim.x - 1 - (int)blockIdx.x; b < B; b += gridDim.x) {
                 dctx_s[tid] = __ldcg(p.DCTX + ((int64_t)t * B + b) * U + tid);
                 __syncthreads();
-                for (int j = warp; j < Tx; j += NW) {                       // dalign_j = dctx . values_j
-                    const float* vj = p.values + ((int64_t)b * Tx + j) * U;
-                    float s = 0.f;
+                // dalign_j = dctx . values_j, four positions per warp and pass: 32 independent L2 loads are in flight before
+                // the first product (one position at a time exposed the L2 latency Tx/8 times per step)
+                for (int j0 = warp; j0 < Tx; j0 += 4 * NW) {
+                    float vv[4][U / 32];
 #pragma unroll
-                    for (int i = 0; i < U / 32; ++i) s = fmaf(dctx_s[lane + 32 * i], __ldg(vj + lane + 32 * i), s);
+                    for (int q = 0; q < 4; ++q) {
+                        const int j = j0 + q * NW;
+                        const float* vj = p.values + ((int64_t)b * Tx + (j < Tx ? j : j0)) * U;
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                    if (lane == 0) dal_s[j] = s;
+                        for (int i = 0; i < U / 32; ++i) vv[q][i] = __ldg(vj + lane + 32 * i);
+                    }
+                    float s4[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float sq = 0.f;
+#pragma unroll
+                        for (int i = 0; i < U / 32; ++i) sq = fmaf(dctx_s[lane + 32 * i], vv[q][i], sq);
+                        s4[q] = sq;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) s4[q] += __shfl_xor_sync(0xffffffffu, s4[q], o);
+                    }
+                    if (lane == 0) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) if (j0 + q * NW < Tx) dal_s[j0 + q * NW] = s4[q];
+                    }
                 }
                 __syncthreads();
                 const float aj = (tid < Tx) ? __ldg(p.align + ((int64_t)b * T + t) * Tx + tid) : 0.f;
@@ -198,12 +275,22 @@ __global__ void __launch_bounds__(256, 1) decoder_bwd_kernel(const DecBwdP p) {
                     const float pq = __ldg(p.PQ + ((int64_t)t * B + b) * U + d);
                     const float* kb = p.keys + (int64_t)b * Tx * U + d;
                     float acc = 0.f;
-                    for (int j = 0; j < Tx; ++j) {
-                        const float ds = ds_s[j];
-                        if (ds != 0.f) {
-                            const float e = tanhf_acc(__ldg(kb + (int64_t)j * U) + pq);
-                            acc = fmaf(ds, 1.0f - e * e, acc);
+                    // eight keys in flight per batch, no data-dependent branch (masked positions carry dscore = 0 and
+                    // finite keys): the one-at-a-time loop paid one L2 latency per position -- ~30 us of every 100 us step
+                    int j = 0;
+                    for (; j + 8 <= Tx; j += 8) {
+                        float kk[8];
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) kk[q] = __ldg(kb + (int64_t)(j + q) * U);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float e = tanhf_acc(kk[q] + pq);
+                            acc = fmaf(ds_s[j + q], 1.0f - e * e, acc);
                         }
+                    }
+                    for (; j < Tx; ++j) {
+                        const float e = tanhf_acc(__ldg(kb + (int64_t)j * U) + pq);
+                        acc = fmaf(ds_s[j], 1.0f - e * e, acc);
                     }
                     p.DPQ[((int64_t)t * B + b) * U + d] = acc * __ldg(p.v + d);
                 }
@@ -212,7 +299,7 @@ __global__ void __launch_bounds__(256, 1) decoder_bwd_kernel(const DecBwdP p) {
         }
         if (tt < T) {
             const float* in = p.DPN1 + (int64_t)tt * B * 256;
-            skinny_gemm(in_s, in, 256, B, 256, p.W1, 256, MF, false, [&](int row, int n, float v) {
+            skinny_gemm(in_s, in, 256, B, 256, p.W1, 256, MF, false, wcp[2], [&](int row, int n, float v) {
                 if (row >= B) return;
                 p.DX[((int64_t)tt * B + row) * MF + n] = v;
             });
@@ -222,7 +309,7 @@ __global__ void __launch_bounds__(256, 1) decoder_bwd_kernel(const DecBwdP p) {
         // ================= stage 3: query layer backward, total gradient at y(t) ======================================
         {
             const float* in = p.DPQ + (int64_t)t * B * U;
-            skinny_gemm(in_s, in, U, B, U, p.W_q, U, OUT, false, [&](int row, int n, float v) {
+            skinny_gemm(in_s, in, U, B, U, p.W_q, U, OUT, false, wcp[3], [&](int row, int n, float v) {
                 if (row >= B) return;
                 const int64_t o = ((int64_t)t * B + row) * OUT + n;
                 float dy = __ldg(p.dy_ext + o) + __ldcg(dyatt + row * 512 + n) + v;
@@ -234,7 +321,7 @@ __global__ void __launch_bounds__(256, 1) decoder_bwd_kernel(const DecBwdP p) {
         // ================= stage 4: output projection backward + GRU3 head ============================================
         {
             const float* in = p.DY + (int64_t)t * B * OUT;
-            skinny_gemm(in_s, in, OUT, B, OUT, p.W_out, OUT, U, false, [&](int row, int n, float v) {
+            skinny_gemm(in_s, in, OUT, B, OUT, p.W_out, OUT, U, false, wcp[4], [&](int row, int n, float v) {
                 if (row >= B) return;
                 dres[row * U + n] = v;
                 gru_head(2, t, row, n, v);
@@ -245,7 +332,7 @@ __global__ void __launch_bounds__(256, 1) decoder_bwd_kernel(const DecBwdP p) {
         for (int i = 2; i >= 0; --i) {
             {   // [dIN_c | drh] = dc_pre . Wc_i^T
                 const float* in = p.DC[i] + (int64_t)t * B * U;
-                skinny_gemm(in_s, in, U, B, U, p.Wc[i], U, 2 * U, false, [&](int row, int n, float v) {
+                skinny_gemm(in_s, in, U, B, U, p.Wc[i], U, 2 * U, false, wcp[5 + 2 * (2 - i)], [&](int row, int n, float v) {
                     if (row >= B) return;
                     if (n < U) { dINc[row * U + n] = v; return; }
                     const int k = n - U;
@@ -259,7 +346,7 @@ __global__ void __launch_bounds__(256, 1) decoder_bwd_kernel(const DecBwdP p) {
             grid.sync();
             {   // [dIN_g | dh_g] = [dr_pre, du_pre] . Wg_i^T
                 const float* in = p.DG[i] + (int64_t)t * B * 2 * U;
-                skinny_gemm(in_s, in, 2 * U, B, 2 * U, p.Wg[i], 2 * U, 2 * U, false, [&](int row, int n, float v) {
+                skinny_gemm(in_s, in, 2 * U, B, 2 * U, p.Wg[i], 2 * U, 2 * U, false, wcp[6 + 2 * (2 - i)], [&](int row, int n, float v) {
                     if (row >= B) return;
                     if (n < U) {
                         const float dIN = __ldcg(dINc + row * U + n) + v;   // gradient at the layer input
@@ -276,7 +363,7 @@ __global__ void __launch_bounds__(256, 1) decoder_bwd_kernel(const DecBwdP p) {
         // ================= stage 7: input projection backward =========================================================
         {
             const float* in = p.DZ + (int64_t)t * B * U;
-            skinny_gemm(in_s, in, U, B, U, p.W_in, U, 128 + U, false, [&](int row, int n, float v) {
+            skinny_gemm(in_s, in, U, B, U, p.W_in, U, 128 + U, false, wcp[11], [&](int row, int n, float v) {
                 if (row >= B) return;
                 if (n < 128) {
                     const int64_t o = ((int64_t)t * B + row) * 128 + n;
@@ -317,9 +404,11 @@ extern "C" int taco_decoder_bwd(const taco_decoder_bwd_args* a, void* stream) {
     p.DATT = a->DATT; p.DY = a->DY; p.DPQ = a->DPQ; p.DSCORE = a->DSCORE; p.DCTX = a->DCTX; p.DZ = a->DZ; p.DPN2 = a->DPN2;
     p.DPN1 = a->DPN1; p.DX = a->DX;
     p.ws = a->workspace;
+    p.bar = reinterpret_cast<unsigned int*>(a->workspace + WS_BAR);
 #ifdef TACO_HOST_EMU
     // host emulation: one CTA (the kernel is written for any grid size), grid.sync() = block barrier
     (void)stream;
+    p.cache_weights = 0;                                 // one CTA owns every column: rows come from global memory
     memset(a->workspace, 0, (size_t)WS_TOTAL * 4);
     memset(a->DATT + (int64_t)(a->T - 1) * a->B * U, 0, (size_t)a->B * U * 4);
     emu::launch(dim3(1), dim3(256), [&] { decoder_bwd_kernel(p); });
@@ -327,18 +416,26 @@ extern "C" int taco_decoder_bwd(const taco_decoder_bwd_args* a, void* stream) {
     return 0;
 #else
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = (size_t)RB * (MAXK + 1) * 4;
+    // dynamic smem: partial sums + the weight rows of one CTA at the grid size used (128 CTAs): ceil(N/128) * K per GEMM
+    const int OUTh = 80 * a->r;
+    const int Nn[NGEMM] = {OUTh + U, 256, 80, OUTh, U, 2 * U, 2 * U, 2 * U, 2 * U, 2 * U, 2 * U, 128 + U};
+    const int Kk[NGEMM] = {U, 128, 256, U, OUTh, U, 2 * U, U, 2 * U, U, 2 * U, U};
+    size_t cache_floats = 0;
+    for (int g = 0; g < NGEMM; ++g) cache_floats += (size_t)(((Nn[g] + 127) / 128) * Kk[g] + 3) & ~(size_t)3;
+    const size_t smem = ((size_t)NW * CB * 32 + cache_floats) * 4;
+    TACO_CHECK(smem <= 200 * 1024, "taco_decoder_bwd: weight-row cache of %zu bytes does not fit", smem);
     static int max_ctas = 0;
     if (max_ctas == 0) {
-        TACO_CUDA(cudaFuncSetAttribute(decoder_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TACO_CUDA(cudaFuncSetAttribute(decoder_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         int dev = 0, sms = 0, per_sm = 0;
         TACO_CUDA(cudaGetDevice(&dev));
         TACO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        TACO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decoder_bwd_kernel, 256, smem));
+        TACO_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decoder_bwd_kernel, 256, 200 * 1024));
         TACO_CHECK(per_sm >= 1, "taco_decoder_bwd: kernel does not fit on an SM");
         max_ctas = sms * per_sm;
     }
     const int G = max_ctas < 128 ? max_ctas : 128;
+    p.cache_weights = (G == 128) ? 1 : 0;                // the cache is sized for 128 CTAs
     // carries start at zero; dattn(T-1) = 0 (the last attention state feeds nothing)
     TACO_CUDA(cudaMemsetAsync(a->workspace, 0, (size_t)WS_TOTAL * 4, st));
     TACO_CUDA(cudaMemsetAsync(a->DATT + (int64_t)(a->T - 1) * a->B * U, 0, (size_t)a->B * U * 4, st));

@@ -66,6 +66,61 @@ constexpr int WS_DHC = WS_DHU + 3 * RB * U;       // [3][32][256]   carries, zer
 constexpr int WS_BAR = WS_DHC + 3 * RB * U;       // grid-barrier counter (1 word, padded)
 constexpr int WS_TOTAL = WS_BAR + 32;
 
+// One block of <= CB output columns: res[c][row] = sum_k in[row][k] * W[nb + c][k]  (row = lane), left in part_s + NW*CB*32.
+// wc: the block's weight rows [nc][K] in shared memory, or nullptr (rows are then read from global memory).
+// NOT inlined: the fully unrolled body is ~1000 instructions and the step has 12 GEMMs -- inlined copies made the kernel
+// 255 KB of code and every stage started with a cold instruction cache (ncu: 11 % issue utilisation, 13 K cycles per stage).
+#ifdef TACO_HOST_EMU
+#define TACO_NOINLINE
+#else
+#define TACO_NOINLINE __noinline__
+#endif
+__device__ TACO_NOINLINE void gemm_block(float* part_s, const float* in, int ldi, int rows, int K, const float* __restrict__ W, int ldw,
+                                         int nb, int nc, const float* wc) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int K4 = K >> 2;
+    const int cpw = (K4 + NW - 1) / NW;                  // 16-byte chunks of K per warp
+    const int c_lo = warp * cpw, c_hi = (c_lo + cpw < K4) ? c_lo + cpw : K4;
+    const float4* arow = reinterpret_cast<const float4*>(in + (int64_t)lane * ldi);
+    const bool live = lane < rows;
+    // this lane's slice of its input row: up to 16 independent 16-byte L2 loads (K <= 512), all in flight before the first product
+    constexpr int MAXC = MAXK / 4 / NW;                  // 16
+    float4 av[MAXC];
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i)
+        av[i] = (live && c_lo + i < c_hi) ? __ldcg(arow + c_lo + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float acc[CB];
+#pragma unroll
+    for (int c = 0; c < CB; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i) {
+        const int k4 = c_lo + i;
+        if (k4 >= c_hi) break;                           // warp-uniform
+        const float4 a = av[i];
+#pragma unroll
+        for (int c = 0; c < CB; ++c) {
+            if (c < nc) {                                // warp-uniform
+                const float4 w = wc ? *reinterpret_cast<const float4*>(wc + (size_t)c * K + 4 * k4)
+                                    : __ldg(reinterpret_cast<const float4*>(W + (int64_t)(nb + c) * ldw) + k4);
+                acc[c] = fmaf(a.x, w.x, acc[c]); acc[c] = fmaf(a.y, w.y, acc[c]);
+                acc[c] = fmaf(a.z, w.z, acc[c]); acc[c] = fmaf(a.w, w.w, acc[c]);
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < CB; ++c)
+        if (c < nc) part_s[(warp * CB + c) * 32 + lane] = acc[c];
+    __syncthreads();
+    if (tid < nc * 32) {                                 // one thread per (column, row)
+        const int c = tid >> 5;
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) v += part_s[(w * CB + c) * 32 + lane];
+        part_s[NW * CB * 32 + tid] = v;
+    }
+    __syncthreads();
+}
+
 // columns of GEMM `N` owned by this CTA: C = ceil(N / grid) consecutive columns; `reverse` deals them from the last CTA
 // backwards so that the two GEMMs of one stage land on different CTAs
 __host__ __device__ inline void cta_columns(int N, int G, int cta, bool reverse, int& n0, int& n1) {
@@ -76,50 +131,17 @@ __host__ __device__ inline void cta_columns(int N, int G, int cta, bool reverse,
     if (n0 > N) n0 = N;
 }
 
-// out[row][n] = sum_k in[row][k] * W[n][k]   (row = lane).  wc: this CTA's weight rows [n1-n0][K] in shared memory, or
-// nullptr (rows are then read from global memory).  part_s: [NW][CB][32] floats.
+// out[row][n] = sum_k in[row][k] * W[n][k] for this CTA's columns, then the stage epilogue per (row, column)
 template <class Epi>
 __device__ __forceinline__ void skinny_gemm(float* part_s, const float* in, int ldi, int rows, int K, const float* __restrict__ W, int ldw,
                                             int N, bool reverse, const float* wc, Epi epi) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     int n0, n1;
     cta_columns(N, (int)gridDim.x, (int)blockIdx.x, reverse, n0, n1);
-    if (n0 >= n1) return;                                // CTA-uniform: no column for this CTA
-    const int K4 = K >> 2;
-    const int cpw = (K4 + NW - 1) / NW;                  // 16-byte chunks of K per warp
-    const int c_lo = warp * cpw, c_hi = (c_lo + cpw < K4) ? c_lo + cpw : K4;
-    const float4* arow = reinterpret_cast<const float4*>(in + (int64_t)lane * ldi);
-    const bool live = lane < rows;
-    for (int nb = n0; nb < n1; nb += CB) {
+    for (int nb = n0; nb < n1; nb += CB) {               // one block on the GPU (<= 6 columns per CTA at 128 CTAs)
         const int nc = (n1 - nb < CB) ? n1 - nb : CB;
-        float acc[CB];
-#pragma unroll
-        for (int c = 0; c < CB; ++c) acc[c] = 0.f;
-        // this lane's slice of its input row: independent 16-byte L2 loads, four in flight ahead of the products
-#pragma unroll 4
-        for (int k4 = c_lo; k4 < c_hi; ++k4) {
-            const float4 a = live ? __ldcg(arow + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-            for (int c = 0; c < CB; ++c) {
-                if (c < nc) {                            // warp-uniform
-                    const float4 w = wc ? *reinterpret_cast<const float4*>(wc + (size_t)(nb - n0 + c) * K + 4 * k4)
-                                        : __ldg(reinterpret_cast<const float4*>(W + (int64_t)(nb + c) * ldw) + k4);
-                    acc[c] = fmaf(a.x, w.x, acc[c]); acc[c] = fmaf(a.y, w.y, acc[c]);
-                    acc[c] = fmaf(a.z, w.z, acc[c]); acc[c] = fmaf(a.w, w.w, acc[c]);
-                }
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < CB; ++c)
-            if (c < nc) part_s[(warp * CB + c) * 32 + lane] = acc[c];
-        __syncthreads();
-        if (tid < nc * 32) {                             // one thread per (column, row)
-            const int c = tid >> 5;
-            float v = 0.f;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) v += part_s[(w * CB + c) * 32 + lane];
-            epi(lane, nb + c, v);
-        }
+        gemm_block(part_s, in, ldi, rows, K, W, ldw, nb, nc, wc ? wc + (size_t)(nb - n0) * K : nullptr);
+        const int tid = threadIdx.x;
+        if (tid < nc * 32) epi(tid & 31, nb + (tid >> 5), part_s[NW * CB * 32 + tid]);
         __syncthreads();                                 // part_s is reused
     }
 }
@@ -172,7 +194,7 @@ __global__ void __launch_bounds__(256, 1) decoder_bwd_kernel(const DecBwdP p) {
         const int Nn[NGEMM] = {OUT + U, 256, MF, OUT, U, 2 * U, 2 * U, 2 * U, 2 * U, 2 * U, 2 * U, 128 + U};
         const int Kk[NGEMM] = {U, 128, 256, U, OUT, U, 2 * U, U, 2 * U, U, 2 * U, U};
         const bool rev[NGEMM] = {false, true, false, false, false, false, false, false, false, false, false, false};
-        float* cur = dyn_s + NW * CB * 32;
+        float* cur = dyn_s + NW * CB * 32 + CB * 32;
         for (int g = 0; g < NGEMM; ++g) {
             int n0, n1;
             cta_columns(Nn[g], (int)gridDim.x, (int)blockIdx.x, rev[g], n0, n1);
@@ -422,7 +444,7 @@ extern "C" int taco_decoder_bwd(const taco_decoder_bwd_args* a, void* stream) {
     const int Kk[NGEMM] = {U, 128, 256, U, OUTh, U, 2 * U, U, 2 * U, U, 2 * U, U};
     size_t cache_floats = 0;
     for (int g = 0; g < NGEMM; ++g) cache_floats += (size_t)(((Nn[g] + 127) / 128) * Kk[g] + 3) & ~(size_t)3;
-    const size_t smem = ((size_t)NW * CB * 32 + cache_floats) * 4;
+    const size_t smem = ((size_t)NW * CB * 32 + CB * 32 + cache_floats) * 4;
     TACO_CHECK(smem <= 200 * 1024, "taco_decoder_bwd: weight-row cache of %zu bytes does not fit", smem);
     static int max_ctas = 0;
     if (max_ctas == 0) {

@@ -42,6 +42,7 @@ struct TcArgs {
     int tile_stride;   // 128, or 127 when pooling
     int pool;
     int lo_row0;       // X3: first row of the lo half in the packed weight buffer (= rows of the hi half)
+    int direct;        // 1: register-direct vectorised epilogue (all row strides multiples of 4 floats), 0: transposing epilogue
     EpiParams e;
 };
 
@@ -51,7 +52,8 @@ struct SmemLayout {
     static constexpr int STAGE_BYTES = (X3 ? 2 : 1) * (A_STAGE_BYTES + B_STAGE_BYTES);   // X3: A | A_lo | B_hi | B_lo
     static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
     static constexpr int BAR_OFFSET = PIPE_BYTES;
-    static constexpr int TOTAL = PIPE_BYTES + 128 + 1024;   // barriers + alignment slack
+    static constexpr int CONST_OFFSET = PIPE_BYTES + 128;   // direct epilogue: bias[256] | scale[256] | shift[256] | first rows [4][32]
+    static constexpr int TOTAL = PIPE_BYTES + 128 + 3072 + 512 + 1024;   // barriers + epilogue constants + alignment slack
 };
 
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
@@ -205,6 +207,125 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                 mbar_arrive(&conv_bar[s]);
             }
         }
+        if (a.direct) {
+            // ================= register-direct epilogue =================
+            // TMEM lane = output row: after tcgen05.ld a lane holds 32 consecutive columns of ITS row.  The fused epilogue
+            // runs on those registers and the row segment leaves as eight 16-byte stores -- ~4 instructions per element
+            // less than the transposing epilogue below (which measured ~37 K warp-instructions per 128x128 tile and made
+            // every short-K contraction epilogue-bound: profiles/r02_ncu_summary.md).
+            float* cst = reinterpret_cast<float*>(smem + L::CONST_OFFSET);
+            float* frow = cst + 768;
+            const int et = threadIdx.x - 64;
+            for (int i = et; i < BN; i += 128) {
+                if (MODE == 1) {
+                    cst[i] = a.e.bias ? __ldg(a.e.bias + i) : 0.f;
+                } else {
+                    const int col = n0 + i;
+                    const bool cv = col < a.N;
+                    cst[i] = (cv && a.e.bias) ? __ldg(a.e.bias + col) : 0.f;
+                    cst[256 + i] = (cv && a.e.scale) ? __ldg(a.e.scale + col) : 1.f;
+                    cst[512 + i] = (cv && a.e.shift) ? __ldg(a.e.shift + col) : 0.f;
+                }
+            }
+            named_bar_sync(1, 128);
+            mbar_wait(tmem_full, 0);
+            tc_fence_after();
+            const int row = q * 32 + lane;
+            const int t = t0 + row;
+            const bool row_ok = (t < a.T) && (!a.pool || row < TC_BM - 1 || t == a.T - 1);
+            const int64_t grow = (int64_t)b * a.T + t;
+            constexpr int NCH = (MODE == 1) ? (BN / 2) / 32 : BN / 32;
+            for (int ch = 0; ch < NCH; ++ch) {
+                uint32_t v[32];
+                float y[32];
+                tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+                tc_wait_ld();
+                const int c0 = ch * 32;                       // column offset inside the tile
+                if (MODE == 1) {
+                    uint32_t w[32];
+                    tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN / 2 + ch * 32), w);
+                    tc_wait_ld();
+                    const float* hx = a.e.hx + grow * a.e.ldhx + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 bh = *reinterpret_cast<const float4*>(cst + c0 + j);
+                        const float4 bt = *reinterpret_cast<const float4*>(cst + BN / 2 + c0 + j);
+                        const float4 x = row_ok ? __ldg(reinterpret_cast<const float4*>(hx + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float xs[4] = {x.x, x.y, x.z, x.w}, bhs[4] = {bh.x, bh.y, bh.z, bh.w}, bts[4] = {bt.x, bt.y, bt.z, bt.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float H = fmaxf(__uint_as_float(v[j + k]) + bhs[k], 0.f);
+                            const float Tg = sigmoidf_acc(__uint_as_float(w[j + k]) + bts[k]);
+                            y[j + k] = H * Tg + xs[k] * (1.0f - Tg);
+                        }
+                    }
+                } else {
+                    const int act = a.e.act;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 cb = *reinterpret_cast<const float4*>(cst + c0 + j);
+                        const float4 sc = *reinterpret_cast<const float4*>(cst + 256 + c0 + j);
+                        const float4 sh = *reinterpret_cast<const float4*>(cst + 512 + c0 + j);
+                        const float cbs[4] = {cb.x, cb.y, cb.z, cb.w}, scs[4] = {sc.x, sc.y, sc.z, sc.w}, shs[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            float u = __uint_as_float(v[j + k]) + cbs[k];
+                            u = (act == TACO_ACT_RELU) ? fmaxf(u, 0.f) : (act == TACO_ACT_NONE) ? u : apply_act(u, act);
+                            y[j + k] = fmaf(u, scs[k], shs[k]);
+                        }
+                    }
+                    if (a.pool) {
+                        // max_pooling1d(2,1,'same') over t: row t needs row t+1 = the next lane; lane 31 takes the first row of
+                        // the next quarter from shared memory (tiles advance by 127 rows, so row 127 never needs a successor)
+                        named_bar_sync(1, 128);               // previous chunk's first rows have been consumed
+                        if (lane == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(frow + q * 32 + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+                        }
+                        named_bar_sync(1, 128);
+                        const bool has_next = (t + 1 < a.T) && (row + 1 < TC_BM);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float nx = __shfl_down_sync(0xffffffffu, y[j], 1);
+                            if (lane == 31) nx = frow[((q + 1) & 3) * 32 + j];
+                            if (has_next) y[j] = fmaxf(y[j], nx);
+                        }
+                    }
+                    if (a.e.keep) {
+                        const uint4* kp = reinterpret_cast<const uint4*>(a.e.keep + grow * (int64_t)a.e.N + n0 + c0);
+                        if (row_ok) {
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const uint4 kk = kp[h];
+                                const uint32_t ks[4] = {kk.x, kk.y, kk.z, kk.w};
+#pragma unroll
+                                for (int k = 0; k < 16; ++k)
+                                    y[16 * h + k] = ((ks[k >> 2] >> (8 * (k & 3))) & 0xffu) ? y[16 * h + k] * a.e.keep_scale : 0.f;
+                            }
+                        }
+                    }
+                    if (a.e.residual && row_ok) {
+                        const float* rp = a.e.residual + grow * a.e.ldr + n0 + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (n0 + c0 + j < a.N) {
+                                const float4 r4 = __ldg(reinterpret_cast<const float4*>(rp + j));
+                                y[j] += r4.x; y[j + 1] += r4.y; y[j + 2] += r4.z; y[j + 3] += r4.w;
+                            }
+                        }
+                    }
+                }
+                if (row_ok) {
+                    float* yp = a.e.Y + grow * a.e.ldy + (MODE == 1 ? 0 : n0) + c0;
+                    const int ncols = (MODE == 1) ? BN / 2 : a.N;
+                    const int cbase = (MODE == 1 ? 0 : n0) + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        if (cbase + j < ncols) *reinterpret_cast<float4*>(yp + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+                }
+            }
+            tc_fence_before();
+        } else {
         mbar_wait(tmem_full, 0);
         tc_fence_after();
         // scratch aliases the (now idle) pipeline buffers: [4 quarters][MODE?2:1][32][33] floats
@@ -261,7 +382,24 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                 const float csh = (cvalid && a.e.shift) ? __ldg(a.e.shift + col) : 0.f;
                 const int act = a.e.act;
                 auto affine = [&](float v) { return apply_act(v + cb, act) * csc + csh; };
-                if (!a.pool) {
+                if (!a.pool && !a.e.keep && !a.e.residual) {
+                    // fast path (the 1025-wide spectrogram projection lands here: its rows are not 16-byte aligned, so
+                    // the register-direct epilogue cannot be used): pointer stepping, no per-element index arithmetic
+                    if (cvalid) {
+                        float* yp = a.e.Y + row0 * a.e.ldy + col;
+                        const int64_t ys = a.e.ldy;
+                        if (act == TACO_ACT_RELU) {
+#pragma unroll 8
+                            for (int rr = 0; rr < nrows; ++rr) { *yp = fmaf(fmaxf(my_scr[rr * 33 + lane] + cb, 0.f), csc, csh); yp += ys; }
+                        } else if (act == TACO_ACT_NONE) {
+#pragma unroll 8
+                            for (int rr = 0; rr < nrows; ++rr) { *yp = fmaf(my_scr[rr * 33 + lane] + cb, csc, csh); yp += ys; }
+                        } else {
+#pragma unroll 4
+                            for (int rr = 0; rr < nrows; ++rr) { *yp = affine(my_scr[rr * 33 + lane]); yp += ys; }
+                        }
+                    }
+                } else if (!a.pool) {
                     if (cvalid) {
                         for (int rr0 = 0; rr0 < nrows; rr0 += EPB) {
                             float res[EPB];
@@ -303,6 +441,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
             if (a.pool) named_bar_sync(1, 128); else __syncwarp();
         }
         tc_fence_before();
+        }   // transposing epilogue
     }
 
     __syncthreads();
@@ -435,6 +574,15 @@ int taco_linear_tc(const taco_linear_desc* d, cudaStream_t st) {
     a.N = d->N;
     a.pool = d->pool ? 1 : 0;
     const bool x3 = d->impl == TACO_IMPL_TC3;
+    // register-direct epilogue: needs 16-byte aligned row segments everywhere it touches
+    {
+        const int nout = highway ? d->N / 2 : d->N;
+        bool ok = (d->ldy % 4) == 0 && (nout % 4) == 0 && taco_aligned16(d->Y);
+        if (d->residual) ok = ok && (d->ldr % 4) == 0 && taco_aligned16(d->residual);
+        if (d->hx) ok = ok && (d->ldhx % 4) == 0 && taco_aligned16(d->hx);
+        if (d->keep) ok = ok && (nout % 16) == 0 && taco_aligned16(d->keep);
+        a.direct = ok ? 1 : 0;
+    }
     a.lo_row0 = d->N;                                    // packed buffer = [hi rows 0..N) | lo rows N..2N)
     a.tile_stride = a.pool ? (TC_BM - 1) : TC_BM;
     a.tiles_per_seq = a.pool ? ((d->T - 1 + a.tile_stride - 1) / a.tile_stride) : ((d->T + TC_BM - 1) / TC_BM);

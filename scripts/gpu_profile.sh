@@ -1,11 +1,11 @@
 #!/bin/bash
-# ncu passes (1 GPU).  profile_step.py runs 3 eager steps; per kernel family we skip the launches of the first
-# two steps (setup + warm) and capture the third.
+# ncu passes (1 GPU).  profile_step.py runs 3 eager steps in the default precision (fp32x3); per kernel family the launches of
+# the first two steps (setup + warm) are skipped and the third is captured.  Outputs: gpurun_out/${TAG}_*.
+TAG=${1:-r02}
 mkdir -p gpurun_out
 P="python scripts/profile_step.py 3"
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'gemm_tc|bigru|decoder_kernel|maxpool|mask_rows|gather' \
-    --csv --log-file gpurun_out/launches.csv $P > gpurun_out/launches.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:decoder_kernel -s 2 -c 1 -f -o gpurun_out/prof_decoder $P > gpurun_out/prof_decoder.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:bigru_kernel -s 4 -c 2 -f -o gpurun_out/prof_gru $P > gpurun_out/prof_gru.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 53 -c 10 -f -o gpurun_out/prof_gemm $P > gpurun_out/prof_gemm.log 2>&1
-ls -la gpurun_out/
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${TAG}_launches.csv $P > gpurun_out/${TAG}_launches.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:decoder_kernel -s 2 -c 1 -f -o gpurun_out/${TAG}_prof_decoder $P > gpurun_out/${TAG}_prof_decoder.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:bigru_kernel -s 4 -c 2 -f -o gpurun_out/${TAG}_prof_gru $P > gpurun_out/${TAG}_prof_gru.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 53 -c 10 -f -o gpurun_out/${TAG}_prof_gemm $P > gpurun_out/${TAG}_prof_gemm.log 2>&1
+ls -la gpurun_out/${TAG}_*

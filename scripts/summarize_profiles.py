@@ -11,17 +11,20 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "profiles")
 GO = os.path.join(ROOT, "gpurun_out")
 os.makedirs(OUT, exist_ok=True)
-lines = [f"# {tag}: ncu summaries (B200, C2 inference step: B=32, Tx=128, T=200, r=5, precision tf32)\n"]
+lines = [f"# {tag}: ncu summaries (B200, C2 inference step: B=32, Tx=128, T=200, r=5, precision fp32x3 = 3xTF32 on tcgen05)\n"]
 
 # ---------------- launch list ----------------
-lp = os.path.join(GO, "launches.csv")
+lp = os.path.join(GO, f"{tag}_launches.csv")
+if not os.path.exists(lp):
+    lp = os.path.join(GO, "launches.csv")
 if os.path.exists(lp):
     rows = list(csv.reader(open(lp)))
     hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
     hdr, data = rows[hi], rows[hi + 1:]
     ki, vi, gi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size")
-    per = len(data) // 3
-    step = data[2 * per:]
+    gi_ = [i for i, r in enumerate(data) if "gather_rows" in r[ki]]
+    start = gi_[-1] - 1 if gi_ else 2 * (len(data) // 3)      # a step starts with the embedding-table GEMM + the row gather
+    step = data[start:]
     tot = sum(float(r[vi].replace(",", "")) for r in step)
     with open(os.path.join(OUT, f"{tag}_launches_step.csv"), "w") as f:
         f.write("kernel,grid,duration_us,share\n")
@@ -72,7 +75,9 @@ def stalls(rep, idx):
 
 
 for name in ("prof_decoder", "prof_gru", "prof_gemm"):
-    rep = os.path.join(GO, name + ".ncu-rep")
+    rep = os.path.join(GO, f"{tag}_{name}.ncu-rep")
+    if not os.path.exists(rep):
+        rep = os.path.join(GO, name + ".ncu-rep")
     if not os.path.exists(rep):
         continue
     hdr, units, data = raw(rep)

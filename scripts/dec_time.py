@@ -40,3 +40,7 @@ if os.environ.get("TACO_TRACE"):
         f = lambda a, b: int(c[a] - c[b]) if c[a] and c[b] else -1
         nxt = ck[st, i + 1, 3] if i + 1 < len(inames) else ck[st + 1, 0, 3]
         print(f"  {nm:8s} {f(0,3):6d} {f(1,0):6d} {f(2,1):6d} | {f(4,2):6d} {f(5,4):6d} {f(6,5):6d} | total {int(nxt - c[3]):6d}")
+    c = ck[1, 8]      # A|P2 stage record of step 11: attention on warp 0 / thread 0
+    if c[3]:
+        print("attention (cycles from slot start): q arrived+exp %d | bar1 %d | scores %d | bar2 %d | stats+bar3 %d | ctx partial+push %d | merged ctx stored %d"
+              % tuple(int(c[i] - c[3]) for i in (0, 1, 2, 4, 5, 6, 7)))

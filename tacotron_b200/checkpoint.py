@@ -88,3 +88,17 @@ def import_tf_variables(model, tf_vars):
             extra[name] = arr
     model.load_params(params)
     return extra
+
+
+def import_tf_checkpoint(model, prefix):
+    """``saver.restore(sess, prefix)`` for a checkpoint WRITTEN BY TENSORFLOW (V2 format: ``prefix.index`` +
+    ``prefix.data-0000N-of-0000M``; train.py:49-58, test.py:40-48, download_weights.sh:4): reads the bundle with
+    tacotron_b200/tf_checkpoint.py (no TensorFlow needed), maps the TF-1.2 variable names through tf_names.py and loads
+    them.  Returns the non-model variables (global_step, Adam slots, stft_mean / stft_std ...) like import_tf_variables;
+    ``global_step`` is applied to the model when present."""
+    from . import tf_checkpoint
+    tf_vars = tf_checkpoint.read_bundle(prefix)
+    extra = import_tf_variables(model, tf_vars)
+    if "global_step" in extra:
+        model.global_step = int(np.asarray(extra["global_step"]))
+    return extra

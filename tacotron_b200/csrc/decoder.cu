@@ -544,7 +544,9 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
             eq_s[k0] = exp2x(qq.x);
             eq_s[k0 + 4] = exp2x(qq.y);
         }
+        if (TR && cktr) cktr[0] = clock64();
         named_bar(1, 256);
+        if (TR && cktr) cktr[1] = clock64();
         {   // scores: lane owns 8 consecutive depth indices (its e^{2q}, v slices stay in registers), warp w owns
             // positions j = w, w+8, ...; four positions are reduced over the warp with one transposing butterfly
             float eq[8], vv[8];
@@ -596,7 +598,9 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
                 if ((lane & 7) == 0 && j < Tq) e_s[j] = ((int)aq * Tq + j < my_len) ? fmaf(-2.0f, b1, V0) : -INFINITY;
             }
         }
+        if (TR && cktr) cktr[2] = clock64();
         named_bar(1, 256);
+        if (TR && cktr) cktr[4] = clock64();
         // quarter statistics (every warp redundantly; Tq <= 64)
         const float e0 = (lane < Tq) ? e_s[lane] : -INFINITY;
         const float e1 = (lane + 32 < Tq) ? e_s[lane + 32] : -INFINITY;
@@ -617,6 +621,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
             dsm_store(xstat + (xp * 4 + aq) * 2 + 1, (uint32_t)tid, ssum, tag);
         }
         named_bar(1, 256);
+        if (TR && cktr) cktr[5] = clock64();
         {   // partial context: column tid; pushed to the CTA that owns it (64 columns per CTA)
             float c0 = 0.f, c1 = 0.f;
 #pragma unroll 4
@@ -627,6 +632,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
             if (Tq & 1) c0 = fmaf(p_s[Tq - 1], vals_s[(Tq - 1) * ENC + tid], c0);
             dsm_store(xbuf + (xp * 4 + aq) * 64 + (tid & 63), (uint32_t)tid >> 6, c0 + c1, tag);
         }
+        if (TR && cktr) cktr[6] = clock64();
         if (tid >= 128) return;
         // merge: global max / sum from the four quarter statistics
         float mq[4], wq[4], M = -INFINITY, S = 0.f, w_own = 0.f;
@@ -645,6 +651,7 @@ __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(NTHR, 1) decoder_ker
 #pragma unroll
             for (int qd = 0; qd < 4; ++qd) c = fmaf(wq[qd], sm_wait(xbuf + (xp * 4 + qd) * 64 + tid, tag), c);
             ll_store(ctx_out, c * inv, tag + 1);
+            if (TR && cktr) cktr[7] = clock64();
         } else {                                         // alignments of this quarter (AttentionWrapper alignment_history)
             const int j = tid - 64;
             if (j < Tq && (int)aq * Tq + j < Tx) A.align[((int64_t)arow * T + t) * Tx + aq * Tq + j] = p_s[j] * (w_own * inv);

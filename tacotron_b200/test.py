@@ -31,9 +31,17 @@ def test(model_cls, config, prompts, log=print):
     model = model_cls(config, None, train=False)                                         # :31
     log("restoring weights")                                                             # :41
     ck = checkpoint.latest_checkpoint(os.path.join("weights", config.save_path))         # :42-45
-    if ck is None:
-        raise FileNotFoundError(f"no checkpoint under weights/{config.save_path}")
-    stft_mean, stft_std = checkpoint.restore(model, ck)                                  # :46-48
+    if ck is not None:
+        stft_mean, stft_std = checkpoint.restore(model, ck)                              # :46-48
+    else:
+        # no checkpoint of ours: a checkpoint written by the reference itself (TensorFlow V2 format, e.g. the released
+        # Nancy weights of download_weights.sh) in the same directory is read directly
+        from . import tf_checkpoint
+        tf_ck = tf_checkpoint.latest_checkpoint(os.path.dirname(os.path.join("weights", config.save_path)))
+        if tf_ck is None:
+            raise FileNotFoundError(f"no checkpoint under weights/{config.save_path}")
+        extra = checkpoint.import_tf_checkpoint(model, tf_ck)
+        stft_mean, stft_std = extra["stft_mean"], extra["stft_std"]
     mean_d = torch.from_numpy(np.asarray(stft_mean, dtype=np.float32)).cuda()
     std_d = torch.from_numpy(np.asarray(stft_std, dtype=np.float32)).cuda()
     out_dir = os.path.join("log", config.save_path, "test")                              # :33

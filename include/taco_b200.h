@@ -290,6 +290,12 @@ int taco_gl_ola(float* y, const float* fr, int B, int n, int hop, int n_fft, int
 int taco_gl_frame(float* frw, const float* y, int B, int n, int hop, int n_fft, int win_length, void* stream);
 /* full = mag * rebuilt/|rebuilt|  (audio.py:84,87) over `count` complex elements */
 int taco_gl_phase(float* full_c64, const float* mag, const float* rebuilt_c64, int64_t count, void* stream);
+/* the two transforms of a Griffin-Lim iteration (librosa.istft / librosa.stft inside audio.griffinlim, audio.py:84-86),
+ * n_fft = 2048: X [rows][1025] complex (interleaved re, im) <-> x [rows][2048] real.  rfft is unnormalised, irfft scales
+ * by 1/2048 and ignores the imaginary parts of the DC and Nyquist bins (numpy / cuFFT conventions).  Shared-memory
+ * radix-2 Stockham transform, one CTA per row: no FFT library on the path.                                          */
+int taco_rfft2048(float* X_c64, const float* x, int64_t rows, void* stream);
+int taco_irfft2048(float* x, const float* X_c64, int64_t rows, void* stream);
 
 /* Input data format: spectrograms are stored float16 (preprocess.py:179-180) and normalised in
  * that dtype (data_input.py:56-64) before the float32 cast (:38-39).  Bit-exact device version of those statements:

@@ -101,7 +101,7 @@ EXPORTS = [
     "taco_dec_inputs", "taco_decoder_bwd_workspace_bytes", "taco_decoder_bwd", "taco_attn_bwd_post", "taco_sumsq",
     "taco_adam_step",
     # spectrogram inversion (Griffin-Lim glue kernels)
-    "taco_gl_init", "taco_gl_ola", "taco_gl_frame", "taco_gl_phase",
+    "taco_gl_init", "taco_gl_ola", "taco_gl_frame", "taco_gl_phase", "taco_rfft2048", "taco_irfft2048",
     # input data format
     "taco_normalize_f16",
 ]
@@ -161,6 +161,8 @@ def lib():
     L.taco_gl_ola.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
     L.taco_gl_frame.argtypes = [vp, vp, i32, i32, i32, i32, i32, vp]
     L.taco_gl_phase.argtypes = [vp, vp, vp, i64, vp]
+    L.taco_rfft2048.argtypes = [vp, vp, i64, vp]
+    L.taco_irfft2048.argtypes = [vp, vp, i64, vp]
     L.taco_normalize_f16.argtypes = [vp, vp, vp, vp, i64, i32, vp]
     for name in EXPORTS:                      # every declared symbol must resolve (AttributeError otherwise)
         getattr(L, name)

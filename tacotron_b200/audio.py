@@ -2,16 +2,16 @@
 (``reshape_frames`` :23-35, ``invert_spectrogram`` :67-75, ``griffinlim`` :77-97), SURVEY.md section 8(f) rank 1:
 it sits inside BASELINE config 5's end-to-end latency (test.py:64) and would dominate it on the CPU.
 
-Design: a batch of utterances stays on the device for all iterations.  The two FFTs per iteration are library calls
-(cuFFT through ``torch.fft`` -- "plain library FFTs", like cuBLAS for a plain GEMM); everything between them is four
-fused kernels of libtaco_b200.so (csrc/audio.cu):
+Design: a batch of utterances stays on the device for all iterations.  The two transforms per iteration are the library's
+own shared-memory FFT kernels (csrc/audio.cu ``taco_rfft2048`` / ``taco_irfft2048``: radix-2 Stockham, one CTA per frame --
+round 1 called cuFFT through ``torch.fft`` here); everything between them is four fused kernels of libtaco_b200.so:
 
     gl_init   reshape_frames(forward=False) + de-normalisation + exp + initial phase  ->  magnitude, first spectrum
     gl_ola    window, overlap-add, window-sum-square normalisation, centre trim        (the tail of librosa.istft)
     gl_frame  reflect padding, framing, window                                         (the head of librosa.stft)
     gl_phase  mag * rebuilt/|rebuilt|                                                  (audio.py:84,87)
 
-so one iteration is irfft -> gl_ola -> gl_frame -> rfft -> gl_phase: 5 launches, ~20 MB of HBM traffic per utterance of
+so one iteration is irfft2048 -> gl_ola -> gl_frame -> rfft2048 -> gl_phase: 5 launches of this library, ~20 MB of HBM traffic per utterance of
 500 frames.  All arithmetic goes through the kernel namespace K (tacotron_b200/kernels.py); tests run the same
 orchestration over tests/mirror_kernels.py on CPU tensors against the numpy oracle (oracle/audio_oracle.py).
 """
@@ -69,21 +69,24 @@ def griffinlim_batch(spec, r, n_iter=50, scale=None, shift=None, phase_u=None, K
     return y
 
 
-def _gl_iterations(K, full, mag, spec, phase_u, r, scale, shift, y, frw, n_iter):
+def _gl_iterations(K, full, mag, spec, phase_u, r, scale, shift, y, frw, n_iter, rebuilt=None):
+    """frw [B, n, 2048] doubles as the istft frame buffer: irfft writes it, gl_ola consumes it, gl_frame refills it."""
+    if rebuilt is None:
+        rebuilt = torch.empty_like(full)
     K.gl_init(full, mag, spec, phase_u, r, scale, shift)
     for it in range(n_iter + 1):
-        fr = torch.fft.irfft(full, n=n_fft, dim=-1).contiguous()             # cuFFT C2R, batch B*n
-        K.gl_ola(y, fr, hop_length, win_length)
+        K.irfft2048(frw, full)                                               # inverse real FFT of every frame
+        K.gl_ola(y, frw, hop_length, win_length)
         if it == n_iter:
             break
         K.gl_frame(frw, y, hop_length, win_length)
-        rebuilt = torch.fft.rfft(frw, dim=-1).contiguous()                   # cuFFT R2C
+        K.rfft2048(rebuilt, frw)                                             # real FFT of every re-framed, windowed frame
         K.gl_phase(full, mag, rebuilt)
 
 
 class GriffinLimGraph:
     """The same 5-launches-per-iteration loop captured ONCE into a CUDA graph for a fixed (B, T, r, n_iter) and replayed:
-    251 launches (and their Python / ctypes / cuFFT-plan overhead, ~0.1 ms per iteration of host time) collapse into one
+    251 launches (and their Python / ctypes overhead, ~0.1 ms per iteration of host time) collapse into one
     graph launch.  Inputs are copied into static device buffers; the result is the static `y` (valid until the next call).
     Opt-in: `invert_spectrogram(...)` stays eager."""
 
@@ -103,10 +106,11 @@ class GriffinLimGraph:
         self.full = torch.empty((B, n, F_BINS), dtype=torch.complex64, device=dev)
         self.y = torch.empty((B, L), **f32)
         self.frw = torch.empty((B, n, n_fft), **f32)
-        args = (K, self.full, self.mag, self.spec, self.phase_u, r, self.scale, self.shift, self.y, self.frw, n_iter)
+        self.rebuilt = torch.empty_like(self.full)
+        args = (K, self.full, self.mag, self.spec, self.phase_u, r, self.scale, self.shift, self.y, self.frw, n_iter, self.rebuilt)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):                     # warm-up outside capture: cuFFT plans, lazy module loads
+        with torch.cuda.stream(side):                     # warm-up outside capture: lazy module loads
             _gl_iterations(*args)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()

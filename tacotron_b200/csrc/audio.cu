@@ -1,4 +1,4 @@
-// audio.cu -- the fused steps of Griffin-Lim spectrogram inversion between the two library FFTs of an iteration
+// audio.cu -- Griffin-Lim spectrogram inversion: the fused steps between the two FFTs of an iteration, and the FFTs
 // (reference: audio.py:67-97 invert_spectrogram / griffinlim, audio.py:30-35 reshape_frames(forward=False);
 // librosa.stft / librosa.istft conventions as restated in oracle/audio_oracle.py).  SURVEY.md section 8(f) rank 1.
 //
@@ -100,6 +100,68 @@ __global__ void gl_phase_kernel(float2* __restrict__ full, const float* __restri
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 2048-point FFT in shared memory: radix-2 Stockham autosort (natural order in, natural order out, ping-pong buffers),
+// one CTA of 256 threads per row, four butterflies per thread and stage, twiddles exp(-2 pi i k / 2048) tabulated once per
+// CTA with sincospi.  The real transforms run as a complex transform of the zero-extended / Hermitian-completed row
+// (twice the minimum arithmetic, all of it on-chip: a Griffin-Lim iteration moves ~20 MB through HBM either way).
+//   INV = false: in = x [rows][2048] real,       out = X [rows][1025] complex (unnormalised)
+//   INV = true : in = X [rows][1025] complex,    out = x [rows][2048] real, scaled by 1/2048
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int FN = 2048;
+template <bool INV>
+__global__ void __launch_bounds__(256) fft2048_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t rows) {
+    __shared__ float2 buf_a[FN];
+    __shared__ float2 buf_b[FN];
+    __shared__ float2 tw[FN / 2];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < FN / 2; i += 256) {
+        float sn, cs;
+        sincospif(-(float)i / (float)(FN / 2), &sn, &cs);       // exp(-2 pi i k / 2048)
+        tw[i] = make_float2(cs, INV ? -sn : sn);
+    }
+    for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+        if (!INV) {
+            const float* x = in + row * FN;
+            for (int i = tid; i < FN; i += 256) buf_a[i] = make_float2(x[i], 0.f);
+        } else {
+            const float2* X = reinterpret_cast<const float2*>(in) + row * (FN / 2 + 1);
+            for (int k = tid; k <= FN / 2; k += 256) {
+                float2 v = X[k];
+                if (k == 0 || k == FN / 2) v.y = 0.f;              // a real signal has real DC / Nyquist bins
+                buf_a[k] = v;
+                if (k > 0 && k < FN / 2) buf_a[FN - k] = make_float2(v.x, -v.y);
+            }
+        }
+        __syncthreads();
+        float2* src = buf_a;
+        float2* dst = buf_b;
+        for (int Ns = 1; Ns < FN; Ns <<= 1) {
+            const int tstride = (FN / 2) / Ns;
+            for (int j = tid; j < FN / 2; j += 256) {
+                const int k = j & (Ns - 1);
+                const float2 w = tw[k * tstride];
+                const float2 v0 = src[j], u = src[j + FN / 2];
+                const float2 v1 = make_float2(u.x * w.x - u.y * w.y, u.x * w.y + u.y * w.x);
+                const int j0 = ((j - k) << 1) + k;
+                dst[j0] = make_float2(v0.x + v1.x, v0.y + v1.y);
+                dst[j0 + Ns] = make_float2(v0.x - v1.x, v0.y - v1.y);
+            }
+            __syncthreads();
+            float2* t = src; src = dst; dst = t;
+        }
+        if (!INV) {
+            float2* X = reinterpret_cast<float2*>(out) + row * (FN / 2 + 1);
+            for (int k = tid; k <= FN / 2; k += 256) X[k] = src[k];
+        } else {
+            float* x = out + row * FN;
+            for (int i = tid; i < FN; i += 256) x[i] = src[i].x * (1.0f / FN);
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -143,6 +205,26 @@ int taco_gl_phase(float* full_c64, const float* mag, const float* rebuilt_c64, i
     if (count == 0) return 0;
     TACO_LAUNCH(gl_phase_kernel, grid_for(count, 256), 256, 0, (cudaStream_t)stream, reinterpret_cast<float2*>(full_c64), mag,
                                                                             reinterpret_cast<const float2*>(rebuilt_c64), count);
+    TACO_LAUNCH_CHECK();
+    return 0;
+}
+
+// real FFT / inverse real FFT of length 2048 over `rows` contiguous rows: x [rows][2048] -> X [rows][1025] complex
+// (interleaved re, im; unnormalised, like numpy / torch rfft) and X -> x (scaled by 1/2048, imaginary parts of the DC
+// and Nyquist bins ignored, like irfft).  Replaces the two cuFFT calls of a Griffin-Lim iteration (audio.py:84-86).
+int taco_rfft2048(float* X_c64, const float* x, int64_t rows, void* stream) {
+    TACO_CHECK(X_c64 && x && rows >= 0, "taco_rfft2048: bad arguments");
+    if (rows == 0) return 0;
+    const int grid = (int)(rows < 148 * 4 ? rows : 148 * 4);
+    TACO_LAUNCH(fft2048_kernel<false>, grid, 256, 0, (cudaStream_t)stream, x, X_c64, rows);
+    TACO_LAUNCH_CHECK();
+    return 0;
+}
+int taco_irfft2048(float* x, const float* X_c64, int64_t rows, void* stream) {
+    TACO_CHECK(X_c64 && x && rows >= 0, "taco_irfft2048: bad arguments");
+    if (rows == 0) return 0;
+    const int grid = (int)(rows < 148 * 4 ? rows : 148 * 4);
+    TACO_LAUNCH(fft2048_kernel<true>, grid, 256, 0, (cudaStream_t)stream, X_c64, x, rows);
     TACO_LAUNCH_CHECK();
     return 0;
 }

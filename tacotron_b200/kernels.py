@@ -268,6 +268,22 @@ def gl_phase(full, mag, rebuilt):
     L.check(L.lib().taco_gl_phase(_p(full), _p(mag), _p(rebuilt), mag.numel(), _st()), "taco_gl_phase")
 
 
+def rfft2048(X, x):
+    """X complex64 [..., 1025] = rfft(x fp32 [..., 2048]) over the last axis (unnormalised) -- librosa.stft's transform"""
+    _f32c(X, "rfft2048 X"); _f32c(x, "rfft2048 x")
+    assert X.dtype == torch.complex64 and x.dtype == torch.float32 and x.shape[-1] == 2048 and X.shape[-1] == 1025
+    assert X.numel() // 1025 == x.numel() // 2048
+    L.check(L.lib().taco_rfft2048(_p(X), _p(x), x.numel() // 2048, _st()), "taco_rfft2048")
+
+
+def irfft2048(x, X):
+    """x fp32 [..., 2048] = irfft(X complex64 [..., 1025], n=2048) over the last axis (1/n scaling) -- librosa.istft's transform"""
+    _f32c(X, "irfft2048 X"); _f32c(x, "irfft2048 x")
+    assert X.dtype == torch.complex64 and x.dtype == torch.float32 and x.shape[-1] == 2048 and X.shape[-1] == 1025
+    assert X.numel() // 1025 == x.numel() // 2048
+    L.check(L.lib().taco_irfft2048(_p(x), _p(X), x.numel() // 2048, _st()), "taco_irfft2048")
+
+
 def normalize_f16(out, x, mean, std):
     """out fp32 [..., W] = the reference's in-place float16 normalisation of x (float16) followed by the float32 cast"""
     W = x.shape[-1]

@@ -400,6 +400,16 @@ def normalize_f16(out, x, mean, std):
     out.copy_((d.float() / std).half().float())
 
 
+def rfft2048(X, x):
+    """X = rfft(x) over the last axis (unnormalised)"""
+    X.copy_(torch.fft.rfft(x, dim=-1))
+
+
+def irfft2048(x, X):
+    """x = irfft(X, n=2048) over the last axis"""
+    x.copy_(torch.fft.irfft(X, n=2048, dim=-1))
+
+
 def gl_phase(full, mag, rebuilt):
     """full = mag * exp(i angle(rebuilt))   (audio.py:84,87; angle(0) = 0)"""
     a = rebuilt.abs()

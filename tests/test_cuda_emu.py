@@ -188,6 +188,24 @@ def test_decoder_bwd_kernel_under_emulation(emu, r, sched):
             assert (got - ref).abs().max().item() <= 2e-5 * (ref.abs().max().item() + 1e-6), (k, i)
 
 
+def test_fft2048_kernels_under_emulation(emu):
+    """the shared-memory Stockham FFT pair of the Griffin-Lim loop (csrc/audio.cu) against torch.fft"""
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(3, 2048, generator=g)
+    X = torch.empty(3, 1025, dtype=torch.complex64)
+    emu.taco_rfft2048.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    emu.taco_irfft2048.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    assert emu.taco_rfft2048(_p(X), _p(x), 3, None) == 0, emu.taco_last_error().decode()
+    ref = torch.fft.rfft(x.double(), dim=-1)
+    assert (X.to(torch.complex128) - ref).abs().max().item() <= 2e-6 * ref.abs().max().item()
+    Y = torch.randn(3, 1025, generator=g) + 1j * torch.randn(3, 1025, generator=g)
+    Y = Y.to(torch.complex64).contiguous()
+    y = torch.empty(3, 2048)
+    assert emu.taco_irfft2048(_p(y), _p(Y), 3, None) == 0, emu.taco_last_error().decode()
+    refy = torch.fft.irfft(Y.to(torch.complex128), n=2048, dim=-1)
+    assert (y.double() - refy).abs().max().item() <= 2e-6 * refy.abs().max().item()
+
+
 def test_bigru_bwd_kernel_under_emulation(emu):
     """the register-resident bi-GRU BPTT kernel (green on hardware): 512-thread CTAs, butterfly shuffles"""
     g = torch.Generator().manual_seed(3)

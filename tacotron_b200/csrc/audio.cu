@@ -102,61 +102,88 @@ __global__ void gl_phase_kernel(float2* __restrict__ full, const float* __restri
 
 
 // ---------------------------------------------------------------------------------------------------------------------
-// 2048-point FFT in shared memory: radix-2 Stockham autosort (natural order in, natural order out, ping-pong buffers),
-// one CTA of 256 threads per row, four butterflies per thread and stage, twiddles exp(-2 pi i k / 2048) tabulated once per
-// CTA with sincospi.  The real transforms run as a complex transform of the zero-extended / Hermitian-completed row
-// (twice the minimum arithmetic, all of it on-chip: a Griffin-Lim iteration moves ~20 MB through HBM either way).
+// 2048-point REAL FFT pair in shared memory.  The real row is transformed as a 1024-point COMPLEX sequence
+// z[n] = x[2n] + i x[2n+1] (half the arithmetic), with a radix-4 Stockham autosort FFT: 1024 = 4^5, so a CTA of 256
+// threads does exactly one radix-4 butterfly per thread and stage, five stages, natural order in and out, ping-pong
+// buffers; the twiddles exp(-2 pi i t / 1024) are tabulated once per CTA with sincospi.  A pre / post pass converts between
+// Z = FFT(z) and the 1025 bins of the real transform:
+//   rfft : X[k] = E[k] + w^k O[k],  E = (Z[k] + conj Z[M-k]) / 2,  O = (Z[k] - conj Z[M-k]) / 2i,  w = exp(-2 pi i / 2048)
+//   irfft: Z[k] = E[k] + i w^-k O'[k],  E = (X[k] + conj X[M-k]) / 2,  O' = (X[k] - conj X[M-k]) / 2;  x = IFFT(Z) / 1024
 //   INV = false: in = x [rows][2048] real,       out = X [rows][1025] complex (unnormalised)
-//   INV = true : in = X [rows][1025] complex,    out = x [rows][2048] real, scaled by 1/2048
+//   INV = true : in = X [rows][1025] complex,    out = x [rows][2048] real  (1/n scaling; imaginary parts of DC / Nyquist ignored)
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int FN = 2048;
+constexpr int FN = 2048, FM = FN / 2;
+__device__ __forceinline__ float2 cmul(const float2 a, const float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+
 template <bool INV>
 __global__ void __launch_bounds__(256) fft2048_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t rows) {
-    __shared__ float2 buf_a[FN];
-    __shared__ float2 buf_b[FN];
-    __shared__ float2 tw[FN / 2];
+    __shared__ float2 buf_a[FM];
+    __shared__ float2 buf_b[FM];
+    __shared__ float2 tw[FM];          // exp(-+ 2 pi i t / 1024)
     const int tid = threadIdx.x;
-    for (int i = tid; i < FN / 2; i += 256) {
+    for (int i = tid; i < FM; i += 256) {
         float sn, cs;
-        sincospif(-(float)i / (float)(FN / 2), &sn, &cs);       // exp(-2 pi i k / 2048)
+        sincospif(-2.0f * (float)i / (float)FM, &sn, &cs);
         tw[i] = make_float2(cs, INV ? -sn : sn);
     }
     for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+        // ---- load (+ pre-pass of the inverse transform) ----
         if (!INV) {
-            const float* x = in + row * FN;
-            for (int i = tid; i < FN; i += 256) buf_a[i] = make_float2(x[i], 0.f);
+            const float2* x2 = reinterpret_cast<const float2*>(in + row * FN);     // (x[2n], x[2n+1]) = z[n]
+            for (int i = tid; i < FM; i += 256) buf_a[i] = x2[i];
         } else {
-            const float2* X = reinterpret_cast<const float2*>(in) + row * (FN / 2 + 1);
-            for (int k = tid; k <= FN / 2; k += 256) {
-                float2 v = X[k];
-                if (k == 0 || k == FN / 2) v.y = 0.f;              // a real signal has real DC / Nyquist bins
-                buf_a[k] = v;
-                if (k > 0 && k < FN / 2) buf_a[FN - k] = make_float2(v.x, -v.y);
+            const float2* X = reinterpret_cast<const float2*>(in) + row * (FM + 1);
+            for (int k = tid; k < FM; k += 256) {
+                float2 xk = X[k], xm = X[FM - k];
+                if (k == 0) { xk.y = 0.f; xm.y = 0.f; }                   // DC and Nyquist bins of a real signal are real
+                const float2 e = make_float2(0.5f * (xk.x + xm.x), 0.5f * (xk.y - xm.y));          // (X[k] + conj X[M-k]) / 2
+                const float2 o = make_float2(0.5f * (xk.x - xm.x), 0.5f * (xk.y + xm.y));          // (X[k] - conj X[M-k]) / 2
+                float sn, cs;
+                sincospif((float)k / (float)FM, &sn, &cs);                // w^-k = exp(+2 pi i k / 2048)
+                const float2 ow = cmul(o, make_float2(cs, sn));
+                buf_a[k] = make_float2(e.x - ow.y, e.y + ow.x);            // E + i * (w^-k O')
             }
         }
         __syncthreads();
+        // ---- five radix-4 Stockham stages ----
         float2* src = buf_a;
         float2* dst = buf_b;
-        for (int Ns = 1; Ns < FN; Ns <<= 1) {
-            const int tstride = (FN / 2) / Ns;
-            for (int j = tid; j < FN / 2; j += 256) {
-                const int k = j & (Ns - 1);
-                const float2 w = tw[k * tstride];
-                const float2 v0 = src[j], u = src[j + FN / 2];
-                const float2 v1 = make_float2(u.x * w.x - u.y * w.y, u.x * w.y + u.y * w.x);
-                const int j0 = ((j - k) << 1) + k;
-                dst[j0] = make_float2(v0.x + v1.x, v0.y + v1.y);
-                dst[j0 + Ns] = make_float2(v0.x - v1.x, v0.y - v1.y);
-            }
+#pragma unroll
+        for (int Ns = 1; Ns < FM; Ns <<= 2) {
+            const int j = tid;                                             // FM / 4 = 256 butterflies
+            const int k = j & (Ns - 1);
+            const int ts = k * (FM / (4 * Ns));
+            const float2 v0 = src[j];
+            const float2 v1 = cmul(src[j + FM / 4], tw[ts]);
+            const float2 v2 = cmul(src[j + 2 * (FM / 4)], tw[2 * ts]);
+            const float2 v3 = cmul(src[j + 3 * (FM / 4)], tw[3 * ts]);
+            const float2 a0 = make_float2(v0.x + v2.x, v0.y + v2.y), a1 = make_float2(v0.x - v2.x, v0.y - v2.y);
+            const float2 a2 = make_float2(v1.x + v3.x, v1.y + v3.y);
+            const float2 d = make_float2(v1.x - v3.x, v1.y - v3.y);
+            const float2 a3 = INV ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);              // (v1 - v3) * (+-i)
+            const int j0 = ((j - k) << 2) + k;
+            dst[j0] = make_float2(a0.x + a2.x, a0.y + a2.y);
+            dst[j0 + Ns] = make_float2(a1.x + a3.x, a1.y + a3.y);
+            dst[j0 + 2 * Ns] = make_float2(a0.x - a2.x, a0.y - a2.y);
+            dst[j0 + 3 * Ns] = make_float2(a1.x - a3.x, a1.y - a3.y);
             __syncthreads();
             float2* t = src; src = dst; dst = t;
         }
+        // ---- store (+ post-pass of the forward transform) ----
         if (!INV) {
-            float2* X = reinterpret_cast<float2*>(out) + row * (FN / 2 + 1);
-            for (int k = tid; k <= FN / 2; k += 256) X[k] = src[k];
+            float2* X = reinterpret_cast<float2*>(out) + row * (FM + 1);
+            for (int k = tid; k <= FM; k += 256) {
+                const float2 zk = src[k & (FM - 1)], zm = src[(FM - k) & (FM - 1)];
+                const float2 e = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));          // (Z[k] + conj Z[M-k]) / 2
+                const float2 o = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));         // (Z[k] - conj Z[M-k]) / 2i
+                float sn, cs;
+                sincospif(-(float)k / (float)FM, &sn, &cs);               // w^k = exp(-2 pi i k / 2048)
+                const float2 ow = cmul(o, make_float2(cs, sn));
+                X[k] = make_float2(e.x + ow.x, e.y + ow.y);
+            }
         } else {
-            float* x = out + row * FN;
-            for (int i = tid; i < FN; i += 256) x[i] = src[i].x * (1.0f / FN);
+            float2* x2 = reinterpret_cast<float2*>(out + row * FN);
+            for (int i = tid; i < FM; i += 256) x2[i] = make_float2(src[i].x * (1.0f / FM), src[i].y * (1.0f / FM));
         }
         __syncthreads();
     }

@@ -131,7 +131,9 @@ int taco_bigru_fwd(const float* xp, const float* Wg_h_fw, const float* Wc_h_fw,
  * Decoder: tacotron.py:46-105 create_decoder + :136-138 dynamic_decode, i.e. per step
  *   pre_net(last frame) ++ attention -> InputProjection -> 3x GRUCell(256) -> Residual ->
  *   OutputProjection(80r) -> BahdanauAttention(query = cell output) -> attention layer.
- * The whole T-step loop runs in ONE persistent cooperative kernel.
+ * The whole T-step loop runs in ONE persistent kernel: 128 co-resident CTAs in clusters of 4, activations exchanged as
+ * {value, step tag} words through L2, weights resident in shared + tensor memory (csrc/decoder.cu).  Tx in [1,256], any
+ * width (the four attention quarters are ragged when Tx % 4 != 0); B <= 32 per launch; 80 r <= 512.
  * ------------------------------------------------------------------------------------------ */
 typedef struct taco_decoder_weights {   /* all TF layout, device pointers */
     const float *pre_W1, *pre_b1, *pre_W2, *pre_b2;      /* [80][256],[256],[256][128],[128]   */

@@ -146,6 +146,10 @@ def test_tf32_vs_fp32_paths_agree_at_full_size():
     torch.cuda.synchronize()
     err3 = float((a - c).abs().max() / a.abs().max())
     assert err3 < 5e-5, err3       # (both sides carry fp32 accumulation rounding over K = 3072; 2.6e-5 measured)
+    # power-of-two scaling commutes exactly with the hi / lo split as well
+    c2 = ops.linear(rt3, x * 2, W, _pack(ops, rt3, W, 3, 1024, 256), 256, taps=3, tag="lin3b")
+    torch.cuda.synchronize()
+    assert torch.equal(c2, c * 2)
 
 
 def test_small_kernels():

@@ -10,7 +10,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
-from tacotron_b200 import kernels as K  # noqa: E402
+from tacotron_b200 import _lib as L, kernels as K  # noqa: E402
 from tacotron_b200.models import grad, ops  # noqa: E402
 from tacotron_b200.models.tacotron import Config, Tacotron  # noqa: E402
 
@@ -46,9 +46,12 @@ class TimedK:
 
 
 def main():
-    if os.environ.get("TACO_GEMM_IMPL") == "1":
-        K.set_gemm_impl(1)                     # time the opt-in 3xTF32 mma.sync GEMM instead of the FFMA default
-    cfg = Config(r=5, vocab_size=64, precision=os.environ.get("PRECISION", "tf32"))
+    precision = os.environ.get("PRECISION", "fp32x3")
+    cfg = Config(r=5, vocab_size=64, precision=precision)
+    # the kernel routes Tacotron.backward() selects for this precision (models/tacotron.py backward())
+    K.set_gemm_impl(int(os.environ.get("TACO_GEMM_IMPL", "0" if precision == "fp32" else "1")))
+    K.DX_TC = precision != "fp32"
+    K.DX_TC_IMPL = L.IMPL_TC if precision == "tf32" else L.IMPL_TC3
     m = Tacotron(cfg, None, train=True)
     g = torch.Generator().manual_seed(0)
     gi = {"text": torch.randint(1, 64, (32, 128), generator=g, dtype=torch.int32).cuda(),

@@ -19,9 +19,14 @@
 //    main loop without a persistent scheduler.
 //  * X3 = true (TACO_IMPL_TC3, precision 'fp32x3'): error-compensated 3xTF32 -- fp32-grade products on
 //    the tensor cores.  Weights arrive pre-split (hi = TF32 head, lo = remainder: taco_pack_weight_x3),
-//    the activation tile is split IN SHARED MEMORY by the four otherwise idle epilogue warps (hi
-//    overwrites the tile, lo goes to a twin tile with the same swizzle), and every k-step issues
-//    lo.hi + hi.lo + hi.hi into the same TMEM accumulator.
+//    the activation tile is split by the four otherwise idle epilogue warps INTO TENSOR MEMORY (lane = tile
+//    row, 32 columns hi + 32 columns lo per stage) and every k-step issues lo.hi + hi.lo + hi.hi into the same
+//    TMEM accumulator with the A operand read from TMEM.  Why TMEM: with both operands in shared memory a
+//    128x128x8 TF32 MMA reads 8 KB per 64 cycles = the SM's whole 128 B/clk of shared-memory bandwidth, and
+//    the TMA writes + the in-smem split of the previous version (another 96 KB per k-block) made every k-block
+//    take ~1500 cycles instead of the 768 the tensor pipe needs (profiles/r02_ncu_summary.md: tensor pipe 34-57 %
+//    active).  A in TMEM halves the MMA's shared-memory reads and removes the split's writes; the stage shrinks
+//    to 48 KB, so two CTAs share an SM again and one CTA's epilogue overlaps the other's main loop.
 #include <cuda.h>
 #include "epilogue.cuh"
 
@@ -49,7 +54,12 @@ struct TcArgs {
 template <int BN, int STAGES, bool X3 = false>
 struct SmemLayout {
     static constexpr int B_STAGE_BYTES = BN * TC_BK * 4;
-    static constexpr int STAGE_BYTES = (X3 ? 2 : 1) * (A_STAGE_BYTES + B_STAGE_BYTES);   // X3: A | A_lo | B_hi | B_lo
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + (X3 ? 2 : 1) * B_STAGE_BYTES;     // X3: A (raw fp32) | B_hi | B_lo
+    static constexpr int ACC_COLS = (BN <= 32) ? 32 : (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;   // TMEM accumulator columns
+    static constexpr int A_COLS = X3 ? 2 * TC_BK : 0;                 // X3: per stage 32 columns A_hi + 32 columns A_lo in TMEM
+    static constexpr int NEED_COLS = ACC_COLS + STAGES * A_COLS;
+    static constexpr int TMEM_COLS = NEED_COLS <= 32 ? 32 : NEED_COLS <= 64 ? 64 : NEED_COLS <= 128 ? 128 : NEED_COLS <= 256 ? 256 : 512;
+    static_assert(NEED_COLS <= 512, "tensor memory: accumulator + A stages exceed 512 columns");
     static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
     static constexpr int BAR_OFFSET = PIPE_BYTES;
     static constexpr int CONST_OFFSET = PIPE_BYTES + 128;   // direct epilogue: bias[256] | scale[256] | shift[256] | first rows [4][32]
@@ -119,7 +129,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         mbar_fence_init();
     }
     if (warp == 1) {
-        constexpr uint32_t cols = (BN <= 32) ? 32 : (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
+        constexpr uint32_t cols = L::TMEM_COLS;
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(cols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -137,7 +147,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(&empty_bar[s], ph ^ 1);
                 uint8_t* As = smem + s * L::STAGE_BYTES;
-                uint8_t* Bs = As + (X3 ? 2 : 1) * A_STAGE_BYTES;
+                uint8_t* Bs = As + A_STAGE_BYTES;
                 const int j = it / a.cchunks;
                 const int c0 = (it - j * a.cchunks) * TC_BK;
                 mbar_arrive_expect_tx(&full_bar[s], A_STAGE_BYTES + (X3 ? 2 : 1) * L::B_STAGE_BYTES);
@@ -157,16 +167,16 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                 tc_fence_after();
                 const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
                 const uint64_t adesc = make_smem_desc(a_addr);
-                const uint64_t bdesc = make_smem_desc(a_addr + (X3 ? 2 : 1) * A_STAGE_BYTES);
+                const uint64_t bdesc = make_smem_desc(a_addr + A_STAGE_BYTES);
+                const uint64_t blo = make_smem_desc(a_addr + A_STAGE_BYTES + L::B_STAGE_BYTES);
+                const uint32_t a_hi = tmem_base + (uint32_t)(L::ACC_COLS + s * L::A_COLS);      // X3: A operand in TMEM
 #pragma unroll
                 for (int k = 0; k < TC_BK / 8; ++k) {
-                    // advance 8 tf32 = 32 bytes along K inside the swizzle atom: +2 in 16-byte units
+                    // advance 8 tf32 along K: +32 bytes inside the swizzle atom (+2 in 16-byte units) / +8 TMEM columns
                     if (X3) {
-                        const uint64_t alo = make_smem_desc(a_addr + A_STAGE_BYTES) + (uint64_t)(2 * k);
-                        const uint64_t blo = make_smem_desc(a_addr + 2 * A_STAGE_BYTES + L::B_STAGE_BYTES) + (uint64_t)(2 * k);
-                        tc_mma_tf32(tmem_base, alo, bdesc + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);     // lo . hi
-                        tc_mma_tf32(tmem_base, adesc + (uint64_t)(2 * k), blo, idesc, 1u);                               // hi . lo
-                        tc_mma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, 1u);         // hi . hi
+                        tc_mma_tf32_ta(tmem_base, a_hi + TC_BK + 8 * k, bdesc + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);   // lo . hi
+                        tc_mma_tf32_ta(tmem_base, a_hi + 8 * k, blo + (uint64_t)(2 * k), idesc, 1u);                                      // hi . lo
+                        tc_mma_tf32_ta(tmem_base, a_hi + 8 * k, bdesc + (uint64_t)(2 * k), idesc, 1u);                                    // hi . hi
                     } else {
                         tc_mma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc,
                                     (it > 0 || k > 0) ? 1u : 0u);
@@ -181,29 +191,40 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
         if (X3) {
             // ---- during the main loop these 128 threads split each landed activation tile: x = hi + lo with hi = the
-            //      nearest TF32 value (written back in place so that the result does not depend on how the tensor core
-            //      narrows fp32) and lo = the exact remainder, itself rounded to TF32 ----
-            const int ct = threadIdx.x - 64;
+            //      nearest TF32 value (so that the result does not depend on how the tensor core narrows fp32) and lo = the
+            //      exact remainder, itself rounded to TF32.  Lane = tile row = TMEM lane: the lane reads its 128-byte row out
+            //      of the swizzled tile (8 lanes of a quarter-warp phase hit 8 different 16-byte chunks: conflict-free) and
+            //      stores hi / lo into this stage's 64 TMEM columns ----
+            const int row = q * 32 + lane;
+            const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)L::ACC_COLS;
             for (int it = 0; it < n_iters; ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(&full_bar[s], ph);
-                float4* A4 = reinterpret_cast<float4*>(smem + s * L::STAGE_BYTES);
-                float4* L4 = reinterpret_cast<float4*>(smem + s * L::STAGE_BYTES + A_STAGE_BYTES);
+                const uint8_t* arow = smem + s * L::STAGE_BYTES + row * 128;
+                const uint32_t ta = lane_taddr + (uint32_t)(s * L::A_COLS);
 #pragma unroll
-                for (int c = 0; c < A_STAGE_BYTES / 16 / 128; ++c) {
-                    const float4 x = A4[ct + c * 128];
-                    float4 h, l;
-                    // round to nearest (ties away) by integer arithmetic on the bit pattern: truncation would bias every
-                    // term the same way and the bias grows linearly with K (1.6e-5 of max|ref| at K = 3072, measured)
-                    h.x = rn_tf32(x.x); l.x = rn_tf32(x.x - h.x);
-                    h.y = rn_tf32(x.y); l.y = rn_tf32(x.y - h.y);
-                    h.z = rn_tf32(x.z); l.z = rn_tf32(x.z - h.z);
-                    h.w = rn_tf32(x.w); l.w = rn_tf32(x.w - h.w);
-                    A4[ct + c * 128] = h;
-                    L4[ct + c * 128] = l;
+                for (int hf = 0; hf < 2; ++hf) {
+                    uint32_t h[16], l[16];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const int chunk = hf * 4 + c;
+                        const float4 x = *reinterpret_cast<const float4*>(arow + ((chunk ^ (row & 7)) << 4));
+                        // round to nearest (ties away) by integer arithmetic on the bit pattern: truncation would bias every
+                        // term the same way and the bias grows linearly with K (1.6e-5 of max|ref| at K = 3072, measured)
+                        const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float hv = rn_tf32(xs[e]);
+                            h[c * 4 + e] = __float_as_uint(hv);
+                            l[c * 4 + e] = __float_as_uint(rn_tf32(xs[e] - hv));
+                        }
+                    }
+                    tc_st_32x32b_x16(ta + (uint32_t)(hf * 16), h);
+                    tc_st_32x32b_x16(ta + (uint32_t)(TC_BK + hf * 16), l);
                 }
-                fence_proxy_async();                   // generic-proxy writes -> visible to the tensor core's async-proxy reads
+                tc_wait_st();
+                tc_fence_before();                     // TMEM stores ordered before the arrive the MMA thread waits on
                 mbar_arrive(&conv_bar[s]);
             }
         }
@@ -447,7 +468,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        constexpr uint32_t cols = (BN <= 32) ? 32 : (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
+        constexpr uint32_t cols = L::TMEM_COLS;
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(cols) : "memory");
     }
 }
@@ -618,7 +639,11 @@ int taco_linear_tc(const taco_linear_desc* d, cudaStream_t st) {
     dim3 grid((d->N + BN - 1) / BN, (unsigned)(a.tiles_per_seq * d->B));
     if (x3) {
         if (highway) return launch_tc<256, 2, 1, true>(tmA, tmB, a, grid, st);
-        return launch_tc<128, 3, 0, true>(tmA, tmB, a, grid, st);
+        // 2 stages x 48 KB + 256 TMEM columns per CTA: two CTAs per SM (4 loads in flight per SM, epilogue of one under the
+        // main loop of the other).  TACO_TC3_STAGES=4 (debug): one CTA per SM with a 4-deep ring.
+        static const int deep = [] { const char* e = getenv("TACO_TC3_STAGES"); return (e && atoi(e) == 4) ? 1 : 0; }();
+        if (deep) return launch_tc<128, 4, 0, true>(tmA, tmB, a, grid, st);
+        return launch_tc<128, 2, 0, true>(tmA, tmB, a, grid, st);
     }
     if (highway) return launch_tc<256, 2, 1>(tmA, tmB, a, grid, st);
     // short K loops (<= 8 k-iterations: dense 128/256-wide inputs) are epilogue/latency bound: a 2-stage ring (64 KB)

@@ -582,7 +582,7 @@ int taco_linear_tc(const taco_linear_desc* d, cudaStream_t st) {
     if (M == 0 || d->N == 0) return 0;
 
     const bool highway = d->epilogue == TACO_EPI_HIGHWAY;
-    const int BN = highway ? 256 : 128;
+    int BN = highway ? 256 : 128;
     if (highway) TACO_CHECK(d->N == 256 && d->taps == 1 && d->bank_K == 0 && d->hx, "highway (TC): needs N == 256 (U = 128), dense, hx");
     if (d->bank_K > 0) TACO_CHECK(d->bank_cout == 128 && d->N == d->bank_K * 128, "bank (TC): bank_cout must be 128");
     if (d->pool) TACO_CHECK(!highway && !d->residual && !d->keep, "pool cannot be combined with highway / residual / dropout");
@@ -595,6 +595,13 @@ int taco_linear_tc(const taco_linear_desc* d, cudaStream_t st) {
     a.N = d->N;
     a.pool = d->pool ? 1 : 0;
     const bool x3 = d->impl == TACO_IMPL_TC3;
+    // few output tiles (encoder-side contractions: 32 utterances x 128 characters = 32 m-tiles): 32-column n-tiles put
+    // four times as many CTAs on the machine, each with a 6-deep ring (the long-K conv projection 2048x3 -> 128 ran on
+    // 32 of 148 SMs with a 2-deep ring: 187 us)
+    {
+        const int64_t mt = (int64_t)((d->T + TC_BM - 1) / TC_BM) * d->B;
+        if (x3 && !highway && d->bank_K == 0 && !d->pool && mt * ((d->N + 127) / 128) <= 37 && d->N >= 64) BN = 32;
+    }
     // register-direct epilogue: needs 16-byte aligned row segments everywhere it touches
     {
         const int nout = highway ? d->N / 2 : d->N;
@@ -639,6 +646,7 @@ int taco_linear_tc(const taco_linear_desc* d, cudaStream_t st) {
     dim3 grid((d->N + BN - 1) / BN, (unsigned)(a.tiles_per_seq * d->B));
     if (x3) {
         if (highway) return launch_tc<256, 2, 1, true>(tmA, tmB, a, grid, st);
+        if (BN == 32) return launch_tc<32, 6, 0, true>(tmA, tmB, a, grid, st);
         // 2 stages x 48 KB + 256 TMEM columns per CTA: two CTAs per SM (4 loads in flight per SM, epilogue of one under the
         // main loop of the other).  TACO_TC3_STAGES=4 (debug): one CTA per SM with a 4-deep ring.
         static const int deep = [] { const char* e = getenv("TACO_TC3_STAGES"); return (e && atoi(e) == 4) ? 1 : 0; }();

@@ -213,6 +213,13 @@ int taco_gemm(const taco_gemm_desc* d, void* stream);
 /* which kernel taco_gemm launches: 0 = exact-product FFMA (default), 1 = 3xTF32 mma.sync tensor cores (fp32-grade,
  * ~1e-6 relative; opt-in until it has had a hardware run).  Returns the previous setting. */
 int taco_set_gemm_impl(int impl);
+/* Weight gradient of tf.layers.conv1d('same') / tf.layers.dense on the tcgen05 tensor cores (error-compensated 3xTF32,
+ * fp32-grade; models/ops.py:54,80, tacotron.py:40,42,148 under tf.gradients, tacotron.py:170):
+ *     dW[j*tap_stride + c*ldw + n] += sum_{b<B, t<T} X[(b*T + t + tap0 + j)*ldx + c] * dZ[(b*T + t)*lddz + n]
+ * for j < taps, c < C, n < N; rows outside [0,T) of an utterance read as zero (the 'same' padding).  Accumulates into dW
+ * (split-K with atomic adds, like taco_gemm's ta=1 path).  X, dZ 16-byte aligned, ldx and lddz multiples of 4 floats. */
+int taco_conv_dw(float* dW, int64_t ldw, int64_t tap_stride, const float* X, int64_t ldx, const float* dZ, int64_t lddz,
+                 int32_t B, int32_t T, int32_t C, int32_t N, int32_t taps, int32_t tap0, void* stream);
 
 /* out[n] += sum_m A[m][n] * (Bm ? Bm[m][n] - (R ? R[m][n] : 0) : 1)     (bias / batch-norm gradients) */
 int taco_colsum(float* out, const float* A, int64_t lda, const float* Bm, int64_t ldb, const float* R, int64_t ldr,

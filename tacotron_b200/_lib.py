@@ -96,7 +96,7 @@ EXPORTS = [
     "taco_decoder_packed_bytes", "taco_decoder_workspace_bytes", "taco_decoder_pack", "taco_decoder_fwd",
     "taco_l1_loss_fwd", "taco_l1_partial_count", "taco_launch_count",
     # training path
-    "taco_gemm", "taco_set_gemm_impl", "taco_colsum", "taco_bias_act", "taco_mul_shift", "taco_epi_bwd", "taco_epi_fwd_keep", "taco_bn_param_grad",
+    "taco_gemm", "taco_set_gemm_impl", "taco_conv_dw", "taco_colsum", "taco_bias_act", "taco_mul_shift", "taco_epi_bwd", "taco_epi_fwd_keep", "taco_bn_param_grad",
     "taco_maxpool_bwd", "taco_highway_fwd", "taco_highway_bwd", "taco_l1_bwd", "taco_scatter_add_rows", "taco_bigru_bwd",
     "taco_dec_inputs", "taco_decoder_bwd_workspace_bytes", "taco_decoder_bwd", "taco_attn_bwd_post", "taco_sumsq",
     "taco_adam_step",
@@ -122,6 +122,7 @@ def lib():
     L.taco_device_info.argtypes = [C.POINTER(C.c_int)] * 3
     L.taco_linear_fwd.argtypes = [C.POINTER(LinearDesc), C.c_void_p]
     L.taco_pack_weight.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]
+    L.taco_conv_dw.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64] + [C.c_int32] * 6 + [C.c_void_p]
     L.taco_pack_weight_x3.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     L.taco_maxpool_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
     L.taco_gather_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float,

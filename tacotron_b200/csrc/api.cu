@@ -17,6 +17,8 @@ int taco_linear_simt(const taco_linear_desc* d, cudaStream_t st);
 int taco_linear_tc(const taco_linear_desc* d, cudaStream_t st);
 int taco_pack_weight_impl(const float* W, int taps, int C, int N, float* dst, int64_t ld_dst, cudaStream_t st);
 int taco_pack_weight_x3_impl(const float* W, int taps, int C, int N, float* dst_hi, float* dst_lo, int64_t ld_dst, cudaStream_t st);
+int taco_conv_dw_tc_impl(float* dW, int64_t ldw, int64_t tap_stride, const float* X, int64_t ldx, const float* dZ, int64_t lddz,
+                         int B, int T, int C, int N, int taps, int tap0, cudaStream_t st);
 
 namespace {
 
@@ -137,6 +139,12 @@ int taco_linear_fwd(const taco_linear_desc* d, void* stream) {
 int taco_pack_weight_x3(const float* W, int taps, int C, int N, float* dst_hi, float* dst_lo, int64_t ld_dst, void* stream) {
     TACO_CHECK(W && dst_hi && dst_lo && taps >= 1 && C >= 1 && N >= 1, "taco_pack_weight_x3: bad arguments");
     return taco_pack_weight_x3_impl(W, taps, C, N, dst_hi, dst_lo, ld_dst, (cudaStream_t)stream);
+}
+
+int taco_conv_dw(float* dW, int64_t ldw, int64_t tap_stride, const float* X, int64_t ldx, const float* dZ, int64_t lddz,
+                 int B, int T, int C, int N, int taps, int tap0, void* stream) {
+    TACO_CHECK(dW && X && dZ, "taco_conv_dw: NULL");
+    return taco_conv_dw_tc_impl(dW, ldw, tap_stride, X, ldx, dZ, lddz, B, T, C, N, taps, tap0, (cudaStream_t)stream);
 }
 
 int taco_pack_weight(const float* W, int taps, int C, int N, float* dst, int64_t ld_dst, void* stream) {

@@ -533,6 +533,210 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+
+// =====================================================================================================================
+// Weight gradient of conv1d('same') / dense on the tensor cores (3xTF32, fp32-grade):
+//     dW[j][c][n] += sum_{b,t} X[b, t+tap0+j, c] * dZ[b, t, n]
+// The contraction runs over the ROWS of both operands (what a BLAS calls a TN product).  Neither operand is
+// transposed in HBM and no MN-major descriptor is needed:
+//   * a k-block = 32 consecutive rows t of one utterance.  TMA (3-D maps (C,T,B) / (N,T,B), no swizzle, OOB rows and
+//     columns zero-filled = the 'same' padding and the ragged edges) lands X[32 rows][128 c] and dZ[32 rows][128 n];
+//   * the four converter warps turn the X tile into the TMEM A operand: lane = c (the M index of the MMA), the 32
+//     rows become 32 TMEM columns -- a conflict-free column read of the tile does the transpose for free -- split
+//     into hi / lo TF32 halves (as in the forward kernel);
+//   * the same warps transpose + split the dZ tile into two K-major SWIZZLE_128B tiles (hi, lo): thread = n reads 4
+//     consecutive rows (conflict-free) and writes one 16-byte chunk per tile (8 lanes of a store phase hit 8
+//     different chunks: conflict-free);
+//   * one thread issues lo.hi + hi.lo + hi.hi tcgen05.mma (A from TMEM) per 8 rows; accumulator [128 c][128 n] in TMEM;
+//   * split-K over the (b, t-block) list: grid.y CTAs each reduce a contiguous range and add their tile into dW with
+//     vector reductions (red.global.add.v4.f32) -- same accumulate-with-atomics contract as taco_gemm's ta=1 path;
+//   * the tensor core's fp32 accumulation is not round-to-nearest: over a 10 K-row chain the bias reached 8e-5 of
+//     max|dW| (measured against float64).  Chains are therefore cut at 1024 rows: two TMEM accumulators alternate and
+//     the converter warps add the finished one into dW while the MMAs fill the other (1024-row chains: <1e-5).
+// =====================================================================================================================
+constexpr int DW_STAGES = 3;
+constexpr int DW_TILE_BYTES = 32 * 128 * 4;               // every staged tile is 16 KB
+constexpr int DW_STAGE_BYTES = 4 * DW_TILE_BYTES;         // X raw | dZ raw | dZ hi (K-major) | dZ lo (K-major)
+constexpr int DW_ACC_COLS = 256;                         // two accumulators [128 c][128 n], used alternately
+constexpr int DW_DRAIN = 32;                             // k-blocks (1024 rows) summed in tensor memory before the partial tile is added to dW
+constexpr int DW_SMEM = DW_STAGES * DW_STAGE_BYTES + 256 + 1024;
+
+struct DwArgs {
+    int T, C, N, taps, tap0;
+    int c_tiles, n_tiles;
+    int blocks_per_seq;      // ceil(T / 32)
+    int total_blocks;        // B * blocks_per_seq
+    int per_split;
+    float* dW; int64_t ldw; int64_t tap_stride;
+    int vec4;                // rows of dW 16-byte aligned
+};
+
+__global__ void __launch_bounds__(192) dw_tc_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                    const __grid_constant__ CUtensorMap tmZ, DwArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + DW_STAGES * DW_STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + DW_STAGES;
+    uint64_t* conv_bar = empty_bar + DW_STAGES;
+    uint64_t* acc_full = conv_bar + DW_STAGES;            // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int tiles = a.c_tiles * a.n_tiles;
+    const int j = blockIdx.x / tiles;
+    const int rem = blockIdx.x - j * tiles;
+    const int c0 = (rem / a.n_tiles) * 128;
+    const int n0 = (rem % a.n_tiles) * 128;
+    const int g0 = blockIdx.y * a.per_split;
+    const int g1 = min(a.total_blocks, g0 + a.per_split);
+    const int n_iters = g1 - g0;                                   // >= 1 (host)
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmZ);
+        for (int s = 0; s < DW_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&conv_bar[s], 128); }
+        mbar_init(&acc_full[0], 1);
+        mbar_init(&acc_full[1], 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < n_iters; ++it) {
+                const int s = it % DW_STAGES;
+                const uint32_t ph = (it / DW_STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                uint8_t* st = smem + s * DW_STAGE_BYTES;
+                const int g = g0 + it;
+                const int b = g / a.blocks_per_seq;
+                const int t = (g - b * a.blocks_per_seq) * 32;
+                mbar_arrive_expect_tx(&full_bar[s], 2 * DW_TILE_BYTES);
+                tma_load_3d(st, &tmX, &full_bar[s], c0, t + a.tap0 + j, b);
+                tma_load_3d(st + DW_TILE_BYTES, &tmZ, &full_bar[s], n0, t, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc<128>();
+            for (int it = 0; it < n_iters; ++it) {
+                const int s = it % DW_STAGES;
+                const uint32_t ph = (it / DW_STAGES) & 1;
+                mbar_wait(&conv_bar[s], ph);
+                tc_fence_after();
+                const uint32_t st = smem_u32(smem + s * DW_STAGE_BYTES);
+                const uint64_t bhi = make_smem_desc(st + 2 * DW_TILE_BYTES);
+                const uint64_t blo = make_smem_desc(st + 3 * DW_TILE_BYTES);
+                const uint32_t a_hi = tmem_base + (uint32_t)(DW_ACC_COLS + s * 64);
+                const int chain = it / DW_DRAIN;
+                const bool first = (it - chain * DW_DRAIN) == 0;
+                const uint32_t acc = tmem_base + (uint32_t)((chain & 1) * 128);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    tc_mma_tf32_ta(acc, a_hi + 32 + 8 * k, bhi + (uint64_t)(2 * k), idesc, (!first || k > 0) ? 1u : 0u);   // lo . hi
+                    tc_mma_tf32_ta(acc, a_hi + 8 * k, blo + (uint64_t)(2 * k), idesc, 1u);                                  // hi . lo
+                    tc_mma_tf32_ta(acc, a_hi + 8 * k, bhi + (uint64_t)(2 * k), idesc, 1u);                                  // hi . hi
+                }
+                tc_commit(&empty_bar[s]);
+                if (it + 1 == n_iters || (it + 1) % DW_DRAIN == 0) tc_commit(&acc_full[chain & 1]);   // this chain's accumulator is complete
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int m = q * 32 + lane;                               // tile row of the accumulator (c) and dZ column (n) this thread converts
+        const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const int c = c0 + m;
+        float* drow = a.dW + (int64_t)j * a.tap_stride + (int64_t)c * a.ldw + n0;
+        // add the finished accumulator of chain `ch` into dW (its MMAs were committed to acc_full[ch & 1])
+        auto drain = [&](int chn) {
+            mbar_wait(&acc_full[chn & 1], (uint32_t)((chn >> 1) & 1));
+            tc_fence_after();
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+                uint32_t v[32];
+                tc_ld_32x32b_x32(lane_taddr + (uint32_t)((chn & 1) * 128 + ch * 32), v);
+                tc_wait_ld();
+                if (c < a.C) {
+                    float* dp = drow + ch * 32;
+                    const int nb = n0 + ch * 32;
+                    if (a.vec4) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4)
+                            if (nb + i < a.N)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dp + i), "r"(v[i]), "r"(v[i + 1]), "r"(v[i + 2]), "r"(v[i + 3]) : "memory");
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (nb + i < a.N) atomicAdd(dp + i, __uint_as_float(v[i]));
+                    }
+                }
+            }
+            tc_fence_before();
+        };
+        for (int it = 0; it < n_iters; ++it) {
+            const int s = it % DW_STAGES;
+            const uint32_t ph = (it / DW_STAGES) & 1;
+            mbar_wait(&full_bar[s], ph);
+            const float* xs = reinterpret_cast<const float*>(smem + s * DW_STAGE_BYTES) + m;            // [32 rows][128]
+            const float* zs = xs + DW_TILE_BYTES / 4;
+            uint8_t* zh = smem + s * DW_STAGE_BYTES + 2 * DW_TILE_BYTES + m * 128;
+            const uint32_t ta = lane_taddr + (uint32_t)(DW_ACC_COLS + s * 64);
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t h[16], l[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const float x = xs[(hf * 16 + k) * 128];
+                    const float hv = rn_tf32(x);
+                    h[k] = __float_as_uint(hv);
+                    l[k] = __float_as_uint(rn_tf32(x - hv));
+                }
+                tc_st_32x32b_x16(ta + (uint32_t)(hf * 16), h);
+                tc_st_32x32b_x16(ta + (uint32_t)(32 + hf * 16), l);
+            }
+#pragma unroll
+            for (int kc = 0; kc < 8; ++kc) {
+                float4 h4, l4;
+                const float z0 = zs[(4 * kc + 0) * 128], z1 = zs[(4 * kc + 1) * 128], z2 = zs[(4 * kc + 2) * 128], z3 = zs[(4 * kc + 3) * 128];
+                h4.x = rn_tf32(z0); l4.x = rn_tf32(z0 - h4.x);
+                h4.y = rn_tf32(z1); l4.y = rn_tf32(z1 - h4.y);
+                h4.z = rn_tf32(z2); l4.z = rn_tf32(z2 - h4.z);
+                h4.w = rn_tf32(z3); l4.w = rn_tf32(z3 - h4.w);
+                const int off = (kc ^ (m & 7)) << 4;
+                *reinterpret_cast<float4*>(zh + off) = h4;
+                *reinterpret_cast<float4*>(zh + DW_TILE_BYTES + off) = l4;
+            }
+            fence_proxy_async();                   // generic-proxy tile writes -> visible to the tensor core's async-proxy reads
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(&conv_bar[s]);
+            // a chain's last block has just been handed to the MMA thread: the PREVIOUS chain finished long ago -- add it to dW
+            // now, while the tensor pipe works through this one.  (The next chain reuses that accumulator; its first block is
+            // converted only after this drain, so the order needs no extra barrier.)
+            if ((it + 1) % DW_DRAIN == 0 && it + 1 < n_iters && it / DW_DRAIN >= 1) drain(it / DW_DRAIN - 1);
+        }
+        // ---- the last two chains ----
+        const int n_chains = (n_iters + DW_DRAIN - 1) / DW_DRAIN;
+        if (n_chains >= 2) drain(n_chains - 2);
+        drain(n_chains - 1);
+    }
+
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 template <int BN, int STAGES, int MODE, bool X3 = false>
 int launch_tc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, dim3 grid, cudaStream_t st) {
     using L = SmemLayout<BN, STAGES, X3>;
@@ -568,6 +772,57 @@ int taco_pack_weight_x3_impl(const float* W, int taps, int C, int N, float* dst_
     if (blocks > 148 * 16) blocks = 148 * 16;
     if (blocks < 1) blocks = 1;
     pack_weight_x3_kernel<<<blocks, 256, 0, st>>>(W, taps, C, N, Cpad, dst_hi, dst_lo, ld_dst);
+    TACO_LAUNCH_CHECK();
+    return 0;
+}
+
+int taco_conv_dw_tc_impl(float* dW, int64_t ldw, int64_t tap_stride, const float* X, int64_t ldx, const float* dZ, int64_t lddz,
+                         int B, int T, int C, int N, int taps, int tap0, cudaStream_t st) {
+    TACO_CHECK(taco_aligned16(X) && taco_aligned16(dZ), "taco_conv_dw: X / dZ must be 16-byte aligned");
+    TACO_CHECK((ldx % 4) == 0 && (lddz % 4) == 0, "taco_conv_dw: ldx and lddz must be multiples of 4 floats (TMA 16B strides)");
+    TACO_CHECK(B >= 1 && T >= 1 && C >= 1 && N >= 1 && taps >= 1, "taco_conv_dw: bad shape");
+    EncodeTiledFn enc = get_encode_fn();
+    TACO_CHECK(enc != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
+    DwArgs a;
+    a.T = T; a.C = C; a.N = N; a.taps = taps; a.tap0 = tap0;
+    a.c_tiles = (C + 127) / 128; a.n_tiles = (N + 127) / 128;
+    a.blocks_per_seq = (T + 31) / 32;
+    a.total_blocks = B * a.blocks_per_seq;
+    const int tiles = a.c_tiles * a.n_tiles * taps;
+    int splits = 148 / tiles;
+    if (splits < 1) splits = 1;
+    if (splits > a.total_blocks) splits = a.total_blocks;
+    a.per_split = (a.total_blocks + splits - 1) / splits;
+    splits = (a.total_blocks + a.per_split - 1) / a.per_split;        // every split owns at least one block
+    a.dW = dW; a.ldw = ldw; a.tap_stride = tap_stride;
+    a.vec4 = (taco_aligned16(dW) && (ldw % 4) == 0 && (tap_stride % 4) == 0) ? 1 : 0;
+    CUtensorMap tmX, tmZ;
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
+        cuuint64_t strides[2] = {(cuuint64_t)ldx * 4, (cuuint64_t)T * (cuuint64_t)ldx * 4};
+        cuuint32_t box[3] = {128, 32, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = enc(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(X), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        TACO_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(X) failed: %d (C=%d T=%d B=%d ldx=%lld)", (int)r, C, T, B, (long long)ldx);
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)T, (cuuint64_t)B};
+        cuuint64_t strides[2] = {(cuuint64_t)lddz * 4, (cuuint64_t)T * (cuuint64_t)lddz * 4};
+        cuuint32_t box[3] = {128, 32, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = enc(&tmZ, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(dZ), dims, strides, box, es,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        TACO_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(dZ) failed: %d (N=%d T=%d B=%d lddz=%lld)", (int)r, N, T, B, (long long)lddz);
+    }
+    static bool configured = false;
+    if (!configured) {
+        TACO_CUDA(cudaFuncSetAttribute(dw_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_SMEM));
+        configured = true;
+    }
+    dw_tc_kernel<<<dim3((unsigned)tiles, (unsigned)splits), 192, DW_SMEM, st>>>(tmX, tmZ, a);
     TACO_LAUNCH_CHECK();
     return 0;
 }

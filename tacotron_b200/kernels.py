@@ -60,6 +60,15 @@ def gemm(Cm, A, B, *, ta=False, tb=False, beta=0.0, shift=0, period=0, taps=1, d
         assert B.shape[0] == N and B.shape[1] * taps == K, (B.shape, N, K)
     else:
         assert B.shape == (K, N), (B.shape, K, N)
+    if ta and DW_TC and _dw_tc_ok(Cm, A, B, tb, beta, period, taps, dshift, kper, batch, a_bstride, b_bstride, c_bstride, bshift):
+        # weight gradient on the tcgen05 kernel: rows of A / B are (utterance, time), batch entries are the conv taps
+        T = period if period > 0 else K
+        if beta == 0.0:
+            for z in range(batch):
+                _offset2(Cm, z * c_bstride).zero_()
+        L.check(L.lib().taco_conv_dw(_p(Cm), _ld(Cm), c_bstride, _p(A), _ld(A), _p(B), _ld(B), K // T, T, M, N, batch,
+                                     shift, _st()), "taco_conv_dw")
+        return
     d = L.GemmDesc()
     d.A = A.data_ptr(); d.lda = _ld(A); d.B = B.data_ptr(); d.ldb = _ld(B); d.C = Cm.data_ptr(); d.ldc = _ld(Cm)
     d.M = M; d.N = N; d.K = K; d.ta = int(ta); d.tb = int(tb); d.beta = float(beta)
@@ -74,6 +83,26 @@ def gemm(Cm, A, B, *, ta=False, tb=False, beta=0.0, shift=0, period=0, taps=1, d
 # TACO_IMPL_TC3 (3xTF32, fp32-grade -- what Tacotron.backward uses in 'fp32x3' mode) or TACO_IMPL_TC (single-pass TF32).
 DX_TC = False
 DX_TC_IMPL = L.IMPL_TC3
+# DW_TC = True routes the weight gradients (gemm(..., ta=True): dW = X^T dZ over the rows) through taco_conv_dw: 3xTF32 on the
+# tcgen05 tensor cores (fp32-grade) instead of the mma.sync / FFMA GEMM.  Tacotron.backward turns it on outside 'fp32' mode.
+DW_TC = False
+DW_TC_MIN_ROWS = 512      # below this the launch is all prologue: keep the plain GEMM
+
+
+def _dw_tc_ok(Cm, A, B, tb, beta, period, taps, dshift, kper, batch, a_bstride, b_bstride, c_bstride, bshift):
+    K = A.shape[0]
+    if tb or taps != 1 or dshift != 0 or kper != 0 or beta not in (0.0, 1.0) or K < DW_TC_MIN_ROWS:
+        return False
+    if batch > 1 and (bshift != 1 or a_bstride != 0 or b_bstride != 0):
+        return False
+    if period > 0 and K % period != 0:
+        return False
+    return (A.stride(0) % 4 == 0 and B.stride(0) % 4 == 0 and A.data_ptr() % 16 == 0 and B.data_ptr() % 16 == 0
+            and A.stride(1) == 1 and B.stride(1) == 1 and Cm.stride(1) == 1)
+
+
+def _offset2(t, off):
+    return t if off == 0 else torch.as_strided(t, t.shape, t.stride(), t.storage_offset() + off)
 
 
 def _cpad(c):

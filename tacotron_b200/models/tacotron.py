@@ -282,12 +282,16 @@ class Tacotron(object):
             dx_tc = self.config.precision != "fp32"
         prev_dx, K.DX_TC = K.DX_TC, bool(dx_tc)
         prev_impl, K.DX_TC_IMPL = K.DX_TC_IMPL, (L.IMPL_TC if self.config.precision == "tf32" else L.IMPL_TC3)
+        # weight gradients of the dense / conv layers: tcgen05 3xTF32 kernel (taco_conv_dw), same switch; Config.grad_dw_tc overrides
+        dw_tc = getattr(self.config, "grad_dw_tc", None)
+        prev_dw, K.DW_TC = K.DW_TC, bool(dx_tc if dw_tc is None else dw_tc)
         try:
             grad.model_bwd(K, self.store, self._gviews, S, self.config)
         finally:
             K.set_gemm_impl(prev)
             K.DX_TC = prev_dx
             K.DX_TC_IMPL = prev_impl
+            K.DW_TC = prev_dw
         return self._gviews
 
     def train_step(self, inputs, lr=None, **kw):

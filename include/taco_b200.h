@@ -246,6 +246,9 @@ int taco_highway_bwd(float* dP, int64_t lddp, float* dXd, int64_t lddx, const fl
                      int64_t ldp, const float* X, int64_t ldx, int M, int U, void* stream);
 /* dA = beta*dA + sign(A - B)    (tacotron.py:158-160) */
 int taco_l1_bwd(float* dA, const float* A, const float* B, int64_t n, float beta, void* stream);
+/* same, A / B as [rows][cols] contiguous and dA with a row pitch of ldd >= cols floats (a 16-byte-aligned pitch for the
+ * [M][1025] spectrogram gradient, so that the tensor-core data / weight gradient kernels can read it through TMA) */
+int taco_l1_bwd_ld(float* dA, int64_t ldd, const float* A, const float* B, int64_t rows, int64_t cols, float beta, void* stream);
 /* dTable[ids[m]][:] += dRows[m][:]   (embedding_lookup backward, tacotron.py:111-114) */
 int taco_scatter_add_rows(float* dTable, const int32_t* ids, const float* dRows, int rows, int width, int vocab,
                           void* stream);

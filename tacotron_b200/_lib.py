@@ -97,7 +97,7 @@ EXPORTS = [
     "taco_l1_loss_fwd", "taco_l1_partial_count", "taco_launch_count",
     # training path
     "taco_gemm", "taco_set_gemm_impl", "taco_conv_dw", "taco_colsum", "taco_bias_act", "taco_mul_shift", "taco_epi_bwd", "taco_epi_fwd_keep", "taco_bn_param_grad",
-    "taco_maxpool_bwd", "taco_highway_fwd", "taco_highway_bwd", "taco_l1_bwd", "taco_scatter_add_rows", "taco_bigru_bwd",
+    "taco_maxpool_bwd", "taco_highway_fwd", "taco_highway_bwd", "taco_l1_bwd", "taco_l1_bwd_ld", "taco_scatter_add_rows", "taco_bigru_bwd",
     "taco_dec_inputs", "taco_decoder_bwd_workspace_bytes", "taco_decoder_bwd", "taco_attn_bwd_post", "taco_sumsq",
     "taco_adam_step",
     # spectrogram inversion (Griffin-Lim glue kernels)
@@ -150,6 +150,7 @@ def lib():
     L.taco_highway_fwd.argtypes = [vp, i64, vp, i64, vp, i64, i32, i32, vp]
     L.taco_highway_bwd.argtypes = [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, vp]
     L.taco_l1_bwd.argtypes = [vp, vp, vp, i64, f32, vp]
+    L.taco_l1_bwd_ld.argtypes = [vp, i64, vp, vp, i64, i64, f32, vp]
     L.taco_scatter_add_rows.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     L.taco_bigru_bwd.argtypes = [vp] * 8 + [i32, i32, vp]
     L.taco_dec_inputs.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, i32, vp]

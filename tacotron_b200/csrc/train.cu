@@ -416,6 +416,20 @@ __global__ void l1_bwd_kernel(float* dA, const float* __restrict__ A, const floa
     }
 }
 
+// same with a row-padded gradient buffer (rows of `cols` values, `ldd` floats apart): lets the [M][1025] spectrogram gradient
+// live in a 16-byte-aligned row pitch so that the tensor-core dX / dW kernels can TMA it
+__global__ void l1_bwd_ld_kernel(float* dA, int64_t ldd, const float* __restrict__ A, const float* __restrict__ Bt, int64_t rows,
+                                 int64_t cols, float beta) {
+    const int64_t n = rows * cols;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / cols, c = i - r * cols;
+        const float d = A[i] - Bt[i];
+        const float s = (d > 0.f) ? 1.f : ((d < 0.f) ? -1.f : 0.f);
+        float* o = dA + r * ldd + c;
+        *o = (beta != 0.f) ? fmaf(beta, *o, s) : s;
+    }
+}
+
 __global__ void scatter_add_rows_kernel(float* dTable, const int32_t* __restrict__ ids, const float* __restrict__ dRows, int rows,
                                         int width, int vocab) {
     const int64_t total = (int64_t)rows * width;
@@ -662,6 +676,14 @@ int taco_l1_bwd(float* dA, const float* A, const float* Bt, int64_t n, float bet
     TACO_CHECK(dA && A && Bt && n >= 0, "taco_l1_bwd: bad arguments");
     if (n == 0) return 0;
     l1_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(dA, A, Bt, n, beta);
+    TACO_LAUNCH_CHECK();
+    return 0;
+}
+
+int taco_l1_bwd_ld(float* dA, int64_t ldd, const float* A, const float* Bt, int64_t rows, int64_t cols, float beta, void* stream) {
+    TACO_CHECK(dA && A && Bt && rows >= 0 && cols >= 0 && ldd >= cols, "taco_l1_bwd_ld: bad arguments");
+    if (rows * cols == 0) return 0;
+    l1_bwd_ld_kernel<<<grid_for(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>(dA, ldd, A, Bt, rows, cols, beta);
     TACO_LAUNCH_CHECK();
     return 0;
 }

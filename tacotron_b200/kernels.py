@@ -39,6 +39,12 @@ def empty(shape, like, dtype=None):
     return torch.empty(shape, dtype=dtype or like.dtype, device=like.device)
 
 
+def padded_rows(rows, cols, like):
+    """[rows, cols] view of a buffer whose row pitch is rounded up to 4 floats (16 bytes): TMA-readable rows for odd widths"""
+    ld = (cols + 3) // 4 * 4
+    return torch.empty((rows, ld), dtype=like.dtype, device=like.device)[:, :cols]
+
+
 def zeros(shape, like, dtype=None):
     return torch.zeros(shape, dtype=dtype or like.dtype, device=like.device)
 
@@ -206,6 +212,10 @@ def highway_bwd(dP, dXd, dY, Pm, X):
 
 
 def l1_bwd(dA, A, Bt, beta=0.0):
+    if not dA.is_contiguous():          # row-padded gradient buffer (see padded_rows)
+        assert dA.dim() == 2 and dA.stride(1) == 1 and A.is_contiguous() and Bt.is_contiguous() and A.shape == Bt.shape == dA.shape
+        L.check(L.lib().taco_l1_bwd_ld(_p(dA), dA.stride(0), _p(A), _p(Bt), dA.shape[0], dA.shape[1], float(beta), _st()), "taco_l1_bwd_ld")
+        return
     assert dA.is_contiguous() and A.is_contiguous() and Bt.is_contiguous() and A.numel() == Bt.numel() == dA.numel()
     L.check(L.lib().taco_l1_bwd(_p(dA), _p(A), _p(Bt), A.numel(), float(beta), _st()), "taco_l1_bwd")
 

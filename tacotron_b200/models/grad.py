@@ -365,7 +365,7 @@ def model_bwd(K, P, G, S, cfg):
     F = cfg.fft_size
     post = _v2(S["post/cbhg/gru_out"])                                         # [B*T*r, 256]
     out2 = out.reshape(-1, F)
-    dOut = K.empty(out2.shape, y)
+    dOut = K.padded_rows(out2.shape[0], F, y)           # 1025 columns in a 1028-float pitch: TMA-readable by the dX / dW kernels
     K.l1_bwd(dOut, out2, S["stft"].reshape(-1, F))
     dPost = K.empty(post.shape, y)
     dense_bwd(K, dOut, post, P["post/dense/W"], G["post/dense/W"], G["post/dense/b"], dX=dPost)

@@ -24,6 +24,10 @@ def empty(shape, like, dtype=None):
     return torch.empty(shape, dtype=dtype or like.dtype, device=like.device)
 
 
+def padded_rows(rows, cols, like):
+    return torch.empty((rows, cols), dtype=like.dtype)
+
+
 def zeros(shape, like, dtype=None):
     return torch.zeros(shape, dtype=dtype or like.dtype, device=like.device)
 

@@ -48,7 +48,6 @@ struct TcArgs {
     int pool;
     int lo_row0;       // X3: first row of the lo half in the packed weight buffer (= rows of the hi half)
     int direct;        // 1: register-direct vectorised epilogue (all row strides multiples of 4 floats), 0: transposing epilogue
-    int n_tiles, m_tiles;   // persistent kernel: tile grid (n fastest; bank: heaviest filters first)
     EpiParams e;
 };
 
@@ -98,13 +97,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 
 // ---------------------------------------------------------------------------------------------------------------------
-// register-direct epilogue, shared by the one-tile kernel and the persistent kernel.
+// register-direct epilogue.
 // TMEM lane = output row: after tcgen05.ld a lane holds 32 consecutive columns of ITS row.  The fused epilogue runs on
 // those registers and the row segment leaves as eight 16-byte stores -- ~4 instructions per element less than the
 // transposing epilogue (which measured ~37 K warp-instructions per 128x128 tile and made every short-K contraction
 // epilogue-bound: profiles/r02_ncu_summary.md).
 // Highway (MODE 1): the tile's columns [0, BN/2) are H pre-activations of output columns oc0.., [BN/2, BN) the matching T
-// pre-activations (BN = 256: the whole layer in one tile; BN = 128: half of it, the B tile gathered from two row blocks).
+// pre-activations (BN = 256: the whole layer in one tile).
 // cst: bias[256] | scale[256] | shift[256]; frow: first rows of the four quarters [4][32] (pool).
 // ---------------------------------------------------------------------------------------------------------------------
 template <int BN, int MODE>
@@ -124,14 +123,24 @@ __device__ __forceinline__ void load_epilogue_consts(const TcArgs& a, float* cst
     }
 }
 
+// explicit shared-memory load (pointers derived from the aligned dynamic-smem base are not provably shared for the compiler:
+// it emitted generic LD.E.128 for the epilogue constants and the splitter's tile reads)
+__device__ __forceinline__ float4 lds128(const void* p) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+    return v;
+}
+template <int CW> __device__ __forceinline__ void tc_ld_cols(uint32_t taddr, uint32_t (&v)[CW]);
+template <> __device__ __forceinline__ void tc_ld_cols<32>(uint32_t taddr, uint32_t (&v)[32]) { tc_ld_32x32b_x32(taddr, v); }
+
 // 32 consecutive outputs of one row to a 4-byte-aligned address: SH scalars, then 16-byte stores, then the remaining scalars
-template <int SH>
-__device__ __forceinline__ void store_row_shifted(float* yp, const float (&y)[32], int cbase, int ncols) {
+template <int SH, int CW>
+__device__ __forceinline__ void store_row_shifted(float* yp, const float (&y)[CW], int cbase, int ncols) {
 #pragma unroll
     for (int j = 0; j < SH; ++j)
         if (cbase + j < ncols) yp[j] = y[j];
 #pragma unroll
-    for (int j = SH; j + 3 < 32; j += 4) {
+    for (int j = SH; j + 3 < CW; j += 4) {
         if (cbase + j + 3 < ncols) {
             *reinterpret_cast<float4*>(yp + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
         } else {
@@ -141,35 +150,40 @@ __device__ __forceinline__ void store_row_shifted(float* yp, const float (&y)[32
         }
     }
 #pragma unroll
-    for (int j = SH + ((32 - SH) / 4) * 4; j < 32; ++j)
+    for (int j = SH + ((CW - SH) / 4) * 4; j < CW; ++j)
         if (cbase + j < ncols) yp[j] = y[j];
 }
 
-template <int BN, int MODE>
+// CW = columns per pass; passes [ch0, ch1) of the tile are handled by the calling warp; bar_id = the 128-thread named barrier of
+// the four epilogue warps (pool only).  The TMEM load of pass i+1 is issued before pass i is finished and stored.
+template <int BN, int MODE, int CW>
 __device__ __forceinline__ void direct_epilogue(const TcArgs& a, const float* cst, float* frow, uint32_t acc_taddr, int q, int lane,
-                                                int b, int t0, int n0, int oc0) {
+                                                int b, int t0, int n0, int oc0, int ch0, int ch1, int bar_id) {
     const int row = q * 32 + lane;
     const int t = t0 + row;
     const bool row_ok = (t < a.T) && (!a.pool || row < TC_BM - 1 || t == a.T - 1);
     const int64_t grow = (int64_t)b * a.T + t;
     constexpr int HW = BN / 2;
-    constexpr int NCH = (MODE == 1) ? HW / 32 : BN / 32;
-    for (int ch = 0; ch < NCH; ++ch) {
-        uint32_t v[32];
-        float y[32];
-        tc_ld_32x32b_x32(acc_taddr + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+    const uint32_t lane_acc = acc_taddr + ((uint32_t)(q * 32) << 16);
+    uint32_t v[CW];
+    tc_ld_cols<CW>(lane_acc + (uint32_t)(ch0 * CW), v);
+    for (int ch = ch0; ch < ch1; ++ch) {
+        float y[CW];
+        const int c0 = ch * CW;                       // column offset inside the tile
         tc_wait_ld();
-        const int c0 = ch * 32;                       // column offset inside the tile
         if (MODE == 1) {
-            uint32_t w[32];
-            tc_ld_32x32b_x32(acc_taddr + ((uint32_t)(q * 32) << 16) + (uint32_t)(HW + ch * 32), w);
-            tc_wait_ld();
+            uint32_t w[CW];
+            tc_ld_cols<CW>(lane_acc + (uint32_t)(HW + c0), w);
             const float* hx = a.e.hx + grow * a.e.ldhx + oc0 + c0;
+            float4 xr[CW / 4];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                const float4 bh = *reinterpret_cast<const float4*>(cst + c0 + j);
-                const float4 bt = *reinterpret_cast<const float4*>(cst + HW + c0 + j);
-                const float4 x = row_ok ? __ldg(reinterpret_cast<const float4*>(hx + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < CW / 4; ++j) xr[j] = row_ok ? __ldg(reinterpret_cast<const float4*>(hx) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            tc_wait_ld();
+#pragma unroll
+            for (int j = 0; j < CW; j += 4) {
+                const float4 bh = lds128(cst + c0 + j);
+                const float4 bt = lds128(cst + HW + c0 + j);
+                const float4 x = xr[j / 4];
                 const float xs[4] = {x.x, x.y, x.z, x.w}, bhs[4] = {bh.x, bh.y, bh.z, bh.w}, bts[4] = {bt.x, bt.y, bt.z, bt.w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -178,13 +192,14 @@ __device__ __forceinline__ void direct_epilogue(const TcArgs& a, const float* cs
                     y[j + k] = H * Tg + xs[k] * (1.0f - Tg);
                 }
             }
+            if (ch + 1 < ch1) tc_ld_cols<CW>(lane_acc + (uint32_t)(c0 + CW), v);      // next pass travels while this one is stored
         } else {
             const int act = a.e.act;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                const float4 cb = *reinterpret_cast<const float4*>(cst + c0 + j);
-                const float4 sc = *reinterpret_cast<const float4*>(cst + 256 + c0 + j);
-                const float4 sh = *reinterpret_cast<const float4*>(cst + 512 + c0 + j);
+            for (int j = 0; j < CW; j += 4) {
+                const float4 cb = lds128(cst + c0 + j);
+                const float4 sc = lds128(cst + 256 + c0 + j);
+                const float4 sh = lds128(cst + 512 + c0 + j);
                 const float cbs[4] = {cb.x, cb.y, cb.z, cb.w}, scs[4] = {sc.x, sc.y, sc.z, sc.w}, shs[4] = {sh.x, sh.y, sh.z, sh.w};
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -193,18 +208,19 @@ __device__ __forceinline__ void direct_epilogue(const TcArgs& a, const float* cs
                     y[j + k] = fmaf(u, scs[k], shs[k]);
                 }
             }
+            if (ch + 1 < ch1) tc_ld_cols<CW>(lane_acc + (uint32_t)(c0 + CW), v);      // next pass travels while this one is finished and stored
             if (a.pool) {
                 // max_pooling1d(2,1,'same') over t: row t needs row t+1 = the next lane; lane 31 takes the first row of
                 // the next quarter from shared memory (tiles advance by 127 rows, so row 127 never needs a successor)
-                named_bar_sync(1, 128);               // previous chunk's first rows have been consumed
+                named_bar_sync(bar_id, 128);          // previous pass's first rows have been consumed
                 if (lane == 0) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(frow + q * 32 + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+                    for (int j = 0; j < CW; j += 4) *reinterpret_cast<float4*>(frow + q * 32 + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
                 }
-                named_bar_sync(1, 128);
+                named_bar_sync(bar_id, 128);
                 const bool has_next = (t + 1 < a.T) && (row + 1 < TC_BM);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
+                for (int j = 0; j < CW; ++j) {
                     float nx = __shfl_down_sync(0xffffffffu, y[j], 1);
                     if (lane == 31) nx = frow[((q + 1) & 3) * 32 + j];
                     if (has_next) y[j] = fmaxf(y[j], nx);
@@ -214,7 +230,7 @@ __device__ __forceinline__ void direct_epilogue(const TcArgs& a, const float* cs
                 const uint4* kp = reinterpret_cast<const uint4*>(a.e.keep + grow * (int64_t)a.e.N + n0 + c0);
                 if (row_ok) {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
+                    for (int h = 0; h < CW / 16; ++h) {
                         const uint4 kk = kp[h];
                         const uint32_t ks[4] = {kk.x, kk.y, kk.z, kk.w};
 #pragma unroll
@@ -226,7 +242,7 @@ __device__ __forceinline__ void direct_epilogue(const TcArgs& a, const float* cs
             if (a.e.residual && row_ok) {
                 const float* rp = a.e.residual + grow * a.e.ldr + n0 + c0;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
+                for (int j = 0; j < CW; j += 4) {
                     if (n0 + c0 + j < a.N) {
                         const float4 r4 = __ldg(reinterpret_cast<const float4*>(rp + j));
                         y[j] += r4.x; y[j + 1] += r4.y; y[j + 2] += r4.z; y[j + 3] += r4.w;
@@ -243,14 +259,14 @@ __device__ __forceinline__ void direct_epilogue(const TcArgs& a, const float* cs
                 // boundary, 16-byte stores from there, scalars for the rest.  The shift depends on the row (lane), so a warp
                 // runs up to four variants -- still far fewer instructions than transposing the tile through shared memory.
                 switch ((4 - (int)((reinterpret_cast<uintptr_t>(yp) >> 2) & 3)) & 3) {
-                    case 0:  store_row_shifted<0>(yp, y, cbase, ncols); break;
-                    case 1:  store_row_shifted<1>(yp, y, cbase, ncols); break;
-                    case 2:  store_row_shifted<2>(yp, y, cbase, ncols); break;
-                    default: store_row_shifted<3>(yp, y, cbase, ncols); break;
+                    case 0:  store_row_shifted<0, CW>(yp, y, cbase, ncols); break;
+                    case 1:  store_row_shifted<1, CW>(yp, y, cbase, ncols); break;
+                    case 2:  store_row_shifted<2, CW>(yp, y, cbase, ncols); break;
+                    default: store_row_shifted<3, CW>(yp, y, cbase, ncols); break;
                 }
             } else {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
+                for (int j = 0; j < CW; j += 4)
                     if (cbase + j < ncols) *reinterpret_cast<float4*>(yp + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
             }
         }
@@ -397,7 +413,7 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
             named_bar_sync(1, 128);
             mbar_wait(tmem_full, 0);
             tc_fence_after();
-            direct_epilogue<BN, MODE>(a, cst, cst + 768, tmem_base, q, lane, b, t0, n0, 0);
+            direct_epilogue<BN, MODE, 32>(a, cst, cst + 768, tmem_base, q, lane, b, t0, n0, 0, 0, (MODE == 1 ? BN / 2 : BN) / 32, 1);
             tc_fence_before();
         } else {
         mbar_wait(tmem_full, 0);
@@ -587,200 +603,6 @@ EncodeTiledFn get_encode_fn() {
 }
 
 
-
-// =====================================================================================================================
-// Persistent 3xTF32 kernel (fp32x3, direct epilogue): one CTA per SM walks a static list of 128x128 output tiles.
-//   warp 0      TMA producer          (4-stage ring of A | B_hi | B_lo, 48 KB per stage, runs ahead across tile borders)
-//   warp 1      MMA issuer            (two TMEM accumulators: tile i+1 is multiplied while tile i is being written out)
-//   warps 2-5   A splitters           (fp32 tile -> hi / lo TF32 halves in TMEM, as in the one-tile kernel)
-//   warps 6-9   epilogue              (direct_epilogue on the finished accumulator, then hands it back)
-// Per-CTA set-up (barriers, TMEM allocation, descriptor fetch), the pipeline fill and the epilogue of a tile no longer
-// serialise with its main loop: for the short-K contractions (highway K=128, GRU input K=128, small bank filters) these
-// were most of the tile time.  Bank tiles are ordered heaviest filter first so that the static round-robin is balanced.
-// Highway (MODE 1): 128-column tiles = 64 H columns + the matching 64 T columns (two 64-row boxes of the packed weight).
-// TMEM: accumulators at columns 0 / 128, A stages at 256 + 64 s  (512 columns).
-// =====================================================================================================================
-constexpr int P_STAGES = 4;
-constexpr int P_STAGE_BYTES = A_STAGE_BYTES + 2 * (128 * TC_BK * 4);      // 48 KB
-constexpr int P_PIPE_BYTES = P_STAGES * P_STAGE_BYTES;
-constexpr int P_CONST_OFFSET = P_PIPE_BYTES + 256;
-constexpr int P_SMEM = P_PIPE_BYTES + 256 + 3072 + 512 + 1024;
-
-struct PTile { int n_tile, b, t0, n0, taps, tap0, n_iters; };
-
-__device__ __forceinline__ PTile p_tile(const TcArgs& a, int ti) {
-    PTile p;
-    int m_tile;
-    if (a.bank) { p.n_tile = a.n_tiles - 1 - ti / a.m_tiles; m_tile = ti % a.m_tiles; }
-    else        { p.n_tile = ti % a.n_tiles; m_tile = ti / a.n_tiles; }
-    p.b = m_tile / a.tiles_per_seq;
-    p.t0 = (m_tile % a.tiles_per_seq) * a.tile_stride;
-    p.n0 = p.n_tile * 128;
-    p.taps = a.taps; p.tap0 = a.tap0;
-    if (a.bank) { p.taps = p.n_tile + 1; p.tap0 = -((p.taps - 1) / 2); }
-    p.n_iters = p.taps * a.cchunks;
-    return p;
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(320) gemm_tc3p_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                        const __grid_constant__ CUtensorMap tmB, TcArgs a) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + P_PIPE_BYTES);
-    uint64_t* empty_bar = full_bar + P_STAGES;
-    uint64_t* conv_bar = empty_bar + P_STAGES;
-    uint64_t* acc_full = conv_bar + P_STAGES;           // [2]
-    uint64_t* acc_empty = acc_full + 2;                 // [2]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int total = a.n_tiles * a.m_tiles;
-
-    if (threadIdx.x == 0) {
-        tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmB);
-        for (int s = 0; s < P_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&conv_bar[s], 128); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
-        mbar_fence_init();
-    }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_ptr;
-
-    if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int ti = blockIdx.x; ti < total; ti += gridDim.x) {
-                const PTile p = p_tile(a, ti);
-                for (int k = 0; k < p.n_iters; ++k, ++it) {
-                    const int s = it % P_STAGES;
-                    const uint32_t ph = (it / P_STAGES) & 1;
-                    mbar_wait(&empty_bar[s], ph ^ 1);
-                    uint8_t* As = smem + s * P_STAGE_BYTES;
-                    uint8_t* Bs = As + A_STAGE_BYTES;
-                    const int j = k / a.cchunks;
-                    const int c0 = (k - j * a.cchunks) * TC_BK;
-                    const int kc = j * a.Cpad + c0;
-                    mbar_arrive_expect_tx(&full_bar[s], P_STAGE_BYTES);
-                    tma_load_3d(As, &tmA, &full_bar[s], c0, p.t0 + p.tap0 + j, p.b);
-                    if (MODE == 1) {
-                        // B tile = [64 H rows | 64 T rows] of the packed highway weight (hi half, then the same of the lo half)
-                        const int U = a.N / 2, r0 = p.n_tile * 64;
-                        tma_load_2d(Bs, &tmB, &full_bar[s], kc, r0);
-                        tma_load_2d(Bs + 64 * 128, &tmB, &full_bar[s], kc, U + r0);
-                        tma_load_2d(Bs + 128 * 128, &tmB, &full_bar[s], kc, a.lo_row0 + r0);
-                        tma_load_2d(Bs + 192 * 128, &tmB, &full_bar[s], kc, a.lo_row0 + U + r0);
-                    } else {
-                        tma_load_2d(Bs, &tmB, &full_bar[s], kc, p.n0);
-                        tma_load_2d(Bs + 128 * 128, &tmB, &full_bar[s], kc, a.lo_row0 + p.n0);
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc<128>();
-            uint32_t it = 0, tc = 0;
-            for (int ti = blockIdx.x; ti < total; ti += gridDim.x, ++tc) {
-                const PTile p = p_tile(a, ti);
-                const uint32_t buf = tc & 1;
-                mbar_wait(&acc_empty[buf], ((tc >> 1) & 1) ^ 1);           // the epilogue has read this accumulator's previous tile
-                tc_fence_after();
-                const uint32_t acc = tmem_base + buf * 128;
-                for (int k = 0; k < p.n_iters; ++k, ++it) {
-                    const int s = it % P_STAGES;
-                    const uint32_t ph = (it / P_STAGES) & 1;
-                    mbar_wait(&conv_bar[s], ph);
-                    tc_fence_after();
-                    const uint32_t st = smem_u32(smem + s * P_STAGE_BYTES);
-                    const uint64_t bdesc = make_smem_desc(st + A_STAGE_BYTES);
-                    const uint64_t blo = make_smem_desc(st + A_STAGE_BYTES + 128 * 128);
-                    const uint32_t a_hi = tmem_base + (uint32_t)(256 + s * 64);
-#pragma unroll
-                    for (int kk = 0; kk < TC_BK / 8; ++kk) {
-                        tc_mma_tf32_ta(acc, a_hi + TC_BK + 8 * kk, bdesc + (uint64_t)(2 * kk), idesc, (k > 0 || kk > 0) ? 1u : 0u);   // lo . hi
-                        tc_mma_tf32_ta(acc, a_hi + 8 * kk, blo + (uint64_t)(2 * kk), idesc, 1u);                                      // hi . lo
-                        tc_mma_tf32_ta(acc, a_hi + 8 * kk, bdesc + (uint64_t)(2 * kk), idesc, 1u);                                    // hi . hi
-                    }
-                    tc_commit(&empty_bar[s]);
-                }
-                tc_commit(&acc_full[buf]);
-            }
-        }
-    } else if (warp < 6) {
-        // ================= A splitters (see the one-tile kernel) =================
-        const int q = warp & 3;
-        const int row = q * 32 + lane;
-        const uint32_t lane_taddr = tmem_base + ((uint32_t)(q * 32) << 16) + 256u;
-        uint32_t it = 0;
-        for (int ti = blockIdx.x; ti < total; ti += gridDim.x) {
-            const PTile p = p_tile(a, ti);
-            for (int k = 0; k < p.n_iters; ++k, ++it) {
-                const int s = it % P_STAGES;
-                const uint32_t ph = (it / P_STAGES) & 1;
-                mbar_wait(&full_bar[s], ph);
-                const uint8_t* arow = smem + s * P_STAGE_BYTES + row * 128;
-                const uint32_t ta = lane_taddr + (uint32_t)(s * 64);
-#pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    uint32_t h[16], l[16];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const int chunk = hf * 4 + c;
-                        const float4 x = *reinterpret_cast<const float4*>(arow + ((chunk ^ (row & 7)) << 4));
-                        const float xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float hv = rn_tf32(xs[e]);
-                            h[c * 4 + e] = __float_as_uint(hv);
-                            l[c * 4 + e] = __float_as_uint(rn_tf32(xs[e] - hv));
-                        }
-                    }
-                    tc_st_32x32b_x16(ta + (uint32_t)(hf * 16), h);
-                    tc_st_32x32b_x16(ta + (uint32_t)(TC_BK + hf * 16), l);
-                }
-                tc_wait_st();
-                tc_fence_before();
-                mbar_arrive(&conv_bar[s]);
-            }
-        }
-    } else {
-        // ================= epilogue warps (6..9) =================
-        const int q = warp & 3;
-        const int et = threadIdx.x - 192;
-        float* cst = reinterpret_cast<float*>(smem + P_CONST_OFFSET);
-        uint32_t tc = 0;
-        for (int ti = blockIdx.x; ti < total; ti += gridDim.x, ++tc) {
-            const PTile p = p_tile(a, ti);
-            const uint32_t buf = tc & 1;
-            const int oc0 = (MODE == 1) ? p.n_tile * 64 : 0;
-            named_bar_sync(1, 128);                                         // everybody is done with the previous tile's constants
-            load_epilogue_consts<128, MODE>(a, cst, et, p.n0, oc0);
-            named_bar_sync(1, 128);
-            mbar_wait(&acc_full[buf], (tc >> 1) & 1);
-            tc_fence_after();
-            direct_epilogue<128, MODE>(a, cst, cst + 768, tmem_base + buf * 128, q, lane, p.b, p.t0, p.n0, oc0);
-            tc_fence_before();
-            mbar_arrive(&acc_empty[buf]);
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-    }
-}
 
 // =====================================================================================================================
 // Weight gradient of conv1d('same') / dense on the tensor cores (3xTF32, fp32-grade):
@@ -1149,37 +971,6 @@ int taco_linear_tc(const taco_linear_desc* d, cudaStream_t st) {
         TACO_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B) failed: %d (N=%d ldwp=%lld)", (int)r, d->N, (long long)d->ldwp);
     }
     dim3 grid((d->N + BN - 1) / BN, (unsigned)(a.tiles_per_seq * d->B));
-    // more than one wave of tiles (2 CTAs per SM) with the vectorised epilogue: persistent kernel
-    static const int no_persist = [] { const char* e = getenv("TACO_TC3_NO_PERSIST"); return (e && atoi(e) == 1) ? 1 : 0; }();
-    if (x3 && a.direct && BN != 32 && !no_persist) {
-        a.m_tiles = a.tiles_per_seq * d->B;
-        a.n_tiles = highway ? 2 : (d->N + 127) / 128;
-        const int64_t total = (int64_t)a.m_tiles * a.n_tiles;
-        if (total > 2 * 148) {
-            CUtensorMap tmBp = tmB;
-            if (highway) {
-                cuuint64_t dims[2] = {(cuuint64_t)d->ldwp, (cuuint64_t)d->N * 2u};
-                cuuint64_t strides[1] = {(cuuint64_t)d->ldwp * 4};
-                cuuint32_t box[2] = {TC_BK, 64};
-                cuuint32_t es[2] = {1, 1};
-                CUresult r = enc(&tmBp, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(d->Wp), dims, strides, box, es,
-                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-                TACO_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(B, highway halves) failed: %d", (int)r);
-            }
-            static bool configured = false;
-            if (!configured) {
-                TACO_CUDA(cudaFuncSetAttribute(gemm_tc3p_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
-                TACO_CUDA(cudaFuncSetAttribute(gemm_tc3p_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
-                configured = true;
-            }
-            const unsigned ctas = (unsigned)(total < 148 ? total : 148);
-            if (highway) gemm_tc3p_kernel<1><<<ctas, 320, P_SMEM, st>>>(tmA, tmBp, a);
-            else         gemm_tc3p_kernel<0><<<ctas, 320, P_SMEM, st>>>(tmA, tmB, a);
-            TACO_LAUNCH_CHECK();
-            return 0;
-        }
-    }
     if (x3) {
         if (highway) return launch_tc<256, 2, 1, true>(tmA, tmB, a, grid, st);
         if (BN == 32) return launch_tc<32, 6, 0, true>(tmA, tmB, a, grid, st);

@@ -27,8 +27,8 @@ def _pack(ops, rt, W, taps, Cin, N):
 
 @pytest.mark.parametrize("precision", ["fp32", "tf32", "fp32x3"])
 @pytest.mark.parametrize("B,T,Cin,N", [(1, 300, 256, 1025), (2, 77, 80, 128), (3, 128, 128, 768), (1, 5, 32, 8),
-                                       (24, 1000, 128, 768), (8, 1000, 256, 1025)])   # last two: > 2 waves of tiles = the persistent fp32x3
-                                                                                      # kernel (aligned rows / 4-byte-aligned rows)
+                                       (24, 1000, 128, 768), (8, 1000, 256, 1025)])   # last two: several waves of tiles
+                                                                                      # (16-byte-aligned rows / 4-byte-aligned rows = the shifted-store epilogue)
 def test_dense(precision, B, T, Cin, N):
     rt, ops = _rt(precision)
     g = torch.Generator().manual_seed(B * 1000 + T)
@@ -44,7 +44,7 @@ def test_dense(precision, B, T, Cin, N):
 
 @pytest.mark.parametrize("precision", ["fp32", "tf32", "fp32x3"])
 @pytest.mark.parametrize("B,T,Cin,N,taps", [(2, 128, 256, 128, 3), (3, 200, 1024, 256, 3), (2, 50, 80, 128, 4), (1, 1, 128, 128, 3),
-                                          (2, 131, 128, 128, 7), (20, 1000, 256, 256, 3)])   # last: persistent kernel
+                                          (2, 131, 128, 128, 7), (20, 1000, 256, 256, 3)])   # last: several waves of tiles
 def test_conv_same_with_bn_residual(precision, B, T, Cin, N, taps):
     rt, ops = _rt(precision)
     g = torch.Generator().manual_seed(T)
@@ -64,7 +64,7 @@ def test_conv_same_with_bn_residual(precision, B, T, Cin, N, taps):
 
 @pytest.mark.parametrize("precision", ["fp32", "tf32", "fp32x3"])
 @pytest.mark.parametrize("B,T,Cin,K", [(2, 128, 128, 16), (2, 300, 80, 8), (1, 127, 80, 8), (1, 255, 128, 4), (3, 20, 80, 8),
-                                       (6, 1000, 80, 8)])           # last: persistent kernel (heaviest-filter-first tile order)
+                                       (6, 1000, 80, 8)])           # last: several waves of tiles
 def test_conv_bank_bn_pool(precision, B, T, Cin, K):
     """models/ops.py:54-71: K filters, concat, BN affine, max-pool(2,1,'same') -- one grouped call."""
     from tacotron_b200.models import ops as O2
@@ -95,7 +95,7 @@ def test_conv_bank_bn_pool(precision, B, T, Cin, K):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "tf32", "fp32x3"])
-@pytest.mark.parametrize("M", [64, 1000, 40000])          # 40000 rows: persistent kernel, half-layer (64 H + 64 T column) tiles
+@pytest.mark.parametrize("M", [64, 1000, 40000])          # 40000 rows: several waves of tiles
 def test_highway(precision, M):
     from tacotron_b200.models import ops as O2
     from tacotron_b200.params import ParamStore
@@ -114,7 +114,7 @@ def test_highway(precision, M):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "tf32", "fp32x3"])
-@pytest.mark.parametrize("B,T", [(2, 40), (40, 1000)])      # (40, 1000): persistent kernel
+@pytest.mark.parametrize("B,T", [(2, 40), (40, 1000)])      # (40, 1000): several waves of tiles
 def test_dropout_keep_mask(precision, B, T):
     rt, ops = _rt(precision)
     g = torch.Generator().manual_seed(5)

@@ -5,15 +5,21 @@
 // The caller (tacotron_b200/models/grad.py::decoder_bwd) has already recomputed, in batch, every activation of
 // every step from what the forward kernel saved (y, alignments, the three GRU state sequences), and will turn the
 // PRE-ACTIVATION gradients this kernel stores per step into all weight gradients with batched GEMMs.  What is left
-// here is the data-gradient chain, which really is serial in t (11 dependent stages per step):
+// here is the data-gradient chain, which really is serial in t.  v3: 9 dependent stages per step instead of 11 -- as in the
+// forward kernel, products of WEIGHTS are formed once per call (taco_gemm, a few hundred microseconds of work for 200 steps)
+// so that two linear stages with nothing non-linear between them become one:
 //
-//   1  [dy_att | dctx] = dattn(t) . W_a^T                         (+ pre-net L2 backward of step t+1)
-//   2  attention: dalign = dctx.values, softmax backward -> dscore, dpq = sum_j dscore_j v (1-e_j^2)
-//                                                                  (+ pre-net L1 backward of step t+1 -> dx(t+1))
-//   3  dy(t) = dy_ext + dy_att + dpq.W_q^T + [sampled] dx(t+1)
-//   4  dres = dy.W_out^T ; GRU3 element-wise part                  (ResidualWrapper: dz += dres, dh3 += dres)
+//   A   attention of step t: dalign = dctx.values, softmax backward -> dscore, dpq = sum_j dscore_j v (1-e_j^2)
+//                                        (+ pre-net L2 backward of step t+1: dpn1(t+1), and its sel-masked copy)
+//   4'  dres = E(t) + [dattn(t) | dpq(t) | sel.dpn1(t+1)] . [M1 | M2 | M4]^T ; GRU3 element-wise part
+//          E  = dy_ext . W_out^T                   (all steps at once, before the kernel)
+//          M1 = W_out . W_a[:OUT]   (dattn -> dy_att -> dres)     M2 = W_out . W_q   (dpq -> dy -> dres)
+//          M4 = W_out[:, mel(r-1)] . W1            (dpn1(t+1) -> dx(t+1) -> dy(t) -> dres; scheduled-sampling rows only)
 //   5,6 x3  GRU_i:  [dIN_c | drh] = dc_pre.Wc_i^T ;  [dIN_g | dh_g] = [dr_pre,du_pre].Wg_i^T ; carries
-//   7  [dpn2 | dattn(t-1)] = dz.W_in^T
+//   7'  [dpn2(t) | dattn(t-1) | dctx(t-1)] = dz . [W_in | Mctx]^T ,  Mctx = W_a[OUT:] . W_in[128:]  (dattn(t-1) -> dctx(t-1))
+//
+// dy(t) itself (needed only for the weight gradients) and dx are formed for all steps at once after the kernel:
+// dy = dy_ext + dattn.W_a[:OUT]^T + dpq.W_q^T + sel(t+1).dx(t+1),  dx = dpn1.W1^T.
 //
 // One cooperative kernel runs all T steps; stages are separated by grid.sync().  Every stage is a skinny GEMM
 // out[32 x N] = in[32 x K] . W^T with W rows contiguous (TF [in,out] layouts make every data-gradient a "NT"
@@ -40,9 +46,9 @@ namespace {
 constexpr int U = 256;        // decoder / attention units
 constexpr int RB = 32;        // rows (utterances) per launch
 constexpr int NW = 8;         // warps per CTA
-constexpr int MAXK = 512;
+constexpr int MAXK = 768;     // widest contraction: stage 4' (dattn | dpq | dpn1)
 constexpr int CB = 8;         // output columns processed per pass (register accumulators per lane)
-constexpr int NGEMM = 12;     // GEMMs per step (weight-row cache slots)
+constexpr int NGEMM = 9;      // GEMMs per step (weight-row cache slots)
 
 struct DecBwdP {
     int B, T, Tx, OUT, MF;
@@ -51,20 +57,26 @@ struct DecBwdP {
     const float *dy_ext, *RU[3], *C[3], *Hs[3], *align, *values, *keys, *PQ, *PN1, *PN2;
     const uint8_t* sel;
     float *DATT, *DY, *DPQ, *DSCORE, *DCTX, *DG[3], *DC[3], *DZ, *DPN2, *DPN1, *DX;
+    const float *M124, *M7, *E;   // fused weights [U][768], [640][U]; E = dy_ext . W_out^T  [T][B][U]   (workspace, see host)
     float* ws;
     unsigned int* bar;       // grid-barrier counter (zeroed by the host before the launch)
     int cache_weights;       // 1: this CTA's weight rows fit in shared memory (the normal case); 0: read them from L2
 };
 
 // scratch layout (floats): every buffer is [32][ld]
-constexpr int WS_DYATT = 0;                       // [32][512]
-constexpr int WS_DRES = WS_DYATT + RB * 512;      // [32][256]
+constexpr int WS_XC = 0;                          // [32][768] input of stage 4': dattn(t) | dpq(t) | sel.dpn1(t+1)
+constexpr int WS_DRES = WS_XC + RB * 768;         // [32][256]
 constexpr int WS_DINC = WS_DRES + RB * U;         // [32][256]
 constexpr int WS_DHR = WS_DINC + RB * U;          // [32][256]
 constexpr int WS_DHU = WS_DHR + RB * U;           // [3][32][256]
 constexpr int WS_DHC = WS_DHU + 3 * RB * U;       // [3][32][256]   carries, zeroed by the host
 constexpr int WS_BAR = WS_DHC + 3 * RB * U;       // grid-barrier counter (1 word, padded)
-constexpr int WS_TOTAL = WS_BAR + 32;
+constexpr int WS_ZERO_END = WS_BAR + 32;          // [0, WS_ZERO_END) is zeroed by the host before every launch
+constexpr int WS_M124 = WS_ZERO_END;              // [256][768]
+constexpr int WS_M7 = WS_M124 + U * 768;          // [640][256]
+constexpr int WS_E = WS_M7 + 640 * U;             // [T][B][256], T <= WS_MAXT
+constexpr int WS_MAXT = 1024;
+constexpr int WS_TOTAL = WS_E + WS_MAXT * RB * U;
 
 // One block of <= CB output columns: res[c][row] = sum_k in[row][k] * W[nb + c][k]  (row = lane), left in part_s + NW*CB*32.
 // wc: the block's weight rows [nc][K] in shared memory, or nullptr (rows are then read from global memory).
@@ -83,8 +95,8 @@ __device__ TACO_NOINLINE void gemm_block(float* part_s, const float* in, int ldi
     const int c_lo = warp * cpw, c_hi = (c_lo + cpw < K4) ? c_lo + cpw : K4;
     const float4* arow = reinterpret_cast<const float4*>(in + (int64_t)lane * ldi);
     const bool live = lane < rows;
-    // this lane's slice of its input row: up to 16 independent 16-byte L2 loads (K <= 512), all in flight before the first product
-    constexpr int MAXC = MAXK / 4 / NW;                  // 16
+    // this lane's slice of its input row: up to 24 independent 16-byte L2 loads (K <= 768), all in flight before the first product
+    constexpr int MAXC = MAXK / 4 / NW;                  // 24
     float4 av[MAXC];
 #pragma unroll
     for (int i = 0; i < MAXC; ++i)
@@ -131,12 +143,14 @@ __host__ __device__ inline void cta_columns(int N, int G, int cta, bool reverse,
     if (n0 > N) n0 = N;
 }
 
+__host__ __device__ inline int side_gemm_ctas(int G, int B) { return (G >= 2 * B) ? G - B : G; }
+
 // out[row][n] = sum_k in[row][k] * W[n][k] for this CTA's columns, then the stage epilogue per (row, column)
 template <class Epi>
 __device__ __forceinline__ void skinny_gemm(float* part_s, const float* in, int ldi, int rows, int K, const float* __restrict__ W, int ldw,
-                                            int N, bool reverse, const float* wc, Epi epi) {
+                                            int N, int geff, const float* wc, Epi epi) {
     int n0, n1;
-    cta_columns(N, (int)gridDim.x, (int)blockIdx.x, reverse, n0, n1);
+    cta_columns(N, geff, (int)blockIdx.x, false, n0, n1);    // geff < grid: only the first geff CTAs take columns
     for (int nb = n0; nb < n1; nb += CB) {               // one block on the GPU (<= 6 columns per CTA at 128 CTAs)
         const int nc = (n1 - nb < CB) ? n1 - nb : CB;
         gemm_block(part_s, in, ldi, rows, K, W, ldw, nb, nc, wc ? wc + (size_t)(nb - n0) * K : nullptr);
@@ -147,7 +161,7 @@ __device__ __forceinline__ void skinny_gemm(float* part_s, const float* in, int 
 }
 
 // Grid barrier on a monotonically increasing counter (all CTAs are co-resident: cooperative launch).  One release-add and
-// an acquire-poll per CTA: the cooperative-groups grid.sync() this replaces cost ~10 us per call here, 13 calls per step.
+// an acquire-poll per CTA: the cooperative-groups grid.sync() this replaces cost ~10 us per call here.
 struct GridBar {
     unsigned int* ctr;
     unsigned int target;
@@ -180,24 +194,26 @@ __global__ void __launch_bounds__(256, 1) decoder_bwd_kernel(const DecBwdP p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int B = p.B, T = p.T, Tx = p.Tx, OUT = p.OUT, MF = p.MF;
     const int lo = OUT - MF;
-    float* dyatt = p.ws + WS_DYATT;
+    float* xc = p.ws + WS_XC;
     float* dres = p.ws + WS_DRES;
     float* dINc = p.ws + WS_DINC;
     float* dhr = p.ws + WS_DHR;
     float* dhu = p.ws + WS_DHU;
     float* dhc = p.ws + WS_DHC;
+    (void)lo;
+    // the attention of stage A runs on the last B CTAs (one utterance each); the side GEMM of that stage goes to the others
+    const int side_ctas = side_gemm_ctas((int)gridDim.x, B);
 
-    // ---- weight-row cache: for each of the 12 GEMMs of a step, the rows of this CTA's columns, copied once ----
+    // ---- weight-row cache: for each of the 9 GEMMs of a step, the rows of this CTA's columns, copied once ----
     const float* wcp[NGEMM];
     {
-        const float* Wm[NGEMM] = {p.W_a, p.W2, p.W1, p.W_q, p.W_out, p.Wc[2], p.Wg[2], p.Wc[1], p.Wg[1], p.Wc[0], p.Wg[0], p.W_in};
-        const int Nn[NGEMM] = {OUT + U, 256, MF, OUT, U, 2 * U, 2 * U, 2 * U, 2 * U, 2 * U, 2 * U, 128 + U};
-        const int Kk[NGEMM] = {U, 128, 256, U, OUT, U, 2 * U, U, 2 * U, U, 2 * U, U};
-        const bool rev[NGEMM] = {false, true, false, false, false, false, false, false, false, false, false, false};
+        const float* Wm[NGEMM] = {p.W2, p.M124, p.Wc[2], p.Wg[2], p.Wc[1], p.Wg[1], p.Wc[0], p.Wg[0], p.M7};
+        const int Nn[NGEMM] = {256, U, 2 * U, 2 * U, 2 * U, 2 * U, 2 * U, 2 * U, 640};
+        const int Kk[NGEMM] = {128, 768, U, 2 * U, U, 2 * U, U, 2 * U, U};
         float* cur = dyn_s + NW * CB * 32 + CB * 32;
         for (int g = 0; g < NGEMM; ++g) {
             int n0, n1;
-            cta_columns(Nn[g], (int)gridDim.x, (int)blockIdx.x, rev[g], n0, n1);
+            cta_columns(Nn[g], g == 0 ? side_ctas : (int)gridDim.x, (int)blockIdx.x, false, n0, n1);
             wcp[g] = nullptr;
             if (p.cache_weights && n1 > n0) {
                 wcp[g] = cur;
@@ -224,25 +240,7 @@ __global__ void __launch_bounds__(256, 1) decoder_bwd_kernel(const DecBwdP p) {
 
     for (int t = T - 1; t >= -1; --t) {
         const int tt = t + 1;
-        // ================= stage 1: attention layer backward  |  pre-net layer 2 backward of step t+1 =================
-        if (t >= 0) {
-            const float* in = p.DATT + (int64_t)t * B * U;
-            skinny_gemm(in_s, in, U, B, U, p.W_a, U, OUT + U, false, wcp[0], [&](int row, int n, float v) {
-                if (row >= B) return;
-                if (n < OUT) dyatt[row * 512 + n] = v;
-                else p.DCTX[((int64_t)t * B + row) * U + (n - OUT)] = v;
-            });
-        }
-        if (tt < T) {
-            const float* in = p.DPN2 + (int64_t)tt * B * 128;
-            skinny_gemm(in_s, in, 128, B, 128, p.W2, 128, 256, true, wcp[1], [&](int row, int n, float v) {
-                if (row >= B) return;
-                const int64_t o = ((int64_t)tt * B + row) * 256 + n;
-                p.DPN1[o] = (__ldg(p.PN1 + o) > 0.f) ? v * p.ks : 0.f;
-            });
-        }
-        grid.sync();
-        // ================= stage 2: attention scores backward  |  pre-net layer 1 backward of step t+1 ================
+        // ================= stage A: attention scores backward of step t  |  pre-net layer 2 backward of step t+1 ==========
         if (t >= 0) {
             for (int b = (int)gridDim.x - 1 - (int)blockIdx.x; b < B; b += gridDim.x) {
                 dctx_s[tid] = __ldcg(p.DCTX + ((int64_t)t * B + b) * U + tid);
@@ -314,39 +312,32 @@ __global__ void __launch_bounds__(256, 1) decoder_bwd_kernel(const DecBwdP p) {
                         const float e = tanhf_acc(__ldg(kb + (int64_t)j * U) + pq);
                         acc = fmaf(ds_s[j], 1.0f - e * e, acc);
                     }
-                    p.DPQ[((int64_t)t * B + b) * U + d] = acc * __ldg(p.v + d);
+                    const float dpq = acc * __ldg(p.v + d);
+                    p.DPQ[((int64_t)t * B + b) * U + d] = dpq;
+                    xc[b * 768 + U + d] = dpq;
                 }
                 __syncthreads();
             }
         }
         if (tt < T) {
-            const float* in = p.DPN1 + (int64_t)tt * B * 256;
-            skinny_gemm(in_s, in, 256, B, 256, p.W1, 256, MF, false, wcp[2], [&](int row, int n, float v) {
+            const float* in = p.DPN2 + (int64_t)tt * B * 128;
+            skinny_gemm(in_s, in, 128, B, 128, p.W2, 128, 256, side_ctas, wcp[0], [&](int row, int n, float v) {
                 if (row >= B) return;
-                p.DX[((int64_t)tt * B + row) * MF + n] = v;
+                const int64_t o = ((int64_t)tt * B + row) * 256 + n;
+                const float d1 = (__ldg(p.PN1 + o) > 0.f) ? v * p.ks : 0.f;
+                p.DPN1[o] = d1;
+                xc[row * 768 + 2 * U + n] = p.sel[(int64_t)tt * B + row] ? d1 : 0.f;   // only sampled inputs pass gradient to y(t)
             });
         }
         grid.sync();
         if (t < 0) break;
-        // ================= stage 3: query layer backward, total gradient at y(t) ======================================
+        // ================= stage 4': everything that arrives at the residual output, GRU3 head ==========================
         {
-            const float* in = p.DPQ + (int64_t)t * B * U;
-            skinny_gemm(in_s, in, U, B, U, p.W_q, U, OUT, false, wcp[3], [&](int row, int n, float v) {
+            skinny_gemm(in_s, xc, 768, B, 768, p.M124, 768, U, (int)gridDim.x, wcp[1], [&](int row, int n, float v) {
                 if (row >= B) return;
-                const int64_t o = ((int64_t)t * B + row) * OUT + n;
-                float dy = __ldg(p.dy_ext + o) + __ldcg(dyatt + row * 512 + n) + v;
-                if (n >= lo && tt < T && p.sel[(int64_t)tt * B + row]) dy += __ldcg(p.DX + ((int64_t)tt * B + row) * MF + (n - lo));
-                p.DY[o] = dy;
-            });
-        }
-        grid.sync();
-        // ================= stage 4: output projection backward + GRU3 head ============================================
-        {
-            const float* in = p.DY + (int64_t)t * B * OUT;
-            skinny_gemm(in_s, in, OUT, B, OUT, p.W_out, OUT, U, false, wcp[4], [&](int row, int n, float v) {
-                if (row >= B) return;
-                dres[row * U + n] = v;
-                gru_head(2, t, row, n, v);
+                const float dr = __ldg(p.E + ((int64_t)t * B + row) * U + n) + v;
+                dres[row * U + n] = dr;
+                gru_head(2, t, row, n, dr);
             });
         }
         grid.sync();
@@ -354,7 +345,7 @@ __global__ void __launch_bounds__(256, 1) decoder_bwd_kernel(const DecBwdP p) {
         for (int i = 2; i >= 0; --i) {
             {   // [dIN_c | drh] = dc_pre . Wc_i^T
                 const float* in = p.DC[i] + (int64_t)t * B * U;
-                skinny_gemm(in_s, in, U, B, U, p.Wc[i], U, 2 * U, false, wcp[5 + 2 * (2 - i)], [&](int row, int n, float v) {
+                skinny_gemm(in_s, in, U, B, U, p.Wc[i], U, 2 * U, (int)gridDim.x, wcp[2 + 2 * (2 - i)], [&](int row, int n, float v) {
                     if (row >= B) return;
                     if (n < U) { dINc[row * U + n] = v; return; }
                     const int k = n - U;
@@ -368,7 +359,7 @@ __global__ void __launch_bounds__(256, 1) decoder_bwd_kernel(const DecBwdP p) {
             grid.sync();
             {   // [dIN_g | dh_g] = [dr_pre, du_pre] . Wg_i^T
                 const float* in = p.DG[i] + (int64_t)t * B * 2 * U;
-                skinny_gemm(in_s, in, 2 * U, B, 2 * U, p.Wg[i], 2 * U, 2 * U, false, wcp[6 + 2 * (2 - i)], [&](int row, int n, float v) {
+                skinny_gemm(in_s, in, 2 * U, B, 2 * U, p.Wg[i], 2 * U, 2 * U, (int)gridDim.x, wcp[3 + 2 * (2 - i)], [&](int row, int n, float v) {
                     if (row >= B) return;
                     if (n < U) {
                         const float dIN = __ldcg(dINc + row * U + n) + v;   // gradient at the layer input
@@ -382,20 +373,35 @@ __global__ void __launch_bounds__(256, 1) decoder_bwd_kernel(const DecBwdP p) {
             }
             grid.sync();
         }
-        // ================= stage 7: input projection backward =========================================================
+        // ================= stage 7': input projection backward, through to the attention context of step t-1 ============
         {
             const float* in = p.DZ + (int64_t)t * B * U;
-            skinny_gemm(in_s, in, U, B, U, p.W_in, U, 128 + U, false, wcp[11], [&](int row, int n, float v) {
+            skinny_gemm(in_s, in, U, B, U, p.M7, U, 640, (int)gridDim.x, wcp[8], [&](int row, int n, float v) {
                 if (row >= B) return;
                 if (n < 128) {
                     const int64_t o = ((int64_t)t * B + row) * 128 + n;
                     p.DPN2[o] = (__ldg(p.PN2 + o) > 0.f) ? v * p.ks : 0.f;
                 } else if (t > 0) {
-                    p.DATT[((int64_t)(t - 1) * B + row) * U + (n - 128)] = v;
+                    if (n < 128 + U) {
+                        p.DATT[((int64_t)(t - 1) * B + row) * U + (n - 128)] = v;
+                        xc[row * 768 + (n - 128)] = v;
+                    } else {
+                        p.DCTX[((int64_t)(t - 1) * B + row) * U + (n - 128 - U)] = v;
+                    }
                 }
             });
         }
         grid.sync();
+    }
+}
+
+// dy(t)[lo + m] += sel(t+1) * dx(t+1)[m]   (gradient of the sampled step inputs, ScheduledOutputTrainingHelper)
+__global__ void dy_tail_kernel(float* DY, const float* __restrict__ DX, const uint8_t* __restrict__ sel, int T, int B, int OUT, int MF) {
+    const int64_t total = (int64_t)(T - 1) * B * MF;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t rowi = i / MF;                     // (t, row) with t < T-1
+        const int m = (int)(i - rowi * MF);
+        if (sel[rowi + B]) DY[rowi * OUT + (OUT - MF) + m] += DX[(rowi + B) * MF + m];
     }
 }
 
@@ -427,23 +433,62 @@ extern "C" int taco_decoder_bwd(const taco_decoder_bwd_args* a, void* stream) {
     p.DPN1 = a->DPN1; p.DX = a->DX;
     p.ws = a->workspace;
     p.bar = reinterpret_cast<unsigned int*>(a->workspace + WS_BAR);
+    TACO_CHECK(a->T <= WS_MAXT, "taco_decoder_bwd: T=%d exceeds %d steps per launch", a->T, WS_MAXT);
+    const int OUTh = 80 * a->r, MF = 80, lo = OUTh - MF;
+    const int M = a->T * a->B;
+    float* M124 = a->workspace + WS_M124;
+    float* M7 = a->workspace + WS_M7;
+    float* E = a->workspace + WS_E;
+    p.M124 = M124; p.M7 = M7; p.E = E;
+    // C[M x N] (ldc) = beta*C + A[M x K] (lda) . B   (tb: B stored [N][K], else [K][N]) through the library's own GEMM
+    auto gemm = [&](float* Cm, int64_t ldc, const float* A, int64_t lda, const float* Bm, int64_t ldb, int Mm, int Nn, int Kk, int tb,
+                    float beta) {
+        taco_gemm_desc g;
+        memset(&g, 0, sizeof(g));
+        g.A = A; g.lda = lda; g.B = Bm; g.ldb = ldb; g.C = Cm; g.ldc = ldc; g.M = Mm; g.N = Nn; g.K = Kk; g.tb = tb; g.beta = beta;
+        g.taps = 1; g.batch = 1;
+        return taco_gemm(&g, stream);
+    };
+    // ---- weight-only products (once per call) and the part of dres that is known for all steps ----
+    if (gemm(M124, 768, a->W_out, OUTh, a->W_a, U, U, U, OUTh, 0, 0.f)) return 1;                           // M1 = W_out . W_a[:OUT]
+    if (gemm(M124 + U, 768, a->W_out, OUTh, a->W_q, U, U, U, OUTh, 0, 0.f)) return 1;                       // M2 = W_out . W_q
+    if (gemm(M124 + 2 * U, 768, a->W_out + lo, OUTh, a->W1, 256, U, 256, MF, 0, 0.f)) return 1;             // M4 = W_out[:, lo:] . W1
+    if (gemm(M7 + 384 * U, U, a->W_a + (int64_t)OUTh * U, U, a->W_in + 128 * U, U, U, U, U, 0, 0.f)) return 1;   // Mctx
+    if (gemm(E, U, a->dy_ext, OUTh, a->W_out, OUTh, M, U, OUTh, 1, 0.f)) return 1;                          // E = dy_ext . W_out^T
+    // after the serial kernel: dx and dy for all steps (outputs of the ABI; dy feeds the weight gradients)
+    auto tail = [&]() -> int {
+        if (gemm(a->DX, MF, a->DPN1, 256, a->W1, 256, M, MF, 256, 1, 0.f)) return 1;                        // dx = dpn1 . W1^T
+        if (gemm(a->DY, OUTh, a->DATT, U, a->W_a, U, M, OUTh, U, 1, 1.f)) return 1;                         // dy += dattn . W_a[:OUT]^T
+        if (gemm(a->DY, OUTh, a->DPQ, U, a->W_q, U, M, OUTh, U, 1, 1.f)) return 1;                          // dy += dpq . W_q^T
+        return 0;
+    };
 #ifdef TACO_HOST_EMU
     // host emulation: one CTA (the kernel is written for any grid size), grid.sync() = block barrier
-    (void)stream;
     p.cache_weights = 0;                                 // one CTA owns every column: rows come from global memory
-    memset(a->workspace, 0, (size_t)WS_TOTAL * 4);
+    memcpy(M7, a->W_in, (size_t)384 * U * 4);
+    memset(a->workspace, 0, (size_t)WS_ZERO_END * 4);
     memset(a->DATT + (int64_t)(a->T - 1) * a->B * U, 0, (size_t)a->B * U * 4);
+    memset(a->DCTX + (int64_t)(a->T - 1) * a->B * U, 0, (size_t)a->B * U * 4);
+    memcpy(a->DY, a->dy_ext, (size_t)M * OUTh * 4);
     emu::launch(dim3(1), dim3(256), [&] { decoder_bwd_kernel(p); });
+    ++g_taco_launches;
+    if (tail()) return 1;
+    {
+        float* DY = a->DY; const float* DX = a->DX; const uint8_t* sel = a->sel; const int T = a->T, B = a->B;
+        emu::launch(dim3(1), dim3(256), [&] { dy_tail_kernel(DY, DX, sel, T, B, OUTh, MF); });
+    }
     ++g_taco_launches;
     return 0;
 #else
     cudaStream_t st = (cudaStream_t)stream;
     // dynamic smem: partial sums + the weight rows of one CTA at the grid size used (128 CTAs): ceil(N/128) * K per GEMM
-    const int OUTh = 80 * a->r;
-    const int Nn[NGEMM] = {OUTh + U, 256, 80, OUTh, U, 2 * U, 2 * U, 2 * U, 2 * U, 2 * U, 2 * U, 128 + U};
-    const int Kk[NGEMM] = {U, 128, 256, U, OUTh, U, 2 * U, U, 2 * U, U, 2 * U, U};
+    const int Nn[NGEMM] = {256, U, 2 * U, 2 * U, 2 * U, 2 * U, 2 * U, 2 * U, 640};
+    const int Kk[NGEMM] = {128, 768, U, 2 * U, U, 2 * U, U, 2 * U, U};
     size_t cache_floats = 0;
-    for (int g = 0; g < NGEMM; ++g) cache_floats += (size_t)(((Nn[g] + 127) / 128) * Kk[g] + 3) & ~(size_t)3;
+    for (int g = 0; g < NGEMM; ++g) {
+        const int ctas = (g == 0) ? side_gemm_ctas(128, a->B) : 128;
+        cache_floats += (size_t)(((Nn[g] + ctas - 1) / ctas) * Kk[g] + 3) & ~(size_t)3;
+    }
     const size_t smem = ((size_t)NW * CB * 32 + CB * 32 + cache_floats) * 4;
     TACO_CHECK(smem <= 200 * 1024, "taco_decoder_bwd: weight-row cache of %zu bytes does not fit", smem);
     static int max_ctas = 0;
@@ -458,12 +503,23 @@ extern "C" int taco_decoder_bwd(const taco_decoder_bwd_args* a, void* stream) {
     }
     const int G = max_ctas < 128 ? max_ctas : 128;
     p.cache_weights = (G == 128) ? 1 : 0;                // the cache is sized for 128 CTAs
-    // carries start at zero; dattn(T-1) = 0 (the last attention state feeds nothing)
-    TACO_CUDA(cudaMemsetAsync(a->workspace, 0, (size_t)WS_TOTAL * 4, st));
+    TACO_CUDA(cudaMemcpyAsync(M7, a->W_in, (size_t)384 * U * 4, cudaMemcpyDeviceToDevice, st));
+    // carries and the stage-4' input start at zero; dattn(T-1) = dctx(T-1) = 0 (the last attention state feeds nothing)
+    TACO_CUDA(cudaMemsetAsync(a->workspace, 0, (size_t)WS_ZERO_END * 4, st));
     TACO_CUDA(cudaMemsetAsync(a->DATT + (int64_t)(a->T - 1) * a->B * U, 0, (size_t)a->B * U * 4, st));
+    TACO_CUDA(cudaMemsetAsync(a->DCTX + (int64_t)(a->T - 1) * a->B * U, 0, (size_t)a->B * U * 4, st));
+    TACO_CUDA(cudaMemcpyAsync(a->DY, a->dy_ext, (size_t)M * OUTh * 4, cudaMemcpyDeviceToDevice, st));
     void* args[] = {(void*)&p};
     TACO_CUDA(cudaLaunchCooperativeKernel((void*)decoder_bwd_kernel, dim3(G), dim3(256), args, smem, st));
     ++g_taco_launches;
+    if (tail()) return 1;
+    if (a->T > 1) {
+        const int64_t total = (int64_t)(a->T - 1) * a->B * MF;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        dy_tail_kernel<<<blocks, 256, 0, st>>>(a->DY, a->DX, a->sel, a->T, a->B, OUTh, MF);
+        TACO_LAUNCH_CHECK();
+    }
     return 0;
 #endif
 }

@@ -145,17 +145,22 @@ __host__ __device__ inline void cta_columns(int N, int G, int cta, bool reverse,
 
 __host__ __device__ inline int side_gemm_ctas(int G, int B) { return (G >= 2 * B) ? G - B : G; }
 
-// out[row][n] = sum_k in[row][k] * W[n][k] for this CTA's columns, then the stage epilogue per (row, column)
-template <class Epi>
+// out[row][n] = sum_k in[row][k] * W[n][k] for this CTA's columns, then the stage epilogue per (row, column).
+// pre(row, n) runs BEFORE the product and returns the saved activations / carries the epilogue of (row, n) needs: those L2
+// loads (~1 us) then travel together with the GEMM's input loads instead of after the reduction.
+struct Pre { float x0, x1, x2, x3, x4; };
+template <class PreF, class Epi>
 __device__ __forceinline__ void skinny_gemm(float* part_s, const float* in, int ldi, int rows, int K, const float* __restrict__ W, int ldw,
-                                            int N, int geff, const float* wc, Epi epi) {
+                                            int N, int geff, const float* wc, PreF pre, Epi epi) {
     int n0, n1;
     cta_columns(N, geff, (int)blockIdx.x, false, n0, n1);    // geff < grid: only the first geff CTAs take columns
     for (int nb = n0; nb < n1; nb += CB) {               // one block on the GPU (<= 6 columns per CTA at 128 CTAs)
         const int nc = (n1 - nb < CB) ? n1 - nb : CB;
-        gemm_block(part_s, in, ldi, rows, K, W, ldw, nb, nc, wc ? wc + (size_t)(nb - n0) * K : nullptr);
         const int tid = threadIdx.x;
-        if (tid < nc * 32) epi(tid & 31, nb + (tid >> 5), part_s[NW * CB * 32 + tid]);
+        Pre pr = {0.f, 0.f, 0.f, 0.f, 0.f};
+        if (tid < nc * 32) pr = pre(tid & 31, nb + (tid >> 5));
+        gemm_block(part_s, in, ldi, rows, K, W, ldw, nb, nc, wc ? wc + (size_t)(nb - n0) * K : nullptr);
+        if (tid < nc * 32) epi(tid & 31, nb + (tid >> 5), part_s[NW * CB * 32 + tid], pr);
         __syncthreads();                                 // part_s is reused
     }
 }
@@ -226,17 +231,24 @@ __global__ void __launch_bounds__(256, 1) decoder_bwd_kernel(const DecBwdP p) {
         __syncthreads();
     }
 
-    // element-wise head of GRU layer i at step t for (row, unit n): consumes the gradient arriving at h_i(t)
-    auto gru_head = [&](int i, int t, int row, int n, float dh_in) {
+    // element-wise head of GRU layer i at step t for (row, unit n): consumes the gradient arriving at h_i(t).
+    // head_pre loads what it needs (carry, h(t-1), u, c) ahead of the product that delivers dh_in.
+    auto head_pre = [&](int i, int t, int row, int n, Pre& q) {
         const int64_t o = (int64_t)t * B + row;
-        const float dh = dh_in + __ldcg(dhc + (i * RB + row) * U + n);
-        const float hprev = (t > 0) ? __ldg(p.Hs[i] + (o - B) * U + n) : 0.f;
-        const float u = __ldg(p.RU[i] + o * 2 * U + U + n);
-        const float c = __ldg(p.C[i] + o * U + n);
+        q.x0 = __ldcg(dhc + (i * RB + row) * U + n);
+        q.x1 = (t > 0) ? __ldg(p.Hs[i] + (o - B) * U + n) : 0.f;
+        q.x2 = __ldg(p.RU[i] + o * 2 * U + U + n);
+        q.x3 = __ldg(p.C[i] + o * U + n);
+    };
+    auto gru_head = [&](int i, int t, int row, int n, float dh_in, const Pre& q) {
+        const int64_t o = (int64_t)t * B + row;
+        const float dh = dh_in + q.x0;
+        const float hprev = q.x1, u = q.x2, c = q.x3;
         p.DG[i][o * 2 * U + U + n] = dh * (hprev - c) * u * (1.0f - u);     // du_pre
         p.DC[i][o * U + n] = dh * (1.0f - u) * (1.0f - c * c);               // dc_pre
         dhu[(i * RB + row) * U + n] = dh * u;
     };
+    const Pre pre0 = {0.f, 0.f, 0.f, 0.f, 0.f};
 
     for (int t = T - 1; t >= -1; --t) {
         const int tt = t + 1;
@@ -321,66 +333,105 @@ __global__ void __launch_bounds__(256, 1) decoder_bwd_kernel(const DecBwdP p) {
         }
         if (tt < T) {
             const float* in = p.DPN2 + (int64_t)tt * B * 128;
-            skinny_gemm(in_s, in, 128, B, 128, p.W2, 128, 256, side_ctas, wcp[0], [&](int row, int n, float v) {
-                if (row >= B) return;
-                const int64_t o = ((int64_t)tt * B + row) * 256 + n;
-                const float d1 = (__ldg(p.PN1 + o) > 0.f) ? v * p.ks : 0.f;
-                p.DPN1[o] = d1;
-                xc[row * 768 + 2 * U + n] = p.sel[(int64_t)tt * B + row] ? d1 : 0.f;   // only sampled inputs pass gradient to y(t)
-            });
+            skinny_gemm(in_s, in, 128, B, 128, p.W2, 128, 256, side_ctas, wcp[0],
+                [&](int row, int n) {
+                    Pre q = pre0;
+                    if (row < B) { q.x0 = __ldg(p.PN1 + ((int64_t)tt * B + row) * 256 + n); q.x1 = p.sel[(int64_t)tt * B + row] ? 1.f : 0.f; }
+                    return q;
+                },
+                [&](int row, int n, float v, const Pre& q) {
+                    if (row >= B) return;
+                    const float d1 = (q.x0 > 0.f) ? v * p.ks : 0.f;
+                    p.DPN1[((int64_t)tt * B + row) * 256 + n] = d1;
+                    xc[row * 768 + 2 * U + n] = (q.x1 != 0.f) ? d1 : 0.f;             // only sampled inputs pass gradient to y(t)
+                });
         }
         grid.sync();
         if (t < 0) break;
         // ================= stage 4': everything that arrives at the residual output, GRU3 head ==========================
         {
-            skinny_gemm(in_s, xc, 768, B, 768, p.M124, 768, U, (int)gridDim.x, wcp[1], [&](int row, int n, float v) {
-                if (row >= B) return;
-                const float dr = __ldg(p.E + ((int64_t)t * B + row) * U + n) + v;
-                dres[row * U + n] = dr;
-                gru_head(2, t, row, n, dr);
-            });
+            skinny_gemm(in_s, xc, 768, B, 768, p.M124, 768, U, (int)gridDim.x, wcp[1],
+                [&](int row, int n) {
+                    Pre q = pre0;
+                    if (row < B) { head_pre(2, t, row, n, q); q.x4 = __ldg(p.E + ((int64_t)t * B + row) * U + n); }
+                    return q;
+                },
+                [&](int row, int n, float v, const Pre& q) {
+                    if (row >= B) return;
+                    const float dr = q.x4 + v;
+                    dres[row * U + n] = dr;
+                    gru_head(2, t, row, n, dr, q);
+                });
         }
         grid.sync();
         // ================= stages 5/6 x 3: the GRU stack, top to bottom ===============================================
         for (int i = 2; i >= 0; --i) {
             {   // [dIN_c | drh] = dc_pre . Wc_i^T
                 const float* in = p.DC[i] + (int64_t)t * B * U;
-                skinny_gemm(in_s, in, U, B, U, p.Wc[i], U, 2 * U, (int)gridDim.x, wcp[2 + 2 * (2 - i)], [&](int row, int n, float v) {
-                    if (row >= B) return;
-                    if (n < U) { dINc[row * U + n] = v; return; }
-                    const int k = n - U;
-                    const int64_t o = (int64_t)t * B + row;
-                    const float hprev = (t > 0) ? __ldg(p.Hs[i] + (o - B) * U + k) : 0.f;
-                    const float r = __ldg(p.RU[i] + o * 2 * U + k);
-                    p.DG[i][o * 2 * U + k] = v * hprev * r * (1.0f - r);     // dr_pre
-                    dhr[row * U + k] = v * r;
-                });
+                skinny_gemm(in_s, in, U, B, U, p.Wc[i], U, 2 * U, (int)gridDim.x, wcp[2 + 2 * (2 - i)],
+                    [&](int row, int n) {
+                        Pre q = pre0;
+                        if (row < B && n >= U) {
+                            const int64_t o = (int64_t)t * B + row;
+                            q.x0 = (t > 0) ? __ldg(p.Hs[i] + (o - B) * U + (n - U)) : 0.f;
+                            q.x1 = __ldg(p.RU[i] + o * 2 * U + (n - U));
+                        }
+                        return q;
+                    },
+                    [&](int row, int n, float v, const Pre& q) {
+                        if (row >= B) return;
+                        if (n < U) { dINc[row * U + n] = v; return; }
+                        const int k = n - U;
+                        const int64_t o = (int64_t)t * B + row;
+                        const float hprev = q.x0, r = q.x1;
+                        p.DG[i][o * 2 * U + k] = v * hprev * r * (1.0f - r);     // dr_pre
+                        dhr[row * U + k] = v * r;
+                    });
             }
             grid.sync();
             {   // [dIN_g | dh_g] = [dr_pre, du_pre] . Wg_i^T
                 const float* in = p.DG[i] + (int64_t)t * B * 2 * U;
-                skinny_gemm(in_s, in, 2 * U, B, 2 * U, p.Wg[i], 2 * U, 2 * U, (int)gridDim.x, wcp[3 + 2 * (2 - i)], [&](int row, int n, float v) {
-                    if (row >= B) return;
-                    if (n < U) {
-                        const float dIN = __ldcg(dINc + row * U + n) + v;   // gradient at the layer input
-                        if (i > 0) gru_head(i - 1, t, row, n, dIN);
-                        else p.DZ[((int64_t)t * B + row) * U + n] = __ldcg(dres + row * U + n) + dIN;
-                    } else {
-                        const int k = n - U;
-                        dhc[(i * RB + row) * U + k] = __ldcg(dhu + (i * RB + row) * U + k) + __ldcg(dhr + row * U + k) + v;
-                    }
-                });
+                skinny_gemm(in_s, in, 2 * U, B, 2 * U, p.Wg[i], 2 * U, 2 * U, (int)gridDim.x, wcp[3 + 2 * (2 - i)],
+                    [&](int row, int n) {                                    // (everything here was written at least one barrier ago)
+                        Pre q = pre0;
+                        if (row >= B) return q;
+                        if (n < U) {
+                            q.x4 = __ldcg(dINc + row * U + n);
+                            if (i > 0) head_pre(i - 1, t, row, n, q);
+                            else q.x0 = __ldcg(dres + row * U + n);
+                        } else {
+                            q.x0 = __ldcg(dhu + (i * RB + row) * U + (n - U));
+                            q.x1 = __ldcg(dhr + row * U + (n - U));
+                        }
+                        return q;
+                    },
+                    [&](int row, int n, float v, const Pre& q) {
+                        if (row >= B) return;
+                        if (n < U) {
+                            const float dIN = q.x4 + v;                     // gradient at the layer input
+                            if (i > 0) gru_head(i - 1, t, row, n, dIN, q);
+                            else p.DZ[((int64_t)t * B + row) * U + n] = q.x0 + dIN;
+                        } else {
+                            dhc[(i * RB + row) * U + (n - U)] = q.x0 + q.x1 + v;
+                        }
+                    });
             }
             grid.sync();
         }
         // ================= stage 7': input projection backward, through to the attention context of step t-1 ============
         {
             const float* in = p.DZ + (int64_t)t * B * U;
-            skinny_gemm(in_s, in, U, B, U, p.M7, U, 640, (int)gridDim.x, wcp[8], [&](int row, int n, float v) {
+            skinny_gemm(in_s, in, U, B, U, p.M7, U, 640, (int)gridDim.x, wcp[8],
+                [&](int row, int n) {
+                    Pre q = pre0;
+                    if (row < B && n < 128) q.x0 = __ldg(p.PN2 + ((int64_t)t * B + row) * 128 + n);
+                    return q;
+                },
+                [&](int row, int n, float v, const Pre& q) {
                 if (row >= B) return;
                 if (n < 128) {
                     const int64_t o = ((int64_t)t * B + row) * 128 + n;
-                    p.DPN2[o] = (__ldg(p.PN2 + o) > 0.f) ? v * p.ks : 0.f;
+                    p.DPN2[o] = (q.x0 > 0.f) ? v * p.ks : 0.f;
                 } else if (t > 0) {
                     if (n < 128 + U) {
                         p.DATT[((int64_t)(t - 1) * B + row) * U + (n - 128)] = v;

@@ -50,7 +50,7 @@ def main():
     cfg = Config(r=5, vocab_size=64, precision=precision)
     # the kernel routes Tacotron.backward() selects for this precision (models/tacotron.py backward())
     K.set_gemm_impl(int(os.environ.get("TACO_GEMM_IMPL", "0" if precision == "fp32" else "1")))
-    K.DX_TC = K.DW_TC = precision != "fp32"
+    K.DX_TC = K.DW_TC = K.GEMM_TC = precision != "fp32"
     K.DX_TC_IMPL = L.IMPL_TC if precision == "tf32" else L.IMPL_TC3
     m = Tacotron(cfg, None, train=True)
     g = torch.Generator().manual_seed(0)

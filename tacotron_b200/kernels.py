@@ -66,6 +66,9 @@ def gemm(Cm, A, B, *, ta=False, tb=False, beta=0.0, shift=0, period=0, taps=1, d
         assert B.shape[0] == N and B.shape[1] * taps == K, (B.shape, N, K)
     else:
         assert B.shape == (K, N), (B.shape, K, N)
+    if (not ta) and GEMM_TC and _gemm_tc_ok(Cm, A, B, beta, period, taps, dshift, kper, batch):
+        _gemm_tc(Cm, A, B, tb, beta, shift, period)
+        return
     if ta and DW_TC and _dw_tc_ok(Cm, A, B, tb, beta, period, taps, dshift, kper, batch, a_bstride, b_bstride, c_bstride, bshift):
         # weight gradient on the tcgen05 kernel: rows of A / B are (utterance, time), batch entries are the conv taps
         T = period if period > 0 else K
@@ -105,6 +108,47 @@ def _dw_tc_ok(Cm, A, B, tb, beta, period, taps, dshift, kper, batch, a_bstride, 
         return False
     return (A.stride(0) % 4 == 0 and B.stride(0) % 4 == 0 and A.data_ptr() % 16 == 0 and B.data_ptr() % 16 == 0
             and A.stride(1) == 1 and B.stride(1) == 1 and Cm.stride(1) == 1)
+
+
+# GEMM_TC = True routes the plain products of the backward (activation recomputation y = x.W, data gradients dx = dy.W^T, with
+# the row shift / period of the recurrent layers) through the tcgen05 forward kernel: a row-shifted product is a 1-tap
+# convolution with tap offset `shift`, accumulation is the kernel's residual input.  Arithmetic = DX_TC_IMPL.
+GEMM_TC = False
+GEMM_TC_MIN_ROWS = 2048
+
+
+def _gemm_tc_ok(Cm, A, B, beta, period, taps, dshift, kper, batch):
+    M = A.shape[0]
+    if taps != 1 or dshift != 0 or kper != 0 or batch != 1 or beta not in (0.0, 1.0) or M < GEMM_TC_MIN_ROWS:
+        return False
+    if period > 0 and M % period != 0:
+        return False
+    return (A.stride(1) == 1 and A.stride(0) % 4 == 0 and A.data_ptr() % 16 == 0 and Cm.stride(1) == 1 and Cm.stride(0) % 4 == 0
+            and Cm.data_ptr() % 16 == 0 and Cm.shape[1] % 4 == 0)
+
+
+def _gemm_tc(Cm, A, B, tb, beta, shift, period):
+    M, Kc = A.shape
+    N = Cm.shape[1]
+    W = (B.t() if tb else B).contiguous()                        # TF layout [K][N] (a transpose is a small copy: <= 512 x 1024 floats)
+    ld = _cpad(Kc)
+    x3 = DX_TC_IMPL == L.IMPL_TC3
+    Wp = torch.zeros(((2 if x3 else 1) * N, ld), dtype=torch.float32, device=A.device)
+    if x3:
+        L.check(L.lib().taco_pack_weight_x3(_p(W), 1, Kc, N, _p(Wp), C.c_void_p(Wp.data_ptr() + N * ld * 4), ld, _st()), "taco_pack_weight_x3")
+    else:
+        L.check(L.lib().taco_pack_weight(_p(W), 1, Kc, N, _p(Wp), ld, _st()), "taco_pack_weight")
+    T = period if period > 0 else M
+    d = L.LinearDesc()
+    d.X = A.data_ptr(); d.ldx = A.stride(0); d.B = M // T; d.T = T; d.C = Kc
+    d.taps = 1; d.tap0 = shift; d.N = N
+    d.W = W.data_ptr(); d.Wp = Wp.data_ptr(); d.ldwp = ld
+    d.Y = Cm.data_ptr(); d.ldy = Cm.stride(0)
+    d.act = ACT_NONE; d.keep_scale = 1.0
+    if beta != 0.0:
+        d.residual = Cm.data_ptr(); d.ldr = Cm.stride(0)           # accumulate: each element is read then written by one thread
+    d.impl = DX_TC_IMPL
+    L.check(L.lib().taco_linear_fwd(C.byref(d), _st()), "taco_linear_fwd[gemm]")
 
 
 def _offset2(t, off):

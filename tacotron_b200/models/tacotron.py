@@ -285,6 +285,7 @@ class Tacotron(object):
         # weight gradients of the dense / conv layers: tcgen05 3xTF32 kernel (taco_conv_dw), same switch; Config.grad_dw_tc overrides
         dw_tc = getattr(self.config, "grad_dw_tc", None)
         prev_dw, K.DW_TC = K.DW_TC, bool(dx_tc if dw_tc is None else dw_tc)
+        prev_g, K.GEMM_TC = K.GEMM_TC, bool(dx_tc)            # recomputation / data-gradient products on the same kernel
         try:
             grad.model_bwd(K, self.store, self._gviews, S, self.config)
         finally:
@@ -292,6 +293,7 @@ class Tacotron(object):
             K.DX_TC = prev_dx
             K.DX_TC_IMPL = prev_impl
             K.DW_TC = prev_dw
+            K.GEMM_TC = prev_g
         return self._gviews
 
     def train_step(self, inputs, lr=None, **kw):

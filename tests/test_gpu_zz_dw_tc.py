@@ -89,3 +89,29 @@ def test_conv_dw_full_size_post_projection(K):
     torch.cuda.synchronize()
     err = (got.double() - ref).abs().max().item()
     assert err <= TOL * ref.abs().max().item(), (err, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("M,Kc,N,tb,beta,shift,period", [(6400, 512, 256, False, 1.0, -32, 0), (4096, 256, 128, True, 0.0, 0, 0),
+                                                         (3000, 128, 768, False, 0.0, 1, 1000), (6400, 80, 256, False, 0.0, 0, 0),
+                                                         (6400, 256, 400, True, 1.0, 0, 0), (3000, 256, 128, True, 1.0, -1, 1000)])
+def test_plain_products_on_tensor_cores(M, Kc, N, tb, beta, shift, period):
+    """kernels.GEMM_TC: y (+)= shift(x) . W and dx (+)= shift(dy) . W^T of the backward (activation recomputation and data
+    gradients, with the row shift / period of the recurrent layers) through the tcgen05 forward kernel, 3xTF32"""
+    from tacotron_b200 import kernels as Kn
+    g = torch.Generator().manual_seed(M + N)
+    A = torch.randn(M, Kc, generator=g)
+    Bm = torch.randn(N, Kc, generator=g) if tb else torch.randn(Kc, N, generator=g)
+    C0 = torch.randn(M, N, generator=g)
+    ref = C0.double().clone()
+    MK.gemm(ref, A.double(), Bm.double(), tb=tb, beta=beta, shift=shift, period=period)
+    got = C0.cuda()
+    prev, Kn.GEMM_TC = Kn.GEMM_TC, True
+    try:
+        n0 = Kn.L.lib().taco_launch_count()
+        Kn.gemm(got, A.cuda(), Bm.cuda(), tb=tb, beta=beta, shift=shift, period=period)
+        assert Kn.L.lib().taco_launch_count() - n0 == 2          # weight pack + the tensor-core kernel (not taco_gemm)
+    finally:
+        Kn.GEMM_TC = prev
+    torch.cuda.synchronize()
+    err = (got.cpu().double() - ref).abs().max().item()
+    assert err <= TOL * ref.abs().max().item(), (err, ref.abs().max().item())

@@ -74,7 +74,7 @@ def stalls(rep, idx):
     return {k: v / s for k, v in sorted(tot.items(), key=lambda x: -x[1])[:6]}
 
 
-for name in ("prof_decoder", "prof_gru", "prof_gemm"):
+for name in ("prof_decoder", "prof_gru", "prof_gemm", "prof_dw"):
     rep = os.path.join(GO, f"{tag}_{name}.ncu-rep")
     if not os.path.exists(rep):
         rep = os.path.join(GO, name + ".ncu-rep")

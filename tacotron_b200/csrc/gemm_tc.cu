@@ -974,10 +974,8 @@ int taco_linear_tc(const taco_linear_desc* d, cudaStream_t st) {
     if (x3) {
         if (highway) return launch_tc<256, 2, 1, true>(tmA, tmB, a, grid, st);
         if (BN == 32) return launch_tc<32, 6, 0, true>(tmA, tmB, a, grid, st);
-        // 2 stages x 48 KB + 256 TMEM columns per CTA: two CTAs per SM (4 loads in flight per SM, epilogue of one under the
-        // main loop of the other).  TACO_TC3_STAGES=4 (debug): one CTA per SM with a 4-deep ring.
-        static const int deep = [] { const char* e = getenv("TACO_TC3_STAGES"); return (e && atoi(e) == 4) ? 1 : 0; }();
-        if (deep) return launch_tc<128, 4, 0, true>(tmA, tmB, a, grid, st);
+        // 2 stages x 48 KB + 256 TMEM columns per CTA: two CTAs per SM (4 loads in flight per SM, the epilogue of one under the
+        // main loop of the other).  A 4-deep ring with one CTA per SM measured 2 % slower on the C2 step.
         return launch_tc<128, 2, 0, true>(tmA, tmB, a, grid, st);
     }
     if (highway) return launch_tc<256, 2, 1>(tmA, tmB, a, grid, st);

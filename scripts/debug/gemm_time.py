@@ -1,7 +1,7 @@
 """Times the post-net feed-forward contractions of C2 one by one (fp32x3), eager launches, CUDA events.
     gpurun -- python scripts/debug/gemm_time.py"""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+sys.path.insert(0, os.getcwd())
 import torch
 from tacotron_b200.models import ops
 from tacotron_b200.params import ParamStore

@@ -95,184 +95,6 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-
-// ---------------------------------------------------------------------------------------------------------------------
-// register-direct epilogue.
-// TMEM lane = output row: after tcgen05.ld a lane holds 32 consecutive columns of ITS row.  The fused epilogue runs on
-// those registers and the row segment leaves as eight 16-byte stores -- ~4 instructions per element less than the
-// transposing epilogue (which measured ~37 K warp-instructions per 128x128 tile and made every short-K contraction
-// epilogue-bound: profiles/r02_ncu_summary.md).
-// Highway (MODE 1): the tile's columns [0, BN/2) are H pre-activations of output columns oc0.., [BN/2, BN) the matching T
-// pre-activations (BN = 256: the whole layer in one tile).
-// cst: bias[256] | scale[256] | shift[256]; frow: first rows of the four quarters [4][32] (pool).
-// ---------------------------------------------------------------------------------------------------------------------
-template <int BN, int MODE>
-__device__ __forceinline__ void load_epilogue_consts(const TcArgs& a, float* cst, int et, int n0, int oc0) {
-    for (int i = et; i < BN; i += 128) {
-        if (MODE == 1) {
-            constexpr int HW = BN / 2;
-            const int src = (i < HW) ? (oc0 + i) : (a.N / 2 + oc0 + i - HW);
-            cst[i] = a.e.bias ? __ldg(a.e.bias + src) : 0.f;
-        } else {
-            const int col = n0 + i;
-            const bool cv = col < a.N;
-            cst[i] = (cv && a.e.bias) ? __ldg(a.e.bias + col) : 0.f;
-            cst[256 + i] = (cv && a.e.scale) ? __ldg(a.e.scale + col) : 1.f;
-            cst[512 + i] = (cv && a.e.shift) ? __ldg(a.e.shift + col) : 0.f;
-        }
-    }
-}
-
-// explicit shared-memory load (pointers derived from the aligned dynamic-smem base are not provably shared for the compiler:
-// it emitted generic LD.E.128 for the epilogue constants and the splitter's tile reads)
-__device__ __forceinline__ float4 lds128(const void* p) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
-    return v;
-}
-template <int CW> __device__ __forceinline__ void tc_ld_cols(uint32_t taddr, uint32_t (&v)[CW]);
-template <> __device__ __forceinline__ void tc_ld_cols<32>(uint32_t taddr, uint32_t (&v)[32]) { tc_ld_32x32b_x32(taddr, v); }
-
-// 32 consecutive outputs of one row to a 4-byte-aligned address: SH scalars, then 16-byte stores, then the remaining scalars
-template <int SH, int CW>
-__device__ __forceinline__ void store_row_shifted(float* yp, const float (&y)[CW], int cbase, int ncols) {
-#pragma unroll
-    for (int j = 0; j < SH; ++j)
-        if (cbase + j < ncols) yp[j] = y[j];
-#pragma unroll
-    for (int j = SH; j + 3 < CW; j += 4) {
-        if (cbase + j + 3 < ncols) {
-            *reinterpret_cast<float4*>(yp + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (cbase + j + k < ncols) yp[j + k] = y[j + k];
-        }
-    }
-#pragma unroll
-    for (int j = SH + ((CW - SH) / 4) * 4; j < CW; ++j)
-        if (cbase + j < ncols) yp[j] = y[j];
-}
-
-// CW = columns per pass; passes [ch0, ch1) of the tile are handled by the calling warp; bar_id = the 128-thread named barrier of
-// the four epilogue warps (pool only).  The TMEM load of pass i+1 is issued before pass i is finished and stored.
-template <int BN, int MODE, int CW>
-__device__ __forceinline__ void direct_epilogue(const TcArgs& a, const float* cst, float* frow, uint32_t acc_taddr, int q, int lane,
-                                                int b, int t0, int n0, int oc0, int ch0, int ch1, int bar_id) {
-    const int row = q * 32 + lane;
-    const int t = t0 + row;
-    const bool row_ok = (t < a.T) && (!a.pool || row < TC_BM - 1 || t == a.T - 1);
-    const int64_t grow = (int64_t)b * a.T + t;
-    constexpr int HW = BN / 2;
-    const uint32_t lane_acc = acc_taddr + ((uint32_t)(q * 32) << 16);
-    uint32_t v[CW];
-    tc_ld_cols<CW>(lane_acc + (uint32_t)(ch0 * CW), v);
-    for (int ch = ch0; ch < ch1; ++ch) {
-        float y[CW];
-        const int c0 = ch * CW;                       // column offset inside the tile
-        tc_wait_ld();
-        if (MODE == 1) {
-            uint32_t w[CW];
-            tc_ld_cols<CW>(lane_acc + (uint32_t)(HW + c0), w);
-            const float* hx = a.e.hx + grow * a.e.ldhx + oc0 + c0;
-            float4 xr[CW / 4];
-#pragma unroll
-            for (int j = 0; j < CW / 4; ++j) xr[j] = row_ok ? __ldg(reinterpret_cast<const float4*>(hx) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-            tc_wait_ld();
-#pragma unroll
-            for (int j = 0; j < CW; j += 4) {
-                const float4 bh = lds128(cst + c0 + j);
-                const float4 bt = lds128(cst + HW + c0 + j);
-                const float4 x = xr[j / 4];
-                const float xs[4] = {x.x, x.y, x.z, x.w}, bhs[4] = {bh.x, bh.y, bh.z, bh.w}, bts[4] = {bt.x, bt.y, bt.z, bt.w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float H = fmaxf(__uint_as_float(v[j + k]) + bhs[k], 0.f);
-                    const float Tg = sigmoidf_acc(__uint_as_float(w[j + k]) + bts[k]);
-                    y[j + k] = H * Tg + xs[k] * (1.0f - Tg);
-                }
-            }
-            if (ch + 1 < ch1) tc_ld_cols<CW>(lane_acc + (uint32_t)(c0 + CW), v);      // next pass travels while this one is stored
-        } else {
-            const int act = a.e.act;
-#pragma unroll
-            for (int j = 0; j < CW; j += 4) {
-                const float4 cb = lds128(cst + c0 + j);
-                const float4 sc = lds128(cst + 256 + c0 + j);
-                const float4 sh = lds128(cst + 512 + c0 + j);
-                const float cbs[4] = {cb.x, cb.y, cb.z, cb.w}, scs[4] = {sc.x, sc.y, sc.z, sc.w}, shs[4] = {sh.x, sh.y, sh.z, sh.w};
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    float u = __uint_as_float(v[j + k]) + cbs[k];
-                    u = (act == TACO_ACT_RELU) ? fmaxf(u, 0.f) : (act == TACO_ACT_NONE) ? u : apply_act(u, act);
-                    y[j + k] = fmaf(u, scs[k], shs[k]);
-                }
-            }
-            if (ch + 1 < ch1) tc_ld_cols<CW>(lane_acc + (uint32_t)(c0 + CW), v);      // next pass travels while this one is finished and stored
-            if (a.pool) {
-                // max_pooling1d(2,1,'same') over t: row t needs row t+1 = the next lane; lane 31 takes the first row of
-                // the next quarter from shared memory (tiles advance by 127 rows, so row 127 never needs a successor)
-                named_bar_sync(bar_id, 128);          // previous pass's first rows have been consumed
-                if (lane == 0) {
-#pragma unroll
-                    for (int j = 0; j < CW; j += 4) *reinterpret_cast<float4*>(frow + q * 32 + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
-                }
-                named_bar_sync(bar_id, 128);
-                const bool has_next = (t + 1 < a.T) && (row + 1 < TC_BM);
-#pragma unroll
-                for (int j = 0; j < CW; ++j) {
-                    float nx = __shfl_down_sync(0xffffffffu, y[j], 1);
-                    if (lane == 31) nx = frow[((q + 1) & 3) * 32 + j];
-                    if (has_next) y[j] = fmaxf(y[j], nx);
-                }
-            }
-            if (a.e.keep) {
-                const uint4* kp = reinterpret_cast<const uint4*>(a.e.keep + grow * (int64_t)a.e.N + n0 + c0);
-                if (row_ok) {
-#pragma unroll
-                    for (int h = 0; h < CW / 16; ++h) {
-                        const uint4 kk = kp[h];
-                        const uint32_t ks[4] = {kk.x, kk.y, kk.z, kk.w};
-#pragma unroll
-                        for (int k = 0; k < 16; ++k)
-                            y[16 * h + k] = ((ks[k >> 2] >> (8 * (k & 3))) & 0xffu) ? y[16 * h + k] * a.e.keep_scale : 0.f;
-                    }
-                }
-            }
-            if (a.e.residual && row_ok) {
-                const float* rp = a.e.residual + grow * a.e.ldr + n0 + c0;
-#pragma unroll
-                for (int j = 0; j < CW; j += 4) {
-                    if (n0 + c0 + j < a.N) {
-                        const float4 r4 = __ldg(reinterpret_cast<const float4*>(rp + j));
-                        y[j] += r4.x; y[j + 1] += r4.y; y[j + 2] += r4.z; y[j + 3] += r4.w;
-                    }
-                }
-            }
-        }
-        if (row_ok) {
-            const int cbase = (MODE == 1 ? oc0 : n0) + c0;
-            float* yp = a.e.Y + grow * a.e.ldy + cbase;
-            const int ncols = (MODE == 1) ? a.N / 2 : a.N;
-            if (MODE == 0 && a.direct == 2) {
-                // rows that are only 4-byte aligned (the [M][1025] spectrogram): 0-3 leading scalars up to the next 16-byte
-                // boundary, 16-byte stores from there, scalars for the rest.  The shift depends on the row (lane), so a warp
-                // runs up to four variants -- still far fewer instructions than transposing the tile through shared memory.
-                switch ((4 - (int)((reinterpret_cast<uintptr_t>(yp) >> 2) & 3)) & 3) {
-                    case 0:  store_row_shifted<0, CW>(yp, y, cbase, ncols); break;
-                    case 1:  store_row_shifted<1, CW>(yp, y, cbase, ncols); break;
-                    case 2:  store_row_shifted<2, CW>(yp, y, cbase, ncols); break;
-                    default: store_row_shifted<3, CW>(yp, y, cbase, ncols); break;
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < CW; j += 4)
-                    if (cbase + j < ncols) *reinterpret_cast<float4*>(yp + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
-            }
-        }
-    }
-}
-
 // MODE 0: normal epilogue (optional fused max-pool), MODE 1: highway (BN = 2U = 256)
 template <int BN, int STAGES, int MODE, bool X3>
 __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -407,13 +229,122 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
             }
         }
         if (a.direct) {
-            // ================= register-direct epilogue (direct_epilogue above) =================
+            // ================= register-direct epilogue =================
+            // TMEM lane = output row: after tcgen05.ld a lane holds 32 consecutive columns of ITS row.  The fused epilogue
+            // runs on those registers and the row segment leaves as eight 16-byte stores -- ~4 instructions per element
+            // less than the transposing epilogue below (which measured ~37 K warp-instructions per 128x128 tile and made
+            // every short-K contraction epilogue-bound: profiles/r02_ncu_summary.md).
             float* cst = reinterpret_cast<float*>(smem + L::CONST_OFFSET);
-            load_epilogue_consts<BN, MODE>(a, cst, threadIdx.x - 64, n0, 0);
+            float* frow = cst + 768;
+            const int et = threadIdx.x - 64;
+            for (int i = et; i < BN; i += 128) {
+                if (MODE == 1) {
+                    cst[i] = a.e.bias ? __ldg(a.e.bias + i) : 0.f;
+                } else {
+                    const int col = n0 + i;
+                    const bool cv = col < a.N;
+                    cst[i] = (cv && a.e.bias) ? __ldg(a.e.bias + col) : 0.f;
+                    cst[256 + i] = (cv && a.e.scale) ? __ldg(a.e.scale + col) : 1.f;
+                    cst[512 + i] = (cv && a.e.shift) ? __ldg(a.e.shift + col) : 0.f;
+                }
+            }
             named_bar_sync(1, 128);
             mbar_wait(tmem_full, 0);
             tc_fence_after();
-            direct_epilogue<BN, MODE, 32>(a, cst, cst + 768, tmem_base, q, lane, b, t0, n0, 0, 0, (MODE == 1 ? BN / 2 : BN) / 32, 1);
+            const int row = q * 32 + lane;
+            const int t = t0 + row;
+            const bool row_ok = (t < a.T) && (!a.pool || row < TC_BM - 1 || t == a.T - 1);
+            const int64_t grow = (int64_t)b * a.T + t;
+            constexpr int NCH = (MODE == 1) ? (BN / 2) / 32 : BN / 32;
+            for (int ch = 0; ch < NCH; ++ch) {
+                uint32_t v[32];
+                float y[32];
+                tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+                tc_wait_ld();
+                const int c0 = ch * 32;                       // column offset inside the tile
+                if (MODE == 1) {
+                    uint32_t w[32];
+                    tc_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(BN / 2 + ch * 32), w);
+                    tc_wait_ld();
+                    const float* hx = a.e.hx + grow * a.e.ldhx + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 bh = *reinterpret_cast<const float4*>(cst + c0 + j);
+                        const float4 bt = *reinterpret_cast<const float4*>(cst + BN / 2 + c0 + j);
+                        const float4 x = row_ok ? __ldg(reinterpret_cast<const float4*>(hx + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float xs[4] = {x.x, x.y, x.z, x.w}, bhs[4] = {bh.x, bh.y, bh.z, bh.w}, bts[4] = {bt.x, bt.y, bt.z, bt.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float H = fmaxf(__uint_as_float(v[j + k]) + bhs[k], 0.f);
+                            const float Tg = sigmoidf_acc(__uint_as_float(w[j + k]) + bts[k]);
+                            y[j + k] = H * Tg + xs[k] * (1.0f - Tg);
+                        }
+                    }
+                } else {
+                    const int act = a.e.act;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 cb = *reinterpret_cast<const float4*>(cst + c0 + j);
+                        const float4 sc = *reinterpret_cast<const float4*>(cst + 256 + c0 + j);
+                        const float4 sh = *reinterpret_cast<const float4*>(cst + 512 + c0 + j);
+                        const float cbs[4] = {cb.x, cb.y, cb.z, cb.w}, scs[4] = {sc.x, sc.y, sc.z, sc.w}, shs[4] = {sh.x, sh.y, sh.z, sh.w};
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            float u = __uint_as_float(v[j + k]) + cbs[k];
+                            u = (act == TACO_ACT_RELU) ? fmaxf(u, 0.f) : (act == TACO_ACT_NONE) ? u : apply_act(u, act);
+                            y[j + k] = fmaf(u, scs[k], shs[k]);
+                        }
+                    }
+                    if (a.pool) {
+                        // max_pooling1d(2,1,'same') over t: row t needs row t+1 = the next lane; lane 31 takes the first row of
+                        // the next quarter from shared memory (tiles advance by 127 rows, so row 127 never needs a successor)
+                        named_bar_sync(1, 128);               // previous chunk's first rows have been consumed
+                        if (lane == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(frow + q * 32 + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+                        }
+                        named_bar_sync(1, 128);
+                        const bool has_next = (t + 1 < a.T) && (row + 1 < TC_BM);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float nx = __shfl_down_sync(0xffffffffu, y[j], 1);
+                            if (lane == 31) nx = frow[((q + 1) & 3) * 32 + j];
+                            if (has_next) y[j] = fmaxf(y[j], nx);
+                        }
+                    }
+                    if (a.e.keep) {
+                        const uint4* kp = reinterpret_cast<const uint4*>(a.e.keep + grow * (int64_t)a.e.N + n0 + c0);
+                        if (row_ok) {
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                const uint4 kk = kp[h];
+                                const uint32_t ks[4] = {kk.x, kk.y, kk.z, kk.w};
+#pragma unroll
+                                for (int k = 0; k < 16; ++k)
+                                    y[16 * h + k] = ((ks[k >> 2] >> (8 * (k & 3))) & 0xffu) ? y[16 * h + k] * a.e.keep_scale : 0.f;
+                            }
+                        }
+                    }
+                    if (a.e.residual && row_ok) {
+                        const float* rp = a.e.residual + grow * a.e.ldr + n0 + c0;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (n0 + c0 + j < a.N) {
+                                const float4 r4 = __ldg(reinterpret_cast<const float4*>(rp + j));
+                                y[j] += r4.x; y[j + 1] += r4.y; y[j + 2] += r4.z; y[j + 3] += r4.w;
+                            }
+                        }
+                    }
+                }
+                if (row_ok) {
+                    float* yp = a.e.Y + grow * a.e.ldy + (MODE == 1 ? 0 : n0) + c0;
+                    const int ncols = (MODE == 1) ? BN / 2 : a.N;
+                    const int cbase = (MODE == 1 ? 0 : n0) + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        if (cbase + j < ncols) *reinterpret_cast<float4*>(yp + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+                }
+            }
             tc_fence_before();
         } else {
         mbar_wait(tmem_full, 0);
@@ -601,7 +532,6 @@ EncodeTiledFn get_encode_fn() {
     fn = reinterpret_cast<EncodeTiledFn>(p);
     return fn;
 }
-
 
 
 // =====================================================================================================================
@@ -935,8 +865,6 @@ int taco_linear_tc(const taco_linear_desc* d, cudaStream_t st) {
         if (d->hx) ok = ok && (d->ldhx % 4) == 0 && taco_aligned16(d->hx);
         if (d->keep) ok = ok && (nout % 16) == 0 && taco_aligned16(d->keep);
         a.direct = ok ? 1 : 0;
-        // rows of Y only 4-byte aligned (N = 1025): the shifted-store variant, for the plain bias/activation/affine epilogue
-        if (!ok && !highway && !d->pool && !d->keep && !d->residual) a.direct = 2;
     }
     a.lo_row0 = d->N;                                    // packed buffer = [hi rows 0..N) | lo rows N..2N)
     a.tile_stride = a.pool ? (TC_BM - 1) : TC_BM;

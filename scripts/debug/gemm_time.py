@@ -24,9 +24,10 @@ def timeit(name, fn, n=20):
     print(f"{name:28s} {e0.elapsed_time(e1) / n * 1e3:8.1f} us", flush=True)
 
 
-B, T = 32, 1000
-for name, Cin, N, taps in [("in-proj 128->768", 128, 768, 1), ("dense 256->1025", 256, 1025, 1), ("proj1 3x1024->256", 1024, 256, 3),
-                           ("proj2 3x256->80", 256, 80, 3), ("dense 128->128", 128, 128, 1)]:
+for name, B, T, Cin, N, taps in [("post in-proj 128->768", 32, 1000, 128, 768, 1), ("post dense 256->1025", 32, 1000, 256, 1025, 1),
+                                 ("post proj1 3x1024->256", 32, 1000, 1024, 256, 3), ("post proj2 3x256->80", 32, 1000, 256, 80, 3),
+                                 ("enc proj1 3x2048->128", 32, 128, 2048, 128, 3), ("enc proj2 3x128->128", 32, 128, 128, 128, 3),
+                                 ("enc in-proj 128->768", 32, 128, 128, 768, 1)]:
     x = torch.randn(B, T, Cin, generator=g).cuda()
     W = (torch.randn(taps, Cin, N, generator=g) / (taps * Cin) ** 0.5).cuda()
     b = torch.randn(N, generator=g).cuda()
